@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- the Newton-Krylov hot path of nosh on B200 (contract: see the task brief).
+
+One "step" = one pass of the hot path over one synthetic mesh (BASELINE.json configs[1]/[2]
+shape): KEO assembly (forced refill) + Jacobian rebuild + ITERS MINRES iterations, each of
+which is one fused Jacobian apply plus the fused vector/reduction kernels.
+
+  value  : Jacobian-apply throughput of the whole step, 2N*ITERS / t_step  [GDOF/s], with psi,
+           b, x resident in HBM
+  e2e    : the same step through the C ABI with pinned HOST vectors (H2D of psi and b, D2H of x
+           inside the timed region)
+  roofline: the fused Jacobian-apply kernel timed alone with CUDA events on the ctx stream,
+           algorithmic bytes / time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference: the oracle (the reference's algorithm restated in the
+           reference's Tpetra data layout; Trilinos cannot be built here) on all host cores, on
+           a bounded sample mesh of the same generator.
+
+N > 1 (torchrun): the mesh grows with N along z (weak scaling), vertex-partitioned, halo
+exchange per apply and group-sum all-reduces over NCCL.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ITERS = 200
+PARAMS = {"g": 1.0, "mu": 1.0, "theta": 0.0}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=200, help="tetgrid vertices per axis (200 -> 8.0M vertices)")
+    ap.add_argument("--layout", default=None, choices=[None, "csr", "sell32"])
+    ap.add_argument("--cpu-n", type=int, default=56, help="sample mesh of the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--apply-reps", type=int, default=50)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profiles():
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_step(n, threads, steps, warmup):
+    """The reference's algorithm (oracle, Tpetra data layout) on host cores: the same step."""
+    from oracle import OracleProblem, meshgen
+    coords, cells = meshgen.tetgrid(n)
+    P = OracleProblem(coords, cells, ("constcurl", (0.0, 0.0, 1.0), None), nthreads=threads)
+    N = P.N
+    psi = meshgen.random_state(N, 42)
+    b = meshgen.random_state(N, 43)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        P.keo_fill(PARAMS["mu"] * (1.0 + 1e-9 * s), nthreads=threads)
+        P.jac_rebuild(PARAMS["g"], psi)
+        _, it, _ = P.krylov(b, 0.0, ITERS)
+        t1 = time.perf_counter()
+        assert it == ITERS
+        if s >= warmup:
+            times.append(t1 - t0)
+    t = float(np.mean(times))
+    return {"N": N, "sec_per_step": t, "gdofs": 2.0 * N * ITERS / t / 1e9, "iters_per_s": ITERS / t}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    threads = oracle.num_threads()
+    steps = max(1, min(args.steps, 3))
+    warm = max(1, min(args.warmup, 1))
+    r = cpu_step(args.cpu_n, threads, steps, warm)
+    out = {
+        "impl": "reference",
+        "metric": "jacobian_apply_gdof_per_s", "value": r["gdofs"], "unit": "GDOF/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "minres_iters_per_s": r["iters_per_s"],
+        "config": {"workload": "tetgrid n=%d (%d vertices), const-curl B=(0,0,1), mu=1, g=1: KEO assembly + "
+                               "Jacobian rebuild + %d MINRES iterations (bounded sample of the b200 arm's "
+                               "workload; per-DOF throughput)" % (args.cpu_n, r["N"], ITERS)},
+        "cpu_baseline": {"value": r["gdofs"], "unit": "GDOF/s", "cores": threads, "kind": "port",
+                         "sample": "tetgrid n=%d, %d vertices, %d steps; oracle = reference algorithm "
+                                   "restated in Tpetra layout (Trilinos/MOAB not buildable offline)"
+                                   % (args.cpu_n, r["N"], steps)},
+        "e2e": {"value": r["gdofs"], "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import nosh_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # a real (non-default) torch stream, shared with the library, so that torch CUDA events
+    # bracket exactly the work the library enqueues
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    layout = {None: None, "csr": nosh_b200.LAYOUT_CSR, "sell32": nosh_b200.LAYOUT_SELL32}[args.layout]
+    ctx = nosh_b200.Context(device=local, stream=stream, layout=layout)
+    if world > 1:
+        obj = [nosh_b200.Context.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        ctx.comm_init(obj[0], rank, world)
+
+    n = args.n
+    nz = n * world  # weak scaling: the brick grows along z with the number of GPUs
+    t_setup = time.perf_counter()
+    mi = ctx.mesh_tetgrid(n, n, nz, lo=(-5.0, -5.0, -5.0 * world), hi=(5.0, 5.0, 5.0 * world))
+    ctx.set_thickness(None, 1.0)
+    ctx.set_potential_constant(-1.0)
+    ctx.set_mvp_constcurl((0.0, 0.0, 1.0))
+    ctx.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    No, Nglob = int(mi.n_owned), int(mi.n_global)
+
+    # synthetic state resident in HBM (random phases), generated on the device
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(42 + rank)
+    ang = torch.rand(No, generator=gen, device="cuda", dtype=torch.float64) * (2 * np.pi)
+    rho = 0.5 + 0.5 * torch.rand(No, generator=gen, device="cuda", dtype=torch.float64)
+    psi_d = torch.stack([rho * torch.cos(ang), rho * torch.sin(ang)], 1).reshape(-1).contiguous()
+    b_d = torch.randn(2 * No, generator=gen, device="cuda", dtype=torch.float64)
+    x_d = torch.empty_like(b_d)
+    psi_h = psi_d.cpu().pin_memory()
+    b_h = b_d.cpu().pin_memory()
+    x_h = torch.empty_like(b_h).pin_memory()
+
+    def step(psi, b, x, k):
+        par = dict(PARAMS)
+        par["mu"] = PARAMS["mu"] * (1.0 + 1e-9 * k)  # a new mu every step: a real refill
+        ctx.keo_fill(par)
+        ctx.jac_rebuild(par, psi)
+        _, res = ctx.minres(b, x, tol=0.0, maxit=ITERS)
+        return res
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(psi, b, x, steps, warmup):
+        for k in range(warmup):
+            step(psi, b, x, k)
+        barrier()
+        l0 = ctx.launch_count()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            res = step(psi, b, x, warmup + k)
+            assert res.iterations == ITERS, res.iterations
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, ctx.launch_count() - l0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_step, launches = timed(psi_d, b_d, x_d, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(psi_h, b_h, x_h, max(1, min(args.steps, 3)), 1)
+
+    # ---- the dominant kernel alone: fused Jacobian apply, CUDA events on the ctx stream --------
+    reps = args.apply_reps
+    par = dict(PARAMS)
+    ctx.jac_rebuild(par, psi_d)
+    for _ in range(3):
+        ctx.jac_apply(b_d, x_d)
+    barrier()
+    ctx.timer_start()
+    for _ in range(reps):
+        ctx.jac_apply(b_d, x_d)
+    ms_apply = ctx.timer_stop() / reps
+    # KEO assembly alone
+    for k in range(2):
+        par["mu"] = 1.0 + 1e-7 * (k + 1)
+        ctx.keo_fill(par)
+    barrier()
+    ctx.timer_start()
+    for k in range(10):
+        par["mu"] = 1.0 + 1e-6 * (k + 1)
+        ctx.keo_fill(par)
+    ms_fill = ctx.timer_stop() / 10
+    if world > 1:
+        t = torch.tensor([ms_apply, ms_fill], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_apply, ms_fill = float(t[0]), float(t[1])
+
+    nb = int(mi.n_blocks)
+    bytes_apply = nb * 20 + (No + 1) * 8 + No * (16 + 16 + 24)   # SURVEY.md 8(d), per launch per GPU
+    peak, peak_src = measured_peak()
+    achieved = bytes_apply / (ms_apply * 1e-3) / 1e9
+    traffic = traffic_from_profiles()
+
+    if rank == 0:
+        out = {
+            "metric": "jacobian_apply_gdof_per_s",
+            "value": 2.0 * Nglob * ITERS / (ms_step * 1e-3) / 1e9,
+            "unit": "GDOF/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "tetgrid %dx%dx%d = %d vertices (%d per GPU), 6 Kuhn tets/hex, jitter 0.2, "
+                            "const-curl B=(0,0,1), mu=1, g=1, V=-1, t=1: KEO assembly + Jacobian rebuild + "
+                            "%d MINRES iterations per step" % (n, n, nz, Nglob, No, ITERS),
+                "layout": "sell32" if mi.n_stored != mi.n_blocks or args.layout == "sell32" else "csr",
+                "l2": "inputs larger than L2 (matrix %.0f MB per GPU)" % (nb * 20 / 1e6),
+                "setup_s": t_setup,
+            },
+            "minres_iters_per_s": ITERS / (ms_step * 1e-3),
+            "jacobian_apply_alone_gdof_per_s": 2.0 * Nglob / (ms_apply * 1e-3) / 1e9,
+            "keo_assembly_ms": ms_fill,
+            "keo_assembly_gedges_per_s": int(mi.n_edges) / (ms_fill * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "k_apply_* <EPI_DIAG> (fused Jacobian apply)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "bytes_per_launch": bytes_apply,
+                         "ms_per_launch": ms_apply,
+                         "traffic": (traffic or {}).get("jacobian_apply_dram_bytes_per_launch")},
+            "e2e": {"value": 2.0 * Nglob * ITERS / (ms_e2e * 1e-3) / 1e9, "unit": "GDOF/s",
+                    "h2d_bytes_per_step": 2 * 16 * No * world, "d2h_bytes_per_step": 16 * No * world,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            import oracle
+            th = oracle.num_threads()
+            r = cpu_step(args.cpu_n, th, 1, 1)
+            out["cpu_baseline"] = {
+                "value": r["gdofs"], "unit": "GDOF/s", "cores": th, "kind": "port",
+                "sample": "tetgrid n=%d (%d vertices), 1 step of the same workload after 1 warm-up; "
+                          "oracle = reference algorithm restated in Tpetra layout" % (args.cpu_n, r["N"])}
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,254 @@
+/* =============================================================================
+ * nosh_b200.h -- C ABI of the B200-native Newton-Krylov hot path of nschloe/nosh.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * Every entry point names the reference interface (file:line under the
+ * reference tree) it replaces.  The C++ mirror of the reference's classes
+ * (nosh::parameter_matrix::keo, nosh::jacobian_operator,
+ * nosh::model_evaluator::nls, ...) lives in nosh_b200/hostcpp/nosh/ and is a thin
+ * forwarder to these functions; INTEGRATION.md shows the binding a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *  - One nosh_ctx per process per GPU.  Not thread-safe per ctx; safe across ctxs.
+ *  - Every function returns a nosh_status; nosh_last_error(ctx) gives the message.
+ *    Nothing throws across this boundary.
+ *  - State vectors are interleaved (re,im) doubles, entry 2k/2k+1 for the k-th
+ *    OWNED vertex (reference: src/mesh.cpp:595-606, src/jacobian_operator.cpp:95-100);
+ *    multi-vectors are column-major with an explicit leading dimension.
+ *  - Vector arguments may be HOST or DEVICE pointers (detected with
+ *    cudaPointerGetAttributes).  Host vectors are staged through the ctx's
+ *    device buffers (H2D / D2H inside the call); device vectors are used in place.
+ *  - Per-vertex field arrays given at set-up are HOST arrays in LOCAL numbering:
+ *    owned vertices first, then ghosts (nosh_mesh_local_gids).  On one GPU
+ *    local == global.
+ *  - Model parameters are passed as (names[], values[], n), the C image of the
+ *    reference's std::map<std::string,double>; a missing name yields NOSH_EKEY
+ *    (the reference's params.at() throws std::out_of_range).
+ *  - All arithmetic is IEEE fp64; indices are int32, as in
+ *    Tpetra::CrsMatrix<double,int,int> (src/jacobian_operator.hpp:26).
+ *  - There is NO CPU fallback: every compute entry point runs sm_100a kernels.
+ * ============================================================================= */
+#ifndef NOSH_B200_H
+#define NOSH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NOSH_API __attribute__((visibility("default")))
+#else
+#define NOSH_API
+#endif
+
+typedef struct nosh_ctx nosh_ctx;
+
+typedef enum {
+  NOSH_OK = 0,
+  NOSH_EINVAL = 1,       /* bad argument (incl. unsupported mode/alpha/beta of apply) */
+  NOSH_ECUDA = 2,        /* CUDA runtime failure */
+  NOSH_ESTATE = 3,       /* call sequence error (e.g. apply before fill) */
+  NOSH_EMESH = 4,        /* illegal mesh (flat tetrahedron, degenerate cell) */
+  NOSH_EKEY = 5,         /* parameter name missing (std::out_of_range in the reference) */
+  NOSH_ECOMM = 6,        /* NCCL failure */
+  NOSH_EUNSUPPORTED = 7  /* out of scope (e.g. the MueLu V-cycle) */
+} nosh_status;
+
+/* Teuchos::ETransp of Tpetra::Operator::apply */
+typedef enum { NOSH_NO_TRANS = 0, NOSH_TRANS = 1, NOSH_CONJ_TRANS = 2 } nosh_transp;
+
+/* storage layout of the complex block matrix in HBM */
+typedef enum { NOSH_LAYOUT_CSR = 0, NOSH_LAYOUT_SELL32 = 1 } nosh_layout;
+
+/* which matrix nosh_get_block_csr exports */
+typedef enum { NOSH_MAT_KEO = 0, NOSH_MAT_DKEO = 1 } nosh_matrix_id;
+
+/* linear operator selector for the Krylov solvers */
+typedef enum { NOSH_OP_JACOBIAN = 0, NOSH_OP_KEO = 1, NOSH_OP_KEOREG = 2 } nosh_operator_id;
+
+/* ---- lifecycle ------------------------------------------------------------- */
+NOSH_API const char *nosh_version(void);
+/* stream: a cudaStream_t (as void*) all work is enqueued on, or NULL for a
+ * ctx-owned stream. */
+NOSH_API nosh_status nosh_ctx_create(int device, void *stream, nosh_ctx **out);
+NOSH_API void nosh_ctx_destroy(nosh_ctx *ctx);
+NOSH_API const char *nosh_last_error(const nosh_ctx *ctx);
+/* options must be set before the mesh: layout (default SELL32, env NOSH_B200_LAYOUT
+ * =csr|sell32) and the reduction/partition granularity in vertices (multiple of 512,
+ * default 65536, env NOSH_B200_GROUP). */
+NOSH_API nosh_status nosh_ctx_set_layout(nosh_ctx *ctx, nosh_layout layout);
+NOSH_API nosh_status nosh_ctx_set_group_vertices(nosh_ctx *ctx, int64_t group_vertices);
+NOSH_API nosh_status nosh_ctx_synchronize(nosh_ctx *ctx);
+
+/* ---- multi-GPU (one process per GPU).  Replaces Teuchos::MpiComm / Tpetra
+ * Import / reduceAll (src/mesh_reader.cpp:53-57; Tpetra, not in tree). ---------- */
+NOSH_API nosh_status nosh_comm_unique_id(void *id128 /* 128 bytes out */);
+NOSH_API nosh_status nosh_ctx_comm_init(nosh_ctx *ctx, const void *id128, int rank, int nranks);
+
+/* ---- mesh (a1-a3).  Replaces nosh::read + mesh_tetra/mesh_tri ctor:
+ * src/mesh_reader.cpp:19-162, src/mesh.cpp:18-51,629-691, src/mesh_tetra.cpp:14-35,
+ * 41-271, src/mesh_tri.cpp:44-210.  Builds, on the device: the unique edge list,
+ * cell->edge relation, edge lengths and FVM edge coefficients ("covolume"),
+ * circumcentric control volumes and the block-CSR graph (src/mesh.cpp:787-881).
+ * With nranks > 1 every rank passes the same GLOBAL mesh and keeps the part it
+ * owns (contiguous vertex ranges) plus a one-cell halo. */
+NOSH_API nosh_status nosh_mesh_set(nosh_ctx *ctx, int dim, int64_t n_vertices,
+                                   const double *coords /* host, n_vertices x 3 */,
+                                   int64_t n_cells,
+                                   const int32_t *cells /* host, n_cells x (dim+1) */);
+/* Synthetic input of SURVEY.md 8(d): nx*ny*nz structured vertices on [lo,hi], x fastest,
+ * 6 Kuhn tetrahedra per hex cell, interior vertices displaced by jitter*h*U(-1,1)
+ * (splitmix64 keyed on seed and the global vertex id).  Generated on the device, each
+ * rank its own part. */
+NOSH_API nosh_status nosh_mesh_tetgrid(nosh_ctx *ctx, int nx, int ny, int nz, const double lo[3],
+                                       const double hi[3], double jitter, uint64_t seed);
+
+typedef struct {
+  int32_t dim;
+  int64_t n_global;    /* vertices of the whole mesh */
+  int64_t owned_begin; /* first global vertex id owned by this ctx */
+  int64_t n_owned;     /* rows / vector length 2*n_owned */
+  int64_t n_ghost;
+  int64_t n_cells;     /* local cells (touching an owned vertex) */
+  int64_t n_edges;     /* local edges (>= 1 owned endpoint) */
+  int64_t n_blocks;    /* complex blocks in the owned rows (CSR count, no padding) */
+  int64_t n_stored;    /* stored complex blocks incl. layout padding */
+} nosh_mesh_info_t;
+NOSH_API nosh_status nosh_mesh_info(const nosh_ctx *ctx, nosh_mesh_info_t *info);
+/* parity accessors (host outputs; any may be NULL) */
+NOSH_API nosh_status nosh_mesh_local_gids(nosh_ctx *ctx, int64_t *gids /* n_owned+n_ghost */);
+NOSH_API nosh_status nosh_mesh_get_coords(nosh_ctx *ctx, double *coords /* (n_owned+n_ghost) x 3 */);
+NOSH_API nosh_status nosh_mesh_get_cells(nosh_ctx *ctx, int32_t *cells /* n_cells x (dim+1), local ids */);
+NOSH_API nosh_status nosh_mesh_get_edges(nosh_ctx *ctx, int32_t *edges /* n_edges x 2 local ids */,
+                                         double *length, double *covolume);
+NOSH_API nosh_status nosh_mesh_get_control_volumes(nosh_ctx *ctx, double *cv /* n_owned */);
+
+/* ---- fields (a5-a8) ---------------------------------------------------------- */
+/* scalar_field::constant(mesh, c) as thickness (src/scalar_field_constant.cpp:43-58), or
+ * explicit per-vertex values (values != NULL, local numbering). */
+NOSH_API nosh_status nosh_set_thickness(nosh_ctx *ctx, const double *values, double c);
+/* scalar_field::constant(mesh, c, param1_name, .) as the scalar potential:
+ * V = c (+ params[param1_name] if present), dV/dp = 1 for its own name
+ * (src/scalar_field_constant.cpp:43-75).  param1_name may be NULL/"". */
+NOSH_API nosh_status nosh_set_potential_constant(nosh_ctx *ctx, double c, const char *param1_name);
+/* scalar_field::explicit_values: V = params["beta"] * values, dV/dbeta = values
+ * (src/scalar_field_explicit_values.cpp:33-62). */
+NOSH_API nosh_status nosh_set_potential_values(nosh_ctx *ctx, const double *values);
+/* vector_field::explicit_values(mesh, "A", mu): cache_e = 0.5(A_v0+A_v1).(x_v0-x_v1),
+ * a_e = mu*cache_e (src/vector_field_explicit_values.cpp:13-90).  A: local n x 3. */
+NOSH_API nosh_status nosh_set_mvp_explicit(nosh_ctx *ctx, const double *A);
+/* same, with A = 0.5 B x X evaluated on the device from the vertex coordinates
+ * (examples/state-equippers/plain-gl:22-39) -- no host array needed at scale. */
+NOSH_API nosh_status nosh_set_mvp_explicit_curl(nosh_ctx *ctx, const double B[3]);
+/* vector_field::constantCurl(mesh, b, u): a_e = mu * R_theta(b) . (0.5 x_v1 x x_v0)
+ * (src/vector_field_constant_curl.cpp:74-227; edge cache restated).
+ * u may be NULL.  b and u must be exactly normalised (:35-44) else NOSH_EINVAL. */
+NOSH_API nosh_status nosh_set_mvp_constcurl(nosh_ctx *ctx, const double b[3], const double u[3]);
+/* parity accessors */
+NOSH_API nosh_status nosh_get_alpha_cache(nosh_ctx *ctx, double *alpha /* n_edges */);
+NOSH_API nosh_status nosh_get_edge_projection(nosh_ctx *ctx, int np, const char *const *names,
+                                              const double *values, const char *dname /* or NULL */,
+                                              double *a /* n_edges */, double *da /* or NULL */);
+
+/* ---- KEO (a9, a10).  parameter_matrix::keo::set_parameters -> refill_
+ * (src/parameter_object.cpp:6-47, src/parameter_matrix_keo.cpp:74-184) and
+ * DkeoDP::refill_ (src/parameter_matrix_dkeo_dp.cpp:60-155).  Needs "mu" (and "theta"
+ * for constantCurl). */
+NOSH_API nosh_status nosh_keo_fill(nosh_ctx *ctx, int np, const char *const *names,
+                                   const double *values);
+NOSH_API nosh_status nosh_dkeo_fill(nosh_ctx *ctx, int np, const char *const *names,
+                                    const double *values, const char *dname);
+/* Tpetra::CrsMatrix::apply of the KEO / dKEO (call sites src/model_evaluator_nls.cpp:537,641,
+ * test/keo.cpp:79-80): Y = alpha*op(A)*X + beta*Y.  A is Hermitian as a complex matrix,
+ * i.e. symmetric in the real layout, so TRANS == NO_TRANS; all alpha/beta supported. */
+NOSH_API nosh_status nosh_matrix_apply(nosh_ctx *ctx, nosh_matrix_id which, const double *X,
+                                       int64_t ldx, double *Y, int64_t ldy, int nvec,
+                                       nosh_transp mode, double alpha, double beta);
+/* block-CSR export for entry-wise parity: rowptr n_owned+1 (int64), cols n_blocks (local
+ * ids, ascending global id within a row), vals n_blocks complex (re,im). */
+NOSH_API nosh_status nosh_get_block_csr(nosh_ctx *ctx, nosh_matrix_id which, int64_t *rowptr,
+                                        int32_t *cols, double *vals);
+
+/* ---- Jacobian (a11, a12).  jacobian_operator::rebuild / apply
+ * (src/jacobian_operator.cpp:38-199).  rebuild needs "g" + KEO params.  apply supports
+ * only NO_TRANS, alpha == 1, beta == 0 -- anything else is NOSH_EINVAL (:48-59 throw). */
+NOSH_API nosh_status nosh_jac_rebuild(nosh_ctx *ctx, int np, const char *const *names,
+                                      const double *values, const double *psi);
+NOSH_API nosh_status nosh_jac_apply(nosh_ctx *ctx, const double *X, int64_t ldx, double *Y,
+                                    int64_t ldy, int nvec, nosh_transp mode, double alpha,
+                                    double beta);
+NOSH_API nosh_status nosh_jac_get_diags(nosh_ctx *ctx, double *d0 /* 2n */, double *d1b /* n */);
+
+/* ---- model evaluator (a13, a14).  nls::compute_f_ / computeDFDP_
+ * (src/model_evaluator_nls.cpp:527-695).  Both refill the (d)KEO first, as the
+ * reference does; an unchanged parameter set is detected and the refill skipped
+ * (the cache the reference meant to have, src/parameter_object.cpp:17-44). */
+NOSH_API nosh_status nosh_compute_f(nosh_ctx *ctx, int np, const char *const *names,
+                                    const double *values, const double *psi, double *f);
+NOSH_API nosh_status nosh_compute_dfdp(nosh_ctx *ctx, int np, const char *const *names,
+                                       const double *values, const char *pname, const double *psi,
+                                       double *dfdp);
+
+/* ---- preconditioner matrix (a16).  keo_regularized::rebuild
+ * (src/keo_regularized.cpp:181-264): P = K + blockdiag([[al+ga, be],[be, al-ga]]), g > 0
+ * only.  nosh_keoreg_matrix_apply applies P (not its inverse).  The inverse (one MueLu
+ * V-cycle, :106-108) is third-party AMG: nosh_keoreg_apply returns NOSH_EUNSUPPORTED. */
+NOSH_API nosh_status nosh_keoreg_rebuild(nosh_ctx *ctx, int np, const char *const *names,
+                                         const double *values, const double *psi);
+NOSH_API nosh_status nosh_keoreg_matrix_apply(nosh_ctx *ctx, const double *X, int64_t ldx,
+                                              double *Y, int64_t ldy, int nvec);
+NOSH_API nosh_status nosh_keoreg_get_diags(nosh_ctx *ctx, double *d0 /* 2n */, double *d1b /* n */);
+NOSH_API nosh_status nosh_keoreg_apply(nosh_ctx *ctx, const double *X, int64_t ldx, double *Y,
+                                       int64_t ldy, int nvec, nosh_transp mode, double alpha,
+                                       double beta);
+
+/* ---- vector reductions (Tpetra::MultiVector::dot / norm2; partition independent) */
+NOSH_API nosh_status nosh_dot(nosh_ctx *ctx, const double *x, const double *y, double *result);
+NOSH_API nosh_status nosh_norm2(nosh_ctx *ctx, const double *x, double *result);
+
+/* ---- Krylov (a18).  Belos::MinresSolMgr / PseudoBlockCGSolMgr as selected at
+ * src/model_evaluator_nls.cpp:280-291 and examples/conf.xml:104-123: unpreconditioned,
+ * x0 = 0, implicit relative residual <= tol, at most maxit iterations.
+ * hist (or NULL): maxit+1 doubles, relative residual estimate after each iteration. */
+typedef struct {
+  int32_t iterations;
+  int32_t converged;
+  double relres; /* final implicit relative residual */
+} nosh_krylov_result;
+NOSH_API nosh_status nosh_minres(nosh_ctx *ctx, nosh_operator_id op, const double *b, double *x,
+                                 double tol, int maxit, nosh_krylov_result *res, double *hist);
+NOSH_API nosh_status nosh_cg(nosh_ctx *ctx, nosh_operator_id op, const double *b, double *x,
+                             double tol, int maxit, nosh_krylov_result *res, double *hist);
+
+/* ---- Newton.  NOX "Line Search Based"/"Full Step" with a NormF test as configured in
+ * examples/conf.xml:76-191, driving evalModel(f), evalModel(W_op) and the MINRES solve
+ * (call stack SURVEY.md 3.4).  psi: in = initial guess, out = solution.
+ * lin_iters: nl_maxit ints; fnorms: nl_maxit+1 doubles (either may be NULL). */
+typedef struct {
+  int32_t steps;
+  int32_t converged;
+  int32_t total_linear_iterations;
+  double fnorm;
+} nosh_newton_result;
+NOSH_API nosh_status nosh_newton(nosh_ctx *ctx, int np, const char *const *names,
+                                 const double *values, double *psi, double nl_tol, int nl_maxit,
+                                 double lin_tol, int lin_maxit, nosh_newton_result *res,
+                                 int32_t *lin_iters, double *fnorms);
+
+/* ---- measurement helpers: device-resident scratch vectors so that benchmarks can
+ * time kernels with inputs already in HBM.  slot in [0,8). Returns a device pointer to
+ * 2*(n_owned+n_ghost) doubles owned by the ctx. */
+NOSH_API nosh_status nosh_scratch_vector(nosh_ctx *ctx, int slot, double **dev_ptr);
+/* number of kernels this library has launched on ctx so far */
+NOSH_API int64_t nosh_launch_count(const nosh_ctx *ctx);
+/* CUDA-event timing on the ctx stream */
+NOSH_API nosh_status nosh_timer_start(nosh_ctx *ctx);
+NOSH_API nosh_status nosh_timer_stop(nosh_ctx *ctx, float *milliseconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOSH_B200_H */

@@ -1,0 +1,122 @@
+"""ctypes binding of libnosh_b200.so (the C ABI of include/nosh_b200.h).
+
+There is no fallback: if the CUDA library is missing the import of this module raises,
+and nosh_ctx_create fails (NOSH_ECUDA) on a machine without a GPU.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libnosh_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "nosh_b200.h")
+
+NOSH_OK, NOSH_EINVAL, NOSH_ECUDA, NOSH_ESTATE, NOSH_EMESH, NOSH_EKEY, NOSH_ECOMM, NOSH_EUNSUPPORTED = range(8)
+NO_TRANS, TRANS, CONJ_TRANS = 0, 1, 2
+LAYOUT_CSR, LAYOUT_SELL32 = 0, 1
+MAT_KEO, MAT_DKEO = 0, 1
+OP_JACOBIAN, OP_KEO, OP_KEOREG = 0, 1, 2
+
+
+class MeshInfo(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("n_global", C.c_int64), ("owned_begin", C.c_int64),
+                ("n_owned", C.c_int64), ("n_ghost", C.c_int64), ("n_cells", C.c_int64),
+                ("n_edges", C.c_int64), ("n_blocks", C.c_int64), ("n_stored", C.c_int64)]
+
+
+class KrylovResult(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("relres", C.c_double)]
+
+
+class NewtonResult(C.Structure):
+    _fields_ = [("steps", C.c_int32), ("converged", C.c_int32),
+                ("total_linear_iterations", C.c_int32), ("fnorm", C.c_double)]
+
+
+def build(force=False):
+    """Compile the library in-tree with nvcc for sm_100a (nosh_b200/csrc/Makefile)."""
+    args = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    if force:
+        args.append("-B")
+    subprocess.check_call(args, stdout=subprocess.DEVNULL)
+    return SO_PATH
+
+
+def declared_symbols():
+    """Every NOSH_API function name declared in include/nosh_b200.h."""
+    txt = open(HEADER_PATH).read()
+    return sorted(set(re.findall(r"NOSH_API\s+[\w\s\*]+?\b(nosh_\w+)\s*\(", txt)))
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(
+            "nosh_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a). There is no CPU fallback." % SO_PATH)
+    L = C.CDLL(SO_PATH)
+    vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+    cpp = C.POINTER(C.c_char_p)
+    sig = {
+        "nosh_version": (C.c_char_p, []),
+        "nosh_ctx_create": (C.c_int, [C.c_int, vp, C.POINTER(vp)]),
+        "nosh_ctx_destroy": (None, [vp]),
+        "nosh_last_error": (C.c_char_p, [vp]),
+        "nosh_ctx_set_layout": (C.c_int, [vp, C.c_int]),
+        "nosh_ctx_set_group_vertices": (C.c_int, [vp, i64]),
+        "nosh_ctx_synchronize": (C.c_int, [vp]),
+        "nosh_comm_unique_id": (C.c_int, [vp]),
+        "nosh_ctx_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "nosh_mesh_set": (C.c_int, [vp, C.c_int, i64, vp, i64, vp]),
+        "nosh_mesh_tetgrid": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, dbl, C.c_uint64]),
+        "nosh_mesh_info": (C.c_int, [vp, C.POINTER(MeshInfo)]),
+        "nosh_mesh_local_gids": (C.c_int, [vp, vp]),
+        "nosh_mesh_get_coords": (C.c_int, [vp, vp]),
+        "nosh_mesh_get_cells": (C.c_int, [vp, vp]),
+        "nosh_mesh_get_edges": (C.c_int, [vp, vp, vp, vp]),
+        "nosh_mesh_get_control_volumes": (C.c_int, [vp, vp]),
+        "nosh_set_thickness": (C.c_int, [vp, vp, dbl]),
+        "nosh_set_potential_constant": (C.c_int, [vp, dbl, C.c_char_p]),
+        "nosh_set_potential_values": (C.c_int, [vp, vp]),
+        "nosh_set_mvp_explicit": (C.c_int, [vp, vp]),
+        "nosh_set_mvp_explicit_curl": (C.c_int, [vp, vp]),
+        "nosh_set_mvp_constcurl": (C.c_int, [vp, vp, vp]),
+        "nosh_get_alpha_cache": (C.c_int, [vp, vp]),
+        "nosh_get_edge_projection": (C.c_int, [vp, C.c_int, cpp, vp, C.c_char_p, vp, vp]),
+        "nosh_keo_fill": (C.c_int, [vp, C.c_int, cpp, vp]),
+        "nosh_dkeo_fill": (C.c_int, [vp, C.c_int, cpp, vp, C.c_char_p]),
+        "nosh_matrix_apply": (C.c_int, [vp, C.c_int, vp, i64, vp, i64, C.c_int, C.c_int, dbl, dbl]),
+        "nosh_get_block_csr": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+        "nosh_jac_rebuild": (C.c_int, [vp, C.c_int, cpp, vp, vp]),
+        "nosh_jac_apply": (C.c_int, [vp, vp, i64, vp, i64, C.c_int, C.c_int, dbl, dbl]),
+        "nosh_jac_get_diags": (C.c_int, [vp, vp, vp]),
+        "nosh_compute_f": (C.c_int, [vp, C.c_int, cpp, vp, vp, vp]),
+        "nosh_compute_dfdp": (C.c_int, [vp, C.c_int, cpp, vp, C.c_char_p, vp, vp]),
+        "nosh_keoreg_rebuild": (C.c_int, [vp, C.c_int, cpp, vp, vp]),
+        "nosh_keoreg_matrix_apply": (C.c_int, [vp, vp, i64, vp, i64, C.c_int]),
+        "nosh_keoreg_get_diags": (C.c_int, [vp, vp, vp]),
+        "nosh_keoreg_apply": (C.c_int, [vp, vp, i64, vp, i64, C.c_int, C.c_int, dbl, dbl]),
+        "nosh_dot": (C.c_int, [vp, vp, vp, C.POINTER(dbl)]),
+        "nosh_norm2": (C.c_int, [vp, vp, C.POINTER(dbl)]),
+        "nosh_minres": (C.c_int, [vp, C.c_int, vp, vp, dbl, C.c_int, C.POINTER(KrylovResult), vp]),
+        "nosh_cg": (C.c_int, [vp, C.c_int, vp, vp, dbl, C.c_int, C.POINTER(KrylovResult), vp]),
+        "nosh_newton": (C.c_int, [vp, C.c_int, cpp, vp, vp, dbl, C.c_int, dbl, C.c_int,
+                                  C.POINTER(NewtonResult), vp, vp]),
+        "nosh_scratch_vector": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+        "nosh_launch_count": (i64, [vp]),
+        "nosh_timer_start": (C.c_int, [vp]),
+        "nosh_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    L._nosh_signatures = sig
+    _lib = L
+    return L

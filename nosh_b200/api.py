@@ -1,0 +1,343 @@
+"""Python front-end over the C ABI, used by the tests, bench.py and as a usage example.
+
+Vectors may be numpy arrays (host: staged H2D/D2H inside every call) or anything with a
+CUDA ``data_ptr()`` (torch tensors: used in place).  Parameters are plain dicts, the image
+of the reference's std::map<std::string,double>.
+
+Error mapping (reference behaviour in parentheses):
+  NOSH_EKEY   -> KeyError      (std::map::at -> std::out_of_range)
+  NOSH_EINVAL -> ValueError    (TEUCHOS_TEST_FOR_EXCEPT_MSG -> std::logic_error)
+  NOSH_EMESH  -> RuntimeError  ("Illegal mesh: tetrahedron too flat")
+  others      -> RuntimeError
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (LAYOUT_CSR, LAYOUT_SELL32, MAT_DKEO, MAT_KEO, NO_TRANS, OP_JACOBIAN, OP_KEO,  # noqa: F401
+                   OP_KEOREG, KrylovResult, MeshInfo, NewtonResult)
+
+
+class NoshError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    raise TypeError(type(a))
+
+
+def _params(p):
+    names = (C.c_char_p * len(p))(*[k.encode() for k in p])
+    vals = np.array([float(v) for v in p.values()], np.float64)
+    return len(p), names, vals
+
+
+class Context:
+    """One nosh_ctx: one process, one GPU."""
+
+    def __init__(self, device=0, stream=None, layout=None, group_vertices=None):
+        self.L = _lib.lib()
+        h = C.c_void_p()
+        rc = self.L.nosh_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise NoshError("nosh_ctx_create failed with status %d (no usable CUDA device? there is "
+                            "no CPU fallback)" % rc)
+        self.h = h
+        if layout is not None:
+            self._ck(self.L.nosh_ctx_set_layout(self.h, int(layout)))
+        if group_vertices is not None:
+            self._ck(self.L.nosh_ctx_set_group_vertices(self.h, int(group_vertices)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.nosh_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc == 0:
+            return
+        msg = self.L.nosh_last_error(self.h).decode()
+        if rc == _lib.NOSH_EKEY:
+            raise KeyError(msg)
+        if rc == _lib.NOSH_EINVAL:
+            raise ValueError(msg)
+        raise NoshError("status %d: %s" % (rc, msg))
+
+    # ---- comm -------------------------------------------------------------------------
+    @staticmethod
+    def unique_id():
+        buf = (C.c_char * 128)()
+        rc = _lib.lib().nosh_comm_unique_id(buf)
+        if rc != 0:
+            raise NoshError("nosh_comm_unique_id failed (%d)" % rc)
+        return bytes(buf)
+
+    def comm_init(self, uid, rank, nranks):
+        b = (C.c_char * 128).from_buffer_copy(uid)
+        self._ck(self.L.nosh_ctx_comm_init(self.h, b, int(rank), int(nranks)))
+
+    def synchronize(self):
+        self._ck(self.L.nosh_ctx_synchronize(self.h))
+
+    # ---- mesh -------------------------------------------------------------------------
+    def mesh_set(self, coords, cells):
+        coords = np.ascontiguousarray(coords, np.float64)
+        cells = np.ascontiguousarray(cells, np.int32)
+        self._ck(self.L.nosh_mesh_set(self.h, cells.shape[1] - 1, coords.shape[0], _ptr(coords),
+                                      cells.shape[0], _ptr(cells)))
+        return self.info()
+
+    def mesh_tetgrid(self, nx, ny=None, nz=None, lo=(-5.0, -5.0, -5.0), hi=(5.0, 5.0, 5.0),
+                     jitter=0.2, seed=1234):
+        ny = nx if ny is None else ny
+        nz = nx if nz is None else nz
+        lo = np.array(lo, np.float64)
+        hi = np.array(hi, np.float64)
+        self._ck(self.L.nosh_mesh_tetgrid(self.h, nx, ny, nz, _ptr(lo), _ptr(hi), float(jitter),
+                                          int(seed)))
+        return self.info()
+
+    def info(self):
+        mi = MeshInfo()
+        self._ck(self.L.nosh_mesh_info(self.h, C.byref(mi)))
+        self._info = mi
+        return mi
+
+    @property
+    def n_owned(self):
+        return int(self._info.n_owned)
+
+    def local_gids(self):
+        mi = self._info
+        g = np.empty(mi.n_owned + mi.n_ghost, np.int64)
+        self._ck(self.L.nosh_mesh_local_gids(self.h, _ptr(g)))
+        return g
+
+    def coords(self):
+        mi = self._info
+        c = np.empty((mi.n_owned + mi.n_ghost, 3))
+        self._ck(self.L.nosh_mesh_get_coords(self.h, _ptr(c)))
+        return c
+
+    def cells(self):
+        mi = self._info
+        c = np.empty((mi.n_cells, mi.dim + 1), np.int32)
+        self._ck(self.L.nosh_mesh_get_cells(self.h, _ptr(c)))
+        return c
+
+    def edges(self):
+        mi = self._info
+        e = np.empty((mi.n_edges, 2), np.int32)
+        ln = np.empty(mi.n_edges)
+        cov = np.empty(mi.n_edges)
+        self._ck(self.L.nosh_mesh_get_edges(self.h, _ptr(e), _ptr(ln), _ptr(cov)))
+        return e, ln, cov
+
+    def control_volumes(self):
+        cv = np.empty(self._info.n_owned)
+        self._ck(self.L.nosh_mesh_get_control_volumes(self.h, _ptr(cv)))
+        return cv
+
+    # ---- fields -----------------------------------------------------------------------
+    def set_thickness(self, values=None, c=1.0):
+        v = None if values is None else np.ascontiguousarray(values, np.float64)
+        self._ck(self.L.nosh_set_thickness(self.h, _ptr(v), float(c)))
+
+    def set_potential_constant(self, c, param1_name=None):
+        self._ck(self.L.nosh_set_potential_constant(self.h, float(c),
+                                                    param1_name.encode() if param1_name else None))
+
+    def set_potential_values(self, values):
+        v = np.ascontiguousarray(values, np.float64)
+        self._ck(self.L.nosh_set_potential_values(self.h, _ptr(v)))
+
+    def set_mvp_explicit(self, A):
+        A = np.ascontiguousarray(A, np.float64)
+        self._ck(self.L.nosh_set_mvp_explicit(self.h, _ptr(A)))
+
+    def set_mvp_explicit_curl(self, B):
+        B = np.array(B, np.float64)
+        self._ck(self.L.nosh_set_mvp_explicit_curl(self.h, _ptr(B)))
+
+    def set_mvp_constcurl(self, b, u=None):
+        b = np.array(b, np.float64)
+        u = None if u is None else np.array(u, np.float64)
+        self._ck(self.L.nosh_set_mvp_constcurl(self.h, _ptr(b), _ptr(u)))
+
+    def alpha_cache(self):
+        a = np.empty(self._info.n_edges)
+        self._ck(self.L.nosh_get_alpha_cache(self.h, _ptr(a)))
+        return a
+
+    def edge_projection(self, params, dname=None):
+        n, names, vals = _params(params)
+        a = np.empty(self._info.n_edges)
+        da = np.empty(self._info.n_edges) if dname else None
+        self._ck(self.L.nosh_get_edge_projection(self.h, n, names, _ptr(vals),
+                                                 dname.encode() if dname else None, _ptr(a), _ptr(da)))
+        return a, da
+
+    # ---- operators --------------------------------------------------------------------
+    def keo_fill(self, params):
+        n, names, vals = _params(params)
+        self._ck(self.L.nosh_keo_fill(self.h, n, names, _ptr(vals)))
+
+    def dkeo_fill(self, params, dname):
+        n, names, vals = _params(params)
+        self._ck(self.L.nosh_dkeo_fill(self.h, n, names, _ptr(vals), dname.encode()))
+
+    def _out_like(self, x):
+        if isinstance(x, np.ndarray):
+            return np.empty_like(x)
+        import torch
+        return torch.empty_like(x)
+
+    @staticmethod
+    def _shape(X, n2):
+        if isinstance(X, np.ndarray):
+            nvec = 1 if X.ndim == 1 else X.shape[0]
+        else:
+            nvec = 1 if X.dim() == 1 else X.shape[0]
+        return nvec, n2
+
+    def matrix_apply(self, which, X, Y=None, mode=NO_TRANS, alpha=1.0, beta=0.0):
+        """Rows of a 2-D X are the columns of the (column-major) multi-vector."""
+        Y = self._out_like(X) if Y is None else Y
+        nvec, ld = self._shape(X, 2 * self.n_owned)
+        self._ck(self.L.nosh_matrix_apply(self.h, which, _ptr(X), ld, _ptr(Y), ld, nvec, mode,
+                                          float(alpha), float(beta)))
+        return Y
+
+    def keo_apply(self, X, Y=None, **kw):
+        return self.matrix_apply(MAT_KEO, X, Y, **kw)
+
+    def dkeo_apply(self, X, Y=None, **kw):
+        return self.matrix_apply(MAT_DKEO, X, Y, **kw)
+
+    def block_csr(self, which=MAT_KEO, values=True):
+        mi = self._info
+        rp = np.empty(mi.n_owned + 1, np.int64)
+        cols = np.empty(mi.n_blocks, np.int32)
+        vals = np.empty(mi.n_blocks, np.complex128) if values else None
+        self._ck(self.L.nosh_get_block_csr(self.h, which, _ptr(rp), _ptr(cols), _ptr(vals)))
+        return rp, cols, vals
+
+    def jac_rebuild(self, params, psi):
+        n, names, vals = _params(params)
+        self._ck(self.L.nosh_jac_rebuild(self.h, n, names, _ptr(vals), _ptr(psi)))
+
+    def jac_apply(self, X, Y=None, mode=NO_TRANS, alpha=1.0, beta=0.0):
+        Y = self._out_like(X) if Y is None else Y
+        nvec, ld = self._shape(X, 2 * self.n_owned)
+        self._ck(self.L.nosh_jac_apply(self.h, _ptr(X), ld, _ptr(Y), ld, nvec, mode, float(alpha),
+                                       float(beta)))
+        return Y
+
+    def jac_diags(self):
+        d0 = np.empty(2 * self.n_owned)
+        d1 = np.empty(self.n_owned)
+        self._ck(self.L.nosh_jac_get_diags(self.h, _ptr(d0), _ptr(d1)))
+        return d0, d1
+
+    def compute_f(self, params, psi, f=None):
+        f = self._out_like(psi) if f is None else f
+        n, names, vals = _params(params)
+        self._ck(self.L.nosh_compute_f(self.h, n, names, _ptr(vals), _ptr(psi), _ptr(f)))
+        return f
+
+    def compute_dfdp(self, params, pname, psi, out=None):
+        out = self._out_like(psi) if out is None else out
+        n, names, vals = _params(params)
+        self._ck(self.L.nosh_compute_dfdp(self.h, n, names, _ptr(vals), pname.encode(), _ptr(psi),
+                                          _ptr(out)))
+        return out
+
+    def keoreg_rebuild(self, params, psi):
+        n, names, vals = _params(params)
+        self._ck(self.L.nosh_keoreg_rebuild(self.h, n, names, _ptr(vals), _ptr(psi)))
+
+    def keoreg_matrix_apply(self, X, Y=None):
+        Y = self._out_like(X) if Y is None else Y
+        nvec, ld = self._shape(X, 2 * self.n_owned)
+        self._ck(self.L.nosh_keoreg_matrix_apply(self.h, _ptr(X), ld, _ptr(Y), ld, nvec))
+        return Y
+
+    def keoreg_diags(self):
+        d0 = np.empty(2 * self.n_owned)
+        d1 = np.empty(self.n_owned)
+        self._ck(self.L.nosh_keoreg_get_diags(self.h, _ptr(d0), _ptr(d1)))
+        return d0, d1
+
+    def keoreg_apply(self, X, Y=None):
+        Y = self._out_like(X) if Y is None else Y
+        self._ck(self.L.nosh_keoreg_apply(self.h, _ptr(X), 0, _ptr(Y), 0, 1, NO_TRANS, 1.0, 0.0))
+        return Y
+
+    # ---- reductions / solvers -----------------------------------------------------------
+    def dot(self, x, y):
+        r = C.c_double()
+        self._ck(self.L.nosh_dot(self.h, _ptr(x), _ptr(y), C.byref(r)))
+        return r.value
+
+    def norm2(self, x):
+        r = C.c_double()
+        self._ck(self.L.nosh_norm2(self.h, _ptr(x), C.byref(r)))
+        return r.value
+
+    def _krylov(self, fn, op, b, x, tol, maxit, history):
+        x = self._out_like(b) if x is None else x
+        res = KrylovResult()
+        hist = np.full(maxit + 1, np.nan) if history else None
+        self._ck(fn(self.h, op, _ptr(b), _ptr(x), float(tol), int(maxit), C.byref(res), _ptr(hist)))
+        if history:
+            return x, res, hist[:res.iterations + 1]
+        return x, res
+
+    def minres(self, b, x=None, op=OP_JACOBIAN, tol=1e-10, maxit=1000, history=False):
+        return self._krylov(self.L.nosh_minres, op, b, x, tol, maxit, history)
+
+    def cg(self, b, x=None, op=OP_JACOBIAN, tol=1e-10, maxit=1000, history=False):
+        return self._krylov(self.L.nosh_cg, op, b, x, tol, maxit, history)
+
+    def newton(self, params, psi, nl_tol=1e-8, nl_maxit=20, lin_tol=1e-10, lin_maxit=1000):
+        """psi is updated in place.  Returns (result, lin_iters, fnorms)."""
+        n, names, vals = _params(params)
+        res = NewtonResult()
+        lin = np.zeros(max(nl_maxit, 1), np.int32)
+        fn = np.full(nl_maxit + 1, np.nan)
+        self._ck(self.L.nosh_newton(self.h, n, names, _ptr(vals), _ptr(psi), float(nl_tol),
+                                    int(nl_maxit), float(lin_tol), int(lin_maxit), C.byref(res),
+                                    _ptr(lin), _ptr(fn)))
+        return res, lin[:res.steps].copy(), fn[:res.steps + 1].copy()
+
+    # ---- measurement ------------------------------------------------------------------
+    def scratch_vector(self, slot):
+        p = C.c_void_p()
+        self._ck(self.L.nosh_scratch_vector(self.h, int(slot), C.byref(p)))
+        return p.value
+
+    def launch_count(self):
+        return int(self.L.nosh_launch_count(self.h))
+
+    def timer_start(self):
+        self._ck(self.L.nosh_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self.L.nosh_timer_stop(self.h, C.byref(ms)))
+        return ms.value

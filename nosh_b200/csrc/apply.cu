@@ -1,0 +1,230 @@
+// apply.cu -- see apply.cuh
+#include "apply.cuh"
+
+namespace nosh {
+
+namespace {
+
+template <int EPI>
+__device__ __forceinline__ double2 epilogue(double2 acc, double2 xi, int64_t i, const ApplyArgs &A) {
+  if (EPI == EPI_DIAG) {
+    const double2 d0 = ld_stream2(A.d0 + i);
+    const double d1 = __ldg(A.d1 + i);
+    acc.x += d0.x * xi.x + d1 * xi.y;
+    acc.y += d1 * xi.x + d0.y * xi.y;
+  } else if (EPI == EPI_F) {
+    const double al = A.cv[i] * A.thick[i] * (A.V[i] + A.g * (xi.x * xi.x + xi.y * xi.y));
+    acc.x += al * xi.x;
+    acc.y += al * xi.y;
+  } else if (EPI == EPI_DG) {
+    const double al = A.cv[i] * A.thick[i] * (xi.x * xi.x + xi.y * xi.y);
+    acc.x += al * xi.x;
+    acc.y += al * xi.y;
+  } else if (EPI == EPI_DV) {
+    const double al = A.cv[i] * A.thick[i] * A.V[i];
+    acc.x += al * xi.x;
+    acc.y += al * xi.y;
+  }
+  return acc;
+}
+
+// complex multiply-accumulate  acc += v * x
+__device__ __forceinline__ void cfma(double2 &acc, double2 v, double2 x) {
+  acc.x += v.x * x.x - v.y * x.y;
+  acc.y += v.x * x.y + v.y * x.x;
+}
+
+template <int FUSE>
+__device__ __forceinline__ bool krylov_skip(const ApplyArgs &A) {
+  if (FUSE == FUSE_MINRES || FUSE == FUSE_CG) {
+    // device-side control flow: after convergence the remaining launches are no-ops
+    return A.st->done || A.st->iter != A.host_iter - 1;
+  }
+  return false;
+}
+
+// -------------------------------------------------------------------------------------------
+// SELL-32, one thread per row, one CTA per CHUNK (=512) rows = 16 slices.
+// -------------------------------------------------------------------------------------------
+template <int EPI, int FUSE, int U>
+__global__ void __launch_bounds__(CHUNK, 2) k_apply_sell(const ApplyArgs A) {
+  if (krylov_skip<FUSE>(A)) return;
+  __shared__ double red[CHUNK / 32];
+  const int64_t row = (int64_t)blockIdx.x * CHUNK + threadIdx.x;
+  const int64_t slice = row >> 5;
+  const int lane = threadIdx.x & 31;
+  const double scale = (FUSE == FUSE_MINRES) ? A.st->inv_beta : 1.0;
+  double2 acc = make_double2(0.0, 0.0);
+  if (slice < A.nslices) {
+    int p = __ldg(A.slice_off + slice) + lane;
+    const int pend = __ldg(A.slice_off + slice + 1);
+    // U independent (column, value) loads, then U gathers, then the FMAs
+    for (; p + 32 * (U - 1) < pend; p += 32 * U) {
+      int c[U];
+      double2 v[U], xv[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) c[u] = ld_stream_i32(A.col + p + 32 * u);
+#pragma unroll
+      for (int u = 0; u < U; u++) v[u] = ld_stream2(A.val + p + 32 * u);
+#pragma unroll
+      for (int u = 0; u < U; u++) xv[u] = __ldg(A.x + c[u]);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (FUSE == FUSE_MINRES) {
+          xv[u].x *= scale;
+          xv[u].y *= scale;
+        }
+        cfma(acc, v[u], xv[u]);
+      }
+    }
+    for (; p < pend; p += 32) {
+      const int c = ld_stream_i32(A.col + p);
+      const double2 v = ld_stream2(A.val + p);
+      double2 xv = __ldg(A.x + c);
+      if (FUSE == FUSE_MINRES) {
+        xv.x *= scale;
+        xv.y *= scale;
+      }
+      cfma(acc, v, xv);
+    }
+  }
+  double contrib = 0.0;
+  if (row < A.No) {
+    double2 xi = __ldg(A.x + row);
+    if (FUSE == FUSE_MINRES) {
+      xi.x *= scale;
+      xi.y *= scale;
+    }
+    double2 yi = epilogue<EPI>(acc, xi, row, A);
+    if (FUSE == FUSE_AXPBY) {
+      yi.x *= A.a;
+      yi.y *= A.a;
+      if (A.b != 0.0) {
+        const double2 yo = A.y[row];
+        yi.x += A.b * yo.x;
+        yi.y += A.b * yo.y;
+      }
+    } else if (FUSE == FUSE_MINRES) {
+      const double f = A.st->f_r1;
+      if (f != 0.0) {
+        const double2 r1 = ld_stream2(A.r1 + row);
+        yi.x -= f * r1.x;
+        yi.y -= f * r1.y;
+      }
+      contrib = xi.x * yi.x + xi.y * yi.y;
+    } else if (FUSE == FUSE_CG) {
+      contrib = xi.x * yi.x + xi.y * yi.y;
+    }
+    A.y[row] = yi;
+  }
+  if (FUSE == FUSE_MINRES || FUSE == FUSE_CG) {
+    const double s = block_sum<CHUNK / 32>(contrib, red);
+    if (threadIdx.x == 0) A.partials[blockIdx.x] = s;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// block-CSR, LPR lanes per row, one CTA per CHUNK rows.
+// -------------------------------------------------------------------------------------------
+template <int EPI, int FUSE, int LPR>
+__global__ void __launch_bounds__(CHUNK, 2) k_apply_csr(const ApplyArgs A) {
+  if (krylov_skip<FUSE>(A)) return;
+  __shared__ double red[CHUNK / 32];
+  constexpr int RPP = CHUNK / LPR;  // rows per pass
+  const int sub = threadIdx.x / LPR, sl = threadIdx.x % LPR;
+  const double scale = (FUSE == FUSE_MINRES) ? A.st->inv_beta : 1.0;
+  double contrib = 0.0;
+#pragma unroll 2
+  for (int pass = 0; pass < LPR; pass++) {
+    const int64_t row = (int64_t)blockIdx.x * CHUNK + pass * RPP + sub;
+    double2 acc = make_double2(0.0, 0.0);
+    if (row < A.No) {
+      const int b = __ldg(A.rowptr + row), e = __ldg(A.rowptr + row + 1);
+      for (int p = b + sl; p < e; p += LPR) {
+        const int c = ld_stream_i32(A.col + p);
+        const double2 v = ld_stream2(A.val + p);
+        double2 xv = __ldg(A.x + c);
+        if (FUSE == FUSE_MINRES) {
+          xv.x *= scale;
+          xv.y *= scale;
+        }
+        cfma(acc, v, xv);
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    }
+    if (sl == 0 && row < A.No) {
+      double2 xi = __ldg(A.x + row);
+      if (FUSE == FUSE_MINRES) {
+        xi.x *= scale;
+        xi.y *= scale;
+      }
+      double2 yi = epilogue<EPI>(acc, xi, row, A);
+      if (FUSE == FUSE_AXPBY) {
+        yi.x *= A.a;
+        yi.y *= A.a;
+        if (A.b != 0.0) {
+          const double2 yo = A.y[row];
+          yi.x += A.b * yo.x;
+          yi.y += A.b * yo.y;
+        }
+      } else if (FUSE == FUSE_MINRES) {
+        const double f = A.st->f_r1;
+        if (f != 0.0) {
+          const double2 r1 = ld_stream2(A.r1 + row);
+          yi.x -= f * r1.x;
+          yi.y -= f * r1.y;
+        }
+        contrib += xi.x * yi.x + xi.y * yi.y;
+      } else if (FUSE == FUSE_CG) {
+        contrib += xi.x * yi.x + xi.y * yi.y;
+      }
+      A.y[row] = yi;
+    }
+  }
+  if (FUSE == FUSE_MINRES || FUSE == FUSE_CG) {
+    const double s = block_sum<CHUNK / 32>(contrib, red);
+    if (threadIdx.x == 0) A.partials[blockIdx.x] = s;
+  }
+}
+
+template <int EPI, int FUSE>
+void launch2(Ctx *ctx, const ApplyArgs &A) {
+  const unsigned grid = (unsigned)cdiv(A.No, CHUNK);
+  if (grid == 0) return;
+  if (ctx->layout == NOSH_LAYOUT_SELL32)
+    k_apply_sell<EPI, FUSE, 4><<<grid, CHUNK, 0, ctx->stream>>>(A);
+  else
+    k_apply_csr<EPI, FUSE, 8><<<grid, CHUNK, 0, ctx->stream>>>(A);
+  ctx->launches++;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+template <int EPI>
+void launch1(Ctx *ctx, int fuse, const ApplyArgs &A) {
+  switch (fuse) {
+    case FUSE_NONE: launch2<EPI, FUSE_NONE>(ctx, A); break;
+    case FUSE_AXPBY: launch2<EPI, FUSE_AXPBY>(ctx, A); break;
+    case FUSE_MINRES: launch2<EPI, FUSE_MINRES>(ctx, A); break;
+    case FUSE_CG: launch2<EPI, FUSE_CG>(ctx, A); break;
+    default: NOSH_THROW(NOSH_EINVAL, "bad fuse mode");
+  }
+}
+
+}  // namespace
+
+void launch_apply(Ctx *ctx, int epi, int fuse, const ApplyArgs &A) {
+  switch (epi) {
+    case EPI_NONE: launch1<EPI_NONE>(ctx, fuse, A); break;
+    case EPI_DIAG: launch1<EPI_DIAG>(ctx, fuse, A); break;
+    case EPI_F: launch2<EPI_F, FUSE_NONE>(ctx, A); break;
+    case EPI_DG: launch2<EPI_DG, FUSE_NONE>(ctx, A); break;
+    case EPI_DV: launch2<EPI_DV, FUSE_NONE>(ctx, A); break;
+    default: NOSH_THROW(NOSH_EINVAL, "bad epilogue");
+  }
+}
+
+}  // namespace nosh

@@ -1,0 +1,654 @@
+// capi.cu -- the extern "C" boundary declared in include/nosh_b200.h.
+// Thin: argument checks, host<->device staging, status codes.  Never throws.
+#include <cstdlib>
+
+#include "apply.cuh"
+#include "comm.h"
+#include "keo.h"
+#include "krylov.h"
+#include "mesh.h"
+
+struct nosh_ctx : public nosh::Ctx {};
+
+using namespace nosh;
+
+namespace {
+
+#define API_BEGIN(ctx)            \
+  if (!(ctx)) return NOSH_EINVAL; \
+  try {
+#define API_END(ctx)                        \
+  }                                         \
+  catch (const nosh::Exception &e) {        \
+    (ctx)->err = e.msg;                     \
+    return e.code;                          \
+  }                                         \
+  catch (const std::exception &e) {         \
+    (ctx)->err = e.what();                  \
+    return NOSH_EINVAL;                     \
+  }                                         \
+  return NOSH_OK;
+
+bool is_device_ptr(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+void require_mesh(Ctx *ctx) {
+  if (!ctx->has_mesh) NOSH_THROW(NOSH_ESTATE, "no mesh set");
+}
+
+// input vector of 2*No doubles -> device pointer with room for ghosts when needed
+double2 *stage_in(Ctx *ctx, const double *p, DBuf<double2> &buf, bool need_ghost_room) {
+  if (!p) NOSH_THROW(NOSH_EINVAL, "NULL vector");
+  const bool dev = is_device_ptr(p);
+  if (dev && !need_ghost_room) return (double2 *)p;
+  buf.ensure(ctx->Nl > 0 ? ctx->Nl : 1);
+  CUDA_CHECK(cudaMemcpyAsync(buf.p, p, sizeof(double2) * ctx->No, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                             ctx->stream));
+  return buf.p;
+}
+struct OutVec {
+  double2 *dev;
+  double *user;
+  bool host;
+};
+OutVec stage_out(Ctx *ctx, double *p, DBuf<double2> &buf) {
+  if (!p) NOSH_THROW(NOSH_EINVAL, "NULL vector");
+  OutVec o;
+  o.user = p;
+  o.host = !is_device_ptr(p);
+  if (o.host) {
+    buf.ensure(ctx->Nl > 0 ? ctx->Nl : 1);
+    o.dev = buf.p;
+  } else {
+    o.dev = (double2 *)p;
+  }
+  return o;
+}
+void finish_out(Ctx *ctx, const OutVec &o) {
+  if (o.host) {
+    CUDA_CHECK(cudaMemcpyAsync(o.user, o.dev, sizeof(double2) * ctx->No, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+}
+template <typename T>
+void d2h(Ctx *ctx, T *host, const T *dev, size_t n) {
+  if (!host || n == 0) return;
+  CUDA_CHECK(cudaMemcpyAsync(host, dev, sizeof(T) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+__global__ void k_gather_vals(const int32_t *pos, const double2 *val, int64_t n, double2 *out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = val[pos[i]];
+}
+__global__ void k_widen(const int32_t *in, int64_t n, int64_t *out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+void after_mesh(Ctx *ctx) {
+  halo_setup(ctx);
+  ensure_work(ctx);
+  ctx->thick_set = false;
+  ctx->mvp_kind = MVP_NONE;
+  ctx->alpha_ok = ctx->keo_filled = ctx->dkeo_filled = ctx->jac_ok = ctx->keoreg_ok = false;
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+void check_apply_shape(Ctx *ctx, int64_t ldx, int64_t ldy, int nvec) {
+  if (nvec < 1) NOSH_THROW(NOSH_EINVAL, "nvec < 1");
+  if (nvec > 1 && (ldx < 2 * ctx->No || ldy < 2 * ctx->No)) NOSH_THROW(NOSH_EINVAL, "leading dimension too small");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *nosh_version(void) { return "nosh_b200 0.1 (sm_100a)"; }
+
+nosh_status nosh_ctx_create(int device, void *stream, nosh_ctx **out) {
+  if (!out) return NOSH_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return NOSH_ECUDA;  // no CPU fallback
+  if (device < 0 || device >= ndev) return NOSH_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return NOSH_ECUDA;
+  nosh_ctx *ctx = new nosh_ctx;
+  ctx->device = device;
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete ctx;
+      return NOSH_ECUDA;
+    }
+    ctx->own_stream = true;
+  }
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  if (const char *e = getenv("NOSH_B200_LAYOUT")) {
+    if (strcmp(e, "csr") == 0) ctx->layout = NOSH_LAYOUT_CSR;
+    if (strcmp(e, "sell32") == 0) ctx->layout = NOSH_LAYOUT_SELL32;
+  }
+  if (const char *e = getenv("NOSH_B200_GROUP")) {
+    const long long g = atoll(e);
+    if (g >= CHUNK && g % CHUNK == 0) ctx->group_vertices = g;
+  }
+  *out = ctx;
+  return NOSH_OK;
+}
+
+void nosh_ctx_destroy(nosh_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  comm_destroy(ctx);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  cudaStream_t s = ctx->own_stream ? ctx->stream : nullptr;
+  delete ctx;
+  if (s) cudaStreamDestroy(s);
+}
+
+const char *nosh_last_error(const nosh_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+nosh_status nosh_ctx_set_layout(nosh_ctx *ctx, nosh_layout layout) {
+  API_BEGIN(ctx)
+  if (ctx->has_mesh) NOSH_THROW(NOSH_ESTATE, "layout must be chosen before the mesh is set");
+  if (layout != NOSH_LAYOUT_CSR && layout != NOSH_LAYOUT_SELL32) NOSH_THROW(NOSH_EINVAL, "unknown layout");
+  ctx->layout = layout;
+  API_END(ctx)
+}
+
+nosh_status nosh_ctx_set_group_vertices(nosh_ctx *ctx, int64_t g) {
+  API_BEGIN(ctx)
+  if (ctx->has_mesh) NOSH_THROW(NOSH_ESTATE, "group size must be chosen before the mesh is set");
+  if (g < CHUNK || g % CHUNK) NOSH_THROW(NOSH_EINVAL, "group_vertices must be a positive multiple of %d", CHUNK);
+  ctx->group_vertices = g;
+  API_END(ctx)
+}
+
+nosh_status nosh_ctx_synchronize(nosh_ctx *ctx) {
+  API_BEGIN(ctx)
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+nosh_status nosh_comm_unique_id(void *id128) {
+  if (!id128) return NOSH_EINVAL;
+  try {
+    comm_unique_id(id128);
+  } catch (const nosh::Exception &e) {
+    return e.code;
+  }
+  return NOSH_OK;
+}
+
+nosh_status nosh_ctx_comm_init(nosh_ctx *ctx, const void *id128, int rank, int nranks) {
+  API_BEGIN(ctx)
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  comm_init(ctx, id128, rank, nranks);
+  API_END(ctx)
+}
+
+nosh_status nosh_mesh_set(nosh_ctx *ctx, int dim, int64_t nv, const double *coords, int64_t nc,
+                          const int32_t *cells) {
+  API_BEGIN(ctx)
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  ctx->has_mesh = false;
+  mesh_from_host(ctx, dim, nv, coords, nc, cells);
+  after_mesh(ctx);
+  API_END(ctx)
+}
+
+nosh_status nosh_mesh_tetgrid(nosh_ctx *ctx, int nx, int ny, int nz, const double lo[3], const double hi[3],
+                              double jitter, uint64_t seed) {
+  API_BEGIN(ctx)
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (!lo || !hi) NOSH_THROW(NOSH_EINVAL, "NULL bounds");
+  ctx->has_mesh = false;
+  mesh_tetgrid(ctx, nx, ny, nz, lo, hi, jitter, seed);
+  after_mesh(ctx);
+  API_END(ctx)
+}
+
+nosh_status nosh_mesh_info(const nosh_ctx *ctx, nosh_mesh_info_t *info) {
+  if (!ctx || !info) return NOSH_EINVAL;
+  if (!ctx->has_mesh) return NOSH_ESTATE;
+  info->dim = ctx->dim;
+  info->n_global = ctx->n_global;
+  info->owned_begin = ctx->vb;
+  info->n_owned = ctx->No;
+  info->n_ghost = ctx->Ng;
+  info->n_cells = ctx->nc;
+  info->n_edges = ctx->E;
+  info->n_blocks = ctx->nb;
+  info->n_stored = ctx->nstored;
+  return NOSH_OK;
+}
+
+nosh_status nosh_mesh_local_gids(nosh_ctx *ctx, int64_t *gids) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  DBuf<int64_t> w;
+  w.alloc(ctx->Nl);
+  k_widen<<<(unsigned)cdiv(ctx->Nl, 256), 256, 0, ctx->stream>>>(ctx->gid.p, ctx->Nl, w.p);
+  ctx->launches++;
+  d2h(ctx, gids, w.p, ctx->Nl);
+  API_END(ctx)
+}
+
+nosh_status nosh_mesh_get_coords(nosh_ctx *ctx, double *coords) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  d2h(ctx, coords, ctx->coords.p, ctx->Nl * 3);
+  API_END(ctx)
+}
+
+nosh_status nosh_mesh_get_cells(nosh_ctx *ctx, int32_t *cells) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  d2h(ctx, cells, ctx->cells.p, ctx->nc * (ctx->dim + 1));
+  API_END(ctx)
+}
+
+nosh_status nosh_mesh_get_edges(nosh_ctx *ctx, int32_t *edges, double *length, double *covolume) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  d2h(ctx, edges, ctx->edges.p, ctx->E * 2);
+  d2h(ctx, length, ctx->elen.p, ctx->E);
+  d2h(ctx, covolume, ctx->ecov.p, ctx->E);
+  API_END(ctx)
+}
+
+nosh_status nosh_mesh_get_control_volumes(nosh_ctx *ctx, double *cv) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  d2h(ctx, cv, ctx->cv.p, ctx->No);
+  API_END(ctx)
+}
+
+nosh_status nosh_set_thickness(nosh_ctx *ctx, const double *values, double c) {
+  API_BEGIN(ctx)
+  set_thickness(ctx, values, c);
+  API_END(ctx)
+}
+
+nosh_status nosh_set_potential_constant(nosh_ctx *ctx, double c, const char *param1_name) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  ctx->pot_kind = POT_CONSTANT;
+  ctx->pot_c = c;
+  ctx->pot_param = param1_name ? param1_name : "";
+  API_END(ctx)
+}
+
+nosh_status nosh_set_potential_values(nosh_ctx *ctx, const double *values) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  if (!values) NOSH_THROW(NOSH_EINVAL, "NULL values");
+  ctx->pot_values.alloc(ctx->No);
+  CUDA_CHECK(cudaMemcpyAsync(ctx->pot_values.p, values, sizeof(double) * ctx->No, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->pot_kind = POT_VALUES;
+  API_END(ctx)
+}
+
+nosh_status nosh_set_mvp_explicit(nosh_ctx *ctx, const double *A) {
+  API_BEGIN(ctx)
+  if (!A) NOSH_THROW(NOSH_EINVAL, "NULL A");
+  set_mvp_explicit(ctx, A, nullptr);
+  API_END(ctx)
+}
+
+nosh_status nosh_set_mvp_explicit_curl(nosh_ctx *ctx, const double B[3]) {
+  API_BEGIN(ctx)
+  if (!B) NOSH_THROW(NOSH_EINVAL, "NULL B");
+  set_mvp_explicit(ctx, nullptr, B);
+  API_END(ctx)
+}
+
+nosh_status nosh_set_mvp_constcurl(nosh_ctx *ctx, const double b[3], const double u[3]) {
+  API_BEGIN(ctx)
+  if (!b) NOSH_THROW(NOSH_EINVAL, "NULL b");
+  set_mvp_constcurl(ctx, b, u);
+  API_END(ctx)
+}
+
+nosh_status nosh_get_alpha_cache(nosh_ctx *ctx, double *alpha) {
+  API_BEGIN(ctx)
+  ensure_alpha(ctx);
+  d2h(ctx, alpha, ctx->alpha.p, ctx->E);
+  API_END(ctx)
+}
+
+nosh_status nosh_get_edge_projection(nosh_ctx *ctx, int np, const char *const *names, const double *values,
+                                     const char *dname, double *a, double *da) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  DBuf<double> da_, a_;
+  a_.alloc(ctx->E);
+  da_.alloc(ctx->E);
+  edge_projection(ctx, np, names, values, dname, a_.p, da_.p);
+  d2h(ctx, a, a_.p, ctx->E);
+  if (dname) d2h(ctx, da, da_.p, ctx->E);
+  API_END(ctx)
+}
+
+nosh_status nosh_keo_fill(nosh_ctx *ctx, int np, const char *const *names, const double *values) {
+  API_BEGIN(ctx)
+  // the reference always refills (its cache never hits, src/parameter_object.cpp:17-44); an
+  // explicit fill request is honoured even for unchanged parameters
+  keo_fill(ctx, np, names, values, true);
+  API_END(ctx)
+}
+
+nosh_status nosh_dkeo_fill(nosh_ctx *ctx, int np, const char *const *names, const double *values,
+                           const char *dname) {
+  API_BEGIN(ctx)
+  ctx->dkeo_filled = false;
+  dkeo_fill(ctx, np, names, values, dname);
+  API_END(ctx)
+}
+
+nosh_status nosh_matrix_apply(nosh_ctx *ctx, nosh_matrix_id which, const double *X, int64_t ldx, double *Y,
+                              int64_t ldy, int nvec, nosh_transp mode, double alpha, double beta) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  (void)mode;  // Hermitian: symmetric in the real layout, every mode is the same operator
+  check_apply_shape(ctx, ldx, ldy, nvec);
+  const double2 *val = nullptr;
+  if (which == NOSH_MAT_KEO) {
+    if (!ctx->keo_filled) NOSH_THROW(NOSH_ESTATE, "KEO not filled");
+    val = ctx->Kval.p;
+  } else if (which == NOSH_MAT_DKEO) {
+    if (!ctx->dkeo_filled) NOSH_THROW(NOSH_ESTATE, "dKEO not filled");
+    val = ctx->dKval.p;
+  } else {
+    NOSH_THROW(NOSH_EINVAL, "unknown matrix id");
+  }
+  ensure_work(ctx);
+  for (int v = 0; v < nvec; v++) {
+    double2 *x = stage_in(ctx, X + (size_t)v * ldx, ctx->stage_x, ctx->nranks > 1);
+    OutVec o = stage_out(ctx, Y + (size_t)v * ldy, ctx->stage_y);
+    if (o.host && beta != 0.0)
+      CUDA_CHECK(cudaMemcpyAsync(o.dev, o.user, sizeof(double2) * ctx->No, cudaMemcpyHostToDevice, ctx->stream));
+    ApplyArgs A;
+    memset(&A, 0, sizeof(A));
+    A.No = ctx->No;
+    A.nslices = ctx->nslices;
+    A.rowptr = ctx->rowptr.p;
+    A.slice_off = ctx->slice_off.p;
+    A.col = ctx->col.p;
+    A.val = val;
+    A.x = x;
+    A.y = o.dev;
+    A.a = alpha;
+    A.b = beta;
+    halo_exchange(ctx, x);
+    launch_apply(ctx, EPI_NONE, (alpha == 1.0 && beta == 0.0) ? FUSE_NONE : FUSE_AXPBY, A);
+    finish_out(ctx, o);
+  }
+  API_END(ctx)
+}
+
+nosh_status nosh_get_block_csr(nosh_ctx *ctx, nosh_matrix_id which, int64_t *rowptr, int32_t *cols,
+                               double *vals) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  if (rowptr) {
+    DBuf<int64_t> w;
+    w.alloc(ctx->No + 1);
+    k_widen<<<(unsigned)cdiv(ctx->No + 1, 256), 256, 0, ctx->stream>>>(ctx->rowptr.p, ctx->No + 1, w.p);
+    ctx->launches++;
+    d2h(ctx, rowptr, w.p, ctx->No + 1);
+  }
+  d2h(ctx, cols, ctx->csr_col.p, ctx->nb);
+  if (vals) {
+    const double2 *val = which == NOSH_MAT_KEO ? ctx->Kval.p : ctx->dKval.p;
+    if (which == NOSH_MAT_KEO && !ctx->keo_filled) NOSH_THROW(NOSH_ESTATE, "KEO not filled");
+    if (which == NOSH_MAT_DKEO && !ctx->dkeo_filled) NOSH_THROW(NOSH_ESTATE, "dKEO not filled");
+    DBuf<double2> g;
+    g.alloc(ctx->nb);
+    if (ctx->nb) {
+      k_gather_vals<<<(unsigned)cdiv(ctx->nb, 256), 256, 0, ctx->stream>>>(ctx->csr_pos.p, val, ctx->nb, g.p);
+      ctx->launches++;
+    }
+    d2h(ctx, (double2 *)vals, g.p, ctx->nb);
+  }
+  API_END(ctx)
+}
+
+nosh_status nosh_jac_rebuild(nosh_ctx *ctx, int np, const char *const *names, const double *values,
+                             const double *psi) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  keo_fill(ctx, np, names, values, false);            // keo_->set_parameters (src/jacobian_operator.cpp:135)
+  const double g = param_at(np, names, values, "g");  // :156
+  update_potential(ctx, np, names, values);
+  double2 *x = stage_in(ctx, psi, ctx->stage_x, false);
+  jac_diags_dev(ctx, g, x);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+nosh_status nosh_jac_apply(nosh_ctx *ctx, const double *X, int64_t ldx, double *Y, int64_t ldy, int nvec,
+                           nosh_transp mode, double alpha, double beta) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  // src/jacobian_operator.cpp:48-59
+  if (mode != NOSH_NO_TRANS) NOSH_THROW(NOSH_EINVAL, "Only untransposed applies supported.");
+  if (alpha != 1.0) NOSH_THROW(NOSH_EINVAL, "Only alpha==1.0 supported.");
+  if (beta != 0.0) NOSH_THROW(NOSH_EINVAL, "Only beta==0.0 supported.");
+  check_apply_shape(ctx, ldx, ldy, nvec);
+  for (int v = 0; v < nvec; v++) {
+    double2 *x = stage_in(ctx, X + (size_t)v * ldx, ctx->stage_x, ctx->nranks > 1);
+    OutVec o = stage_out(ctx, Y + (size_t)v * ldy, ctx->stage_y);
+    apply_op_dev(ctx, NOSH_OP_JACOBIAN, x, o.dev);
+    finish_out(ctx, o);
+  }
+  API_END(ctx)
+}
+
+nosh_status nosh_jac_get_diags(nosh_ctx *ctx, double *d0, double *d1b) {
+  API_BEGIN(ctx)
+  if (!ctx->jac_ok) NOSH_THROW(NOSH_ESTATE, "Jacobian not built");
+  d2h(ctx, (double2 *)d0, ctx->jd0.p, ctx->No);
+  d2h(ctx, d1b, ctx->jd1.p, ctx->No);
+  API_END(ctx)
+}
+
+nosh_status nosh_compute_f(nosh_ctx *ctx, int np, const char *const *names, const double *values,
+                           const double *psi, double *f) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  keo_fill(ctx, np, names, values, false);            // src/model_evaluator_nls.cpp:536
+  const double g = param_at(np, names, values, "g");  // :559
+  update_potential(ctx, np, names, values);
+  double2 *x = stage_in(ctx, psi, ctx->stage_x, ctx->nranks > 1);
+  OutVec o = stage_out(ctx, f, ctx->stage_y);
+  compute_f_dev(ctx, g, x, o.dev);
+  finish_out(ctx, o);
+  API_END(ctx)
+}
+
+nosh_status nosh_compute_dfdp(nosh_ctx *ctx, int np, const char *const *names, const double *values,
+                              const char *pname, const double *psi, double *dfdp) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  if (!pname) NOSH_THROW(NOSH_EINVAL, "NULL parameter name");
+  // dK/dp for the column's own parameter
+  dkeo_fill(ctx, np, names, values, pname);
+  ensure_work(ctx);
+  double2 *x = stage_in(ctx, psi, ctx->stage_x, ctx->nranks > 1);
+  OutVec o = stage_out(ctx, dfdp, ctx->stage_y);
+  ApplyArgs A;
+  memset(&A, 0, sizeof(A));
+  A.No = ctx->No;
+  A.nslices = ctx->nslices;
+  A.rowptr = ctx->rowptr.p;
+  A.slice_off = ctx->slice_off.p;
+  A.col = ctx->col.p;
+  A.val = ctx->dKval.p;
+  A.x = x;
+  A.y = o.dev;
+  A.cv = ctx->cv.p;
+  A.thick = ctx->thick.p;
+  A.a = 1.0;
+  halo_exchange(ctx, x);
+  if (strcmp(pname, "g") == 0) {  // src/model_evaluator_nls.cpp:665-674
+    launch_apply(ctx, EPI_DG, FUSE_NONE, A);
+  } else {  // :676-691
+    DBuf<double> dv;
+    dv.alloc(ctx->No);
+    potential_dvdp(ctx, pname, dv.p);
+    A.V = dv.p;
+    launch_apply(ctx, EPI_DV, FUSE_NONE, A);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+  finish_out(ctx, o);
+  API_END(ctx)
+}
+
+nosh_status nosh_keoreg_rebuild(nosh_ctx *ctx, int np, const char *const *names, const double *values,
+                                const double *psi) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  keo_fill(ctx, np, names, values, false);            // src/keo_regularized.cpp:196
+  const double g = param_at(np, names, values, "g");  // :198
+  double2 *x = stage_in(ctx, psi, ctx->stage_x, false);
+  keoreg_diags_dev(ctx, g, x);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+nosh_status nosh_keoreg_matrix_apply(nosh_ctx *ctx, const double *X, int64_t ldx, double *Y, int64_t ldy,
+                                     int nvec) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  check_apply_shape(ctx, ldx, ldy, nvec);
+  for (int v = 0; v < nvec; v++) {
+    double2 *x = stage_in(ctx, X + (size_t)v * ldx, ctx->stage_x, ctx->nranks > 1);
+    OutVec o = stage_out(ctx, Y + (size_t)v * ldy, ctx->stage_y);
+    apply_op_dev(ctx, NOSH_OP_KEOREG, x, o.dev);
+    finish_out(ctx, o);
+  }
+  API_END(ctx)
+}
+
+nosh_status nosh_keoreg_get_diags(nosh_ctx *ctx, double *d0, double *d1b) {
+  API_BEGIN(ctx)
+  if (!ctx->keoreg_ok) NOSH_THROW(NOSH_ESTATE, "regularised KEO not built");
+  d2h(ctx, (double2 *)d0, ctx->pd0.p, ctx->No);
+  d2h(ctx, d1b, ctx->pd1.p, ctx->No);
+  API_END(ctx)
+}
+
+nosh_status nosh_keoreg_apply(nosh_ctx *ctx, const double *, int64_t, double *, int64_t, int, nosh_transp,
+                              double, double) {
+  API_BEGIN(ctx)
+  NOSH_THROW(NOSH_EUNSUPPORTED,
+             "keo_regularized::apply is one MueLu AMG V-cycle (src/keo_regularized.cpp:106-108): third-party, "
+             "out of scope; use nosh_keoreg_matrix_apply for the matrix itself");
+  API_END(ctx)
+}
+
+nosh_status nosh_dot(nosh_ctx *ctx, const double *x, const double *y, double *result) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  if (!result) NOSH_THROW(NOSH_EINVAL, "NULL result");
+  const double2 *xd = stage_in(ctx, x, ctx->stage_x, false);
+  const double2 *yd = (y == x) ? xd : stage_in(ctx, y, ctx->stage_y, false);
+  *result = dot_dev(ctx, xd, yd);
+  API_END(ctx)
+}
+
+nosh_status nosh_norm2(nosh_ctx *ctx, const double *x, double *result) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  if (!result) NOSH_THROW(NOSH_EINVAL, "NULL result");
+  const double2 *xd = stage_in(ctx, x, ctx->stage_x, false);
+  *result = sqrt(dot_dev(ctx, xd, xd));
+  API_END(ctx)
+}
+
+static nosh_status krylov_entry(nosh_ctx *ctx, bool is_minres, nosh_operator_id op, const double *b, double *x,
+                                double tol, int maxit, nosh_krylov_result *res, double *hist) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  ensure_work(ctx);
+  const double2 *bd = stage_in(ctx, b, ctx->stage_x, false);
+  OutVec o = stage_out(ctx, x, ctx->stage_y);
+  if (is_minres)
+    minres_dev(ctx, op, bd, 1.0, o.dev, tol, maxit, res, hist);
+  else
+    cg_dev(ctx, op, bd, 1.0, o.dev, tol, maxit, res, hist);
+  finish_out(ctx, o);
+  API_END(ctx)
+}
+
+nosh_status nosh_minres(nosh_ctx *ctx, nosh_operator_id op, const double *b, double *x, double tol, int maxit,
+                        nosh_krylov_result *res, double *hist) {
+  return krylov_entry(ctx, true, op, b, x, tol, maxit, res, hist);
+}
+
+nosh_status nosh_cg(nosh_ctx *ctx, nosh_operator_id op, const double *b, double *x, double tol, int maxit,
+                    nosh_krylov_result *res, double *hist) {
+  return krylov_entry(ctx, false, op, b, x, tol, maxit, res, hist);
+}
+
+nosh_status nosh_newton(nosh_ctx *ctx, int np, const char *const *names, const double *values, double *psi,
+                        double nl_tol, int nl_maxit, double lin_tol, int lin_maxit, nosh_newton_result *res,
+                        int32_t *lin_iters, double *fnorms) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  ensure_work(ctx);
+  if (!psi) NOSH_THROW(NOSH_EINVAL, "NULL psi");
+  if (nl_maxit < 0) NOSH_THROW(NOSH_EINVAL, "nl_maxit < 0");
+  const bool dev = is_device_ptr(psi);
+  double2 *x = ctx->work[8].p;  // Nl entries: the SpMV needs ghost room
+  CUDA_CHECK(cudaMemcpyAsync(x, psi, sizeof(double2) * ctx->No, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                             ctx->stream));
+  newton_dev(ctx, np, names, values, x, nl_tol, nl_maxit, lin_tol, lin_maxit, res, lin_iters, fnorms);
+  CUDA_CHECK(cudaMemcpyAsync(psi, x, sizeof(double2) * ctx->No, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                             ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+nosh_status nosh_scratch_vector(nosh_ctx *ctx, int slot, double **dev_ptr) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  if (slot < 0 || slot >= 8 || !dev_ptr) NOSH_THROW(NOSH_EINVAL, "bad scratch slot");
+  const size_t n = ctx->Nl > 0 ? ctx->Nl : 1;
+  if (ctx->scratch[slot].n < n) {
+    ctx->scratch[slot].alloc(n);
+    CUDA_CHECK(cudaMemsetAsync(ctx->scratch[slot].p, 0, sizeof(double2) * n, ctx->stream));
+  }
+  *dev_ptr = (double *)ctx->scratch[slot].p;
+  API_END(ctx)
+}
+
+int64_t nosh_launch_count(const nosh_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+nosh_status nosh_timer_start(nosh_ctx *ctx) {
+  API_BEGIN(ctx)
+  CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+  API_END(ctx)
+}
+
+nosh_status nosh_timer_stop(nosh_ctx *ctx, float *ms) {
+  API_BEGIN(ctx)
+  CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+  if (ms) CUDA_CHECK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  API_END(ctx)
+}
+
+}  // extern "C"

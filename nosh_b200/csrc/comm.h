@@ -1,0 +1,11 @@
+// comm.h -- NCCL plumbing (comm.cu)
+#pragma once
+#include "common.cuh"
+namespace nosh {
+void comm_unique_id(void *id128);
+void comm_init(Ctx *ctx, const void *id128, int rank, int nranks);
+void comm_destroy(Ctx *ctx);
+void comm_allreduce_sum(Ctx *ctx, const double *send, double *recv, int64_t n);
+void halo_setup(Ctx *ctx);
+void halo_exchange(Ctx *ctx, double2 *vec);
+}  // namespace nosh

@@ -1,0 +1,247 @@
+// common.cuh -- context, device buffers, deterministic reductions, load/store helpers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/nosh_b200.h"
+
+namespace nosh {
+
+// ----------------------------------------------------------------------------
+// fixed reduction geometry: every grid reduction is a
+// three-level tree keyed by the GLOBAL vertex index, so that its result does not
+// depend on how vertices are distributed over GPUs:
+//   level 1: one CTA sums one chunk of CHUNK consecutive vertices (fixed order)
+//   level 2: one warp sums the chunk partials of one group (group_vertices)
+//   level 3: the group sums of the whole mesh are added in a fixed tree
+// ----------------------------------------------------------------------------
+constexpr int CHUNK = 512;       // vertices per level-1 partial
+constexpr int TPB = 256;         // threads per CTA of the vector kernels (2 vertices/thread)
+constexpr int MAX_GROUPS = 1024; // level-3 fan-in limit
+
+struct Exception {
+  nosh_status code;
+  std::string msg;
+};
+
+#define NOSH_THROW(code, ...)                           \
+  do {                                                  \
+    char _b[512];                                       \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);              \
+    throw ::nosh::Exception{code, std::string(_b)};     \
+  } while (0)
+
+#define CUDA_CHECK(expr)                                                                     \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      NOSH_THROW(NOSH_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                 __LINE__);                                                                  \
+  } while (0)
+
+template <typename T>
+struct DBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DBuf() = default;
+  DBuf(const DBuf &) = delete;
+  DBuf &operator=(const DBuf &) = delete;
+  ~DBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    release();
+    if (count == 0) count = 1;
+    CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+  }
+  void ensure(size_t count) {
+    if (count > n) alloc(count);
+  }
+  void swap(DBuf &o) {
+    std::swap(p, o.p);
+    std::swap(n, o.n);
+  }
+};
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- MINRES / CG device-resident scalar state -------------------------------
+struct KrylovState {
+  // recurrences (Belos::MinresIter names)
+  double beta1, beta, oldBeta, alpha, dbar, epsln, oldeps, delta, gbar, gamma, cs, sn, phi, phibar;
+  // coefficients consumed by the vector kernels
+  double inv_beta;      // 1/beta_k                 (v_k = r_k * inv_beta)
+  double f_r1;          // beta_k/beta_{k-1}        (0 on the first iteration)
+  double f_r2;          // alpha_k/beta_k
+  double inv_beta_prev; // 1/beta of the vector W is built from
+  double c_w1, c_w2, inv_gamma, phi_w;
+  // CG
+  double rho, rho_old, pAp, cg_alpha, cg_beta, r0norm;
+  double tol;
+  double relres;
+  int iter;
+  int maxit;
+  int done;      // 1 => all further kernels are no-ops
+  int converged;
+  int breakdown;
+};
+
+struct NcclApi;  // comm.cpp
+
+enum MvpKind { MVP_NONE = 0, MVP_EXPLICIT = 1, MVP_CONSTCURL = 2 };
+enum PotKind { POT_NONE = 0, POT_CONSTANT = 1, POT_VALUES = 2 };
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // comm
+  int rank = 0, nranks = 1;
+  NcclApi *nccl = nullptr;
+  void *comm = nullptr;  // ncclComm_t
+
+  // options
+  int layout = NOSH_LAYOUT_SELL32;
+  int64_t group_vertices = 65536;
+
+  // ---- mesh ----
+  bool has_mesh = false;
+  int dim = 0;
+  int64_t n_global = 0, vb = 0, ve = 0;
+  int64_t No = 0, Ng = 0, Nl = 0, nc = 0, E = 0;
+  std::vector<int64_t> part_begin;  // nranks+1 global vertex offsets
+  DBuf<int32_t> gid;                // Nl global ids (int32: n_global < 2^31)
+  DBuf<double> coords;              // Nl x 3
+  DBuf<int32_t> cells;              // nc x (dim+1) local ids
+  DBuf<int32_t> edges;              // E x 2 local ids, gid(v0) < gid(v1)
+  DBuf<double> elen, ecov;          // E
+  DBuf<double> cv;                  // No
+  // ---- block matrix structure (owned rows) ----
+  int64_t nb = 0;                   // CSR blocks
+  int64_t nstored = 0;              // stored blocks (incl. SELL padding)
+  int64_t nslices = 0;
+  DBuf<int32_t> rowptr;             // No+1 (CSR positions)
+  DBuf<int32_t> csr_col;            // nb local col ids (CSR order)
+  DBuf<int32_t> csr_pos;            // nb: CSR position -> storage position
+  DBuf<int32_t> edge_of;            // nb: edge of a CSR position (-1: diagonal)
+  DBuf<int32_t> col;                // nstored local col ids (storage order)
+  DBuf<int32_t> slice_off;          // nslices+1 (SELL)
+  DBuf<int32_t> slot_ij, slot_ji;   // E storage positions (-1: row not owned)
+  DBuf<int32_t> diag_slot;          // No storage positions
+  DBuf<double2> Kval, dKval;        // nstored
+  DBuf<double> Kdiag;               // No: sum of alpha over incident edges
+  // ---- fields ----
+  DBuf<double> thick;               // Nl
+  bool thick_set = false;
+  int pot_kind = POT_NONE;
+  double pot_c = 0.0;
+  std::string pot_param;
+  DBuf<double> pot_values;          // No (POT_VALUES)
+  DBuf<double> Vcur;                // No: V for the current parameters
+  int mvp_kind = MVP_NONE;
+  DBuf<double> ecache;              // E (explicit) or 3E (constcurl)
+  double cc_b[3] = {0, 0, 1}, cc_u[3] = {0, 0, 0};
+  bool cc_has_u = false;
+  DBuf<double> alpha;               // E
+  bool alpha_ok = false;
+  // fill caches (the parameter cache the reference meant to have)
+  bool keo_filled = false, dkeo_filled = false;
+  double keo_mu = 0, keo_theta = 0, dkeo_mu = 0, dkeo_theta = 0;
+  std::string dkeo_name;
+  // ---- Jacobian / preconditioner diagonals ----
+  DBuf<double2> jd0;                // No (d0[2k], d0[2k+1])
+  DBuf<double> jd1;                 // No
+  bool jac_ok = false;
+  DBuf<double2> pd0;
+  DBuf<double> pd1;
+  bool keoreg_ok = false;
+  // ---- work vectors (2*Nl doubles each) ----
+  DBuf<double2> work[12];
+  DBuf<double2> scratch[8];
+  DBuf<double2> stage_x, stage_y;   // host staging
+  // ---- reductions ----
+  DBuf<double> partials;            // 2 x n_chunks
+  DBuf<double> group_sums;          // 2 x MAX_GROUPS (global group index)
+  DBuf<KrylovState> kstate;
+  DBuf<double> hist;
+  DBuf<double> scalar_out;          // misc device scalars
+  int64_t n_chunks = 0;
+  int64_t n_groups_global = 0, group_begin = 0, n_groups_local = 0;
+  int chunks_per_group = 0;
+  // ---- halo exchange ----
+  std::vector<int64_t> send_count, recv_count, send_off, recv_off;  // per peer, in vertices
+  DBuf<int32_t> send_idx;           // owned local ids to pack, grouped by peer
+  DBuf<double2> send_buf;
+  int64_t n_send = 0;
+};
+
+// ---- parameter map helpers ---------------------------------------------------
+inline const double *find_param(int np, const char *const *names, const double *values,
+                                const char *key) {
+  for (int i = 0; i < np; i++)
+    if (names[i] && strcmp(names[i], key) == 0) return &values[i];
+  return nullptr;
+}
+inline double param_at(int np, const char *const *names, const double *values, const char *key) {
+  const double *p = find_param(np, names, values, key);
+  if (!p) NOSH_THROW(NOSH_EKEY, "parameter \"%s\" missing (std::map::at)", key);
+  return *p;
+}
+
+#ifdef __CUDACC__
+// ---- device helpers ------------------------------------------------------------
+__device__ __forceinline__ double2 ldg2(const double2 *p) { return __ldg(p); }
+
+// streaming (read-once) 128-bit load: do not pollute L1
+__device__ __forceinline__ double2 ld_stream2(const double2 *p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+               : "=d"(r.x), "=d"(r.y)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int ld_stream_i32(const int *p) {
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic CTA sum (fixed tree: xor-shuffle inside each warp, then the warp
+// sums in warp order).  Result valid in thread 0.  NW = warps per CTA.
+template <int NW>
+__device__ __forceinline__ double block_sum(double v, double *smem /* NW doubles */) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) smem[w] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NW; i++) s += smem[i];
+  }
+  __syncthreads();
+  return s;
+}
+#endif
+
+}  // namespace nosh

@@ -1,0 +1,704 @@
+// krylov.cu -- Krylov solvers (a18) and the Newton driver with device-resident control flow.
+//
+// MINRES follows Belos::MinresIter's organisation of Paige-Saunders MINRES (restated in
+// oracle/nosh_oracle.cpp:minres; Belos itself is not in the reference tree).  One
+// iteration is three vector kernels and two one-CTA "finalize" kernels:
+//
+//   A  y   = J (r_k/beta_k) - (beta_k/beta_{k-1}) r_{k-1},  partials of <v_k, y>   [apply.cu, fused]
+//   fA alpha_k
+//   B  r_{k+1} = y - (alpha_k/beta_k) r_k,                  partials of <r_{k+1}, r_{k+1}>
+//   fB beta_{k+1}, Givens rotation, phi, convergence test, iteration counter
+//   C  w_k = (v_k - eps w_{k-2} - delta w_{k-1})/gamma,  x += phi w_k
+//
+// All scalars live in a KrylovState in HBM; the host never reads one inside the loop, it
+// only polls `done` every few iterations.  Once `done` is set every later launch returns
+// immediately, so x is exactly the iterate of the passing iteration.
+// Reductions are the fixed three-level tree of common.cuh => bit-identical results for
+// any number of GPUs.
+#include "krylov.h"
+
+#include "apply.cuh"
+#include "comm.h"
+#include "keo.h"
+
+namespace nosh {
+
+namespace {
+
+enum { FIN_DOT = 0, FIN_MINRES_INIT, FIN_MINRES_ALPHA, FIN_MINRES_BETA, FIN_CG_INIT, FIN_CG_PAP, FIN_CG_RHO };
+
+#define KLAUNCH(ctx, kernel, grid, block, ...)                    \
+  do {                                                            \
+    kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);   \
+    (ctx)->launches++;                                            \
+    CUDA_CHECK(cudaGetLastError());                               \
+  } while (0)
+
+// ---- chunked vector kernels: one CTA (256 threads) per CHUNK = 512 vertices ------------------
+__device__ __forceinline__ double cdot(double2 a, double2 b) { return a.x * b.x + a.y * b.y; }
+
+__global__ void __launch_bounds__(TPB) k_dot(const double2 *x, const double2 *y, int64_t No, double *partials) {
+  __shared__ double red[TPB / 32];
+  const int64_t i0 = (int64_t)blockIdx.x * CHUNK + threadIdx.x, i1 = i0 + TPB;
+  double c = 0.0;
+  if (i0 < No) c = cdot(x[i0], y[i0]);
+  if (i1 < No) c += cdot(x[i1], y[i1]);
+  const double s = block_sum<TPB / 32>(c, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(TPB) k_minres_init(const double2 *b, double bscale, int64_t No, double2 *r0,
+                                                     double2 *w0, double2 *w1, double2 *w2, double2 *x,
+                                                     double *partials) {
+  __shared__ double red[TPB / 32];
+  double c = 0.0;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int64_t i = (int64_t)blockIdx.x * CHUNK + threadIdx.x + h * TPB;
+    if (i < No) {
+      double2 r = b[i];
+      r.x *= bscale;
+      r.y *= bscale;
+      r0[i] = r;
+      const double2 z = make_double2(0.0, 0.0);
+      w0[i] = z;
+      w1[i] = z;
+      w2[i] = z;
+      x[i] = z;
+      c += cdot(r, r);
+    }
+  }
+  const double s = block_sum<TPB / 32>(c, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(TPB) k_minres_B(const KrylovState *st, int host_iter, const double2 *p,
+                                                  const double2 *r2, double2 *rnew, int64_t No,
+                                                  double *partials) {
+  if (st->done || st->iter != host_iter - 1) return;
+  __shared__ double red[TPB / 32];
+  const double f = st->f_r2;
+  const int64_t i0 = (int64_t)blockIdx.x * CHUNK + threadIdx.x, i1 = i0 + TPB;
+  double2 p0, p1, q0, q1;
+  if (i0 < No) { p0 = ld_stream2(p + i0); q0 = ld_stream2(r2 + i0); }
+  if (i1 < No) { p1 = ld_stream2(p + i1); q1 = ld_stream2(r2 + i1); }
+  double c = 0.0;
+  if (i0 < No) {
+    const double2 r = make_double2(p0.x - f * q0.x, p0.y - f * q0.y);
+    rnew[i0] = r;
+    c = cdot(r, r);
+  }
+  if (i1 < No) {
+    const double2 r = make_double2(p1.x - f * q1.x, p1.y - f * q1.y);
+    rnew[i1] = r;
+    c += cdot(r, r);
+  }
+  const double s = block_sum<TPB / 32>(c, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(TPB) k_minres_C(const KrylovState *st, int host_iter, const double2 *rcur,
+                                                  const double2 *w1, const double2 *w2, double2 *wnew,
+                                                  double2 *x, int64_t No) {
+  if (st->iter != host_iter) return;  // this iteration did not execute (already converged)
+  const double ib = st->inv_beta_prev, oe = st->oldeps, de = st->delta, ig = st->inv_gamma, ph = st->phi;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int64_t i = (int64_t)blockIdx.x * CHUNK + threadIdx.x + h * TPB;
+    if (i < No) {
+      const double2 r = ld_stream2(rcur + i), a = ld_stream2(w1 + i), b = ld_stream2(w2 + i);
+      double2 xx = x[i];
+      double2 w;
+      w.x = ((r.x * ib - oe * a.x) - de * b.x) * ig;
+      w.y = ((r.y * ib - oe * a.y) - de * b.y) * ig;
+      wnew[i] = w;
+      xx.x += ph * w.x;
+      xx.y += ph * w.y;
+      x[i] = xx;
+    }
+  }
+}
+
+// ---- CG vector kernels --------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_cg_init(const double2 *b, double bscale, int64_t No, double2 *r,
+                                                 double2 *p, double2 *x, double *partials) {
+  __shared__ double red[TPB / 32];
+  double c = 0.0;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int64_t i = (int64_t)blockIdx.x * CHUNK + threadIdx.x + h * TPB;
+    if (i < No) {
+      double2 v = b[i];
+      v.x *= bscale;
+      v.y *= bscale;
+      r[i] = v;
+      p[i] = v;
+      x[i] = make_double2(0.0, 0.0);
+      c += cdot(v, v);
+    }
+  }
+  const double s = block_sum<TPB / 32>(c, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(TPB) k_cg_update(const KrylovState *st, int host_iter, const double2 *p,
+                                                   const double2 *ap, double2 *r, double2 *x, int64_t No,
+                                                   double *partials) {
+  if (st->done || st->iter != host_iter - 1) return;
+  __shared__ double red[TPB / 32];
+  const double al = st->cg_alpha;
+  double c = 0.0;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int64_t i = (int64_t)blockIdx.x * CHUNK + threadIdx.x + h * TPB;
+    if (i < No) {
+      const double2 pp = p[i], aa = ld_stream2(ap + i);
+      double2 xx = x[i], rr = r[i];
+      xx.x += al * pp.x;
+      xx.y += al * pp.y;
+      rr.x -= al * aa.x;
+      rr.y -= al * aa.y;
+      x[i] = xx;
+      r[i] = rr;
+      c += cdot(rr, rr);
+    }
+  }
+  const double s = block_sum<TPB / 32>(c, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(TPB) k_cg_direction(const KrylovState *st, int host_iter, const double2 *r,
+                                                      double2 *p, int64_t No) {
+  if (st->iter != host_iter) return;
+  const double be = st->cg_beta;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int64_t i = (int64_t)blockIdx.x * CHUNK + threadIdx.x + h * TPB;
+    if (i < No) {
+      const double2 rr = r[i];
+      double2 pp = p[i];
+      pp.x = rr.x + be * pp.x;
+      pp.y = rr.y + be * pp.y;
+      p[i] = pp;
+    }
+  }
+}
+
+// ---- misc vector kernels ---------------------------------------------------------------------------
+__global__ void k_axpy(double a, const double2 *x, double2 *y, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double2 xx = x[i];
+    double2 yy = y[i];
+    yy.x += a * xx.x;
+    yy.y += a * xx.y;
+    y[i] = yy;
+  }
+}
+// jacobian_operator::rebuild_diags_ (src/jacobian_operator.cpp:184-197)
+__global__ void k_jac_diags(double g, const double *cv, const double *thick, const double *V,
+                            const double2 *psi, int64_t No, double2 *d0, double *d1) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= No) return;
+  const double2 x = psi[k];
+  const double ct = cv[k] * thick[k];
+  const double alpha = ct * (V[k] + g * 2.0 * (x.x * x.x + x.y * x.y));
+  const double realX2 = g * ct * (x.x * x.x - x.y * x.y);
+  d0[k] = make_double2(alpha + realX2, alpha - realX2);
+  d1[k] = g * ct * (2.0 * x.x * x.y);
+}
+// keo_regularized::rebuild diagonal blocks (src/keo_regularized.cpp:233-259); zero if g <= 0 (:200)
+__global__ void k_keoreg_diags(double g, const double *cv, const double *thick, const double2 *psi,
+                               int64_t No, double2 *d0, double *d1) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= No) return;
+  if (!(g > 0.0)) {
+    d0[k] = make_double2(0.0, 0.0);
+    d1[k] = 0.0;
+    return;
+  }
+  const double2 x = psi[k];
+  const double gct = g * cv[k] * thick[k];
+  const double al = gct * 2.0 * (x.x * x.x + x.y * x.y);
+  const double be = gct * (2.0 * x.x * x.y);
+  const double ga = gct * (x.x * x.x - x.y * x.y);
+  d0[k] = make_double2(al + ga, al - ga);
+  d1[k] = be;
+}
+
+// ---- finalize: levels 2 and 3 of the reduction tree + the scalar recurrences ------------------------
+struct FinArgs {
+  const double *partials;
+  int64_t n_chunks;
+  int cpg;
+  int64_t group_begin, n_groups_local;
+  int n_groups_global;
+  double *gsend;        // MAX_GROUPS, global group index; zero outside the local groups
+  const double *grecv;  // all-reduced copy (== gsend on one GPU)
+  KrylovState *st;
+  double *out;
+  double *hist;
+  int what, host_iter, stage;  // stage 0: single GPU; 1: level 2 only; 2: level 3 + scalars
+  double tol;
+  int maxit;
+};
+
+__device__ __forceinline__ void sym_ortho(double a, double b, double &c, double &s, double &r) {
+  const double absA = fabs(a), absB = fabs(b);
+  if (absB == 0.0) {
+    s = 0.0;
+    r = absA;
+    c = (absA == 0.0) ? 1.0 : (a >= 0.0 ? 1.0 : -1.0);
+  } else if (absA == 0.0) {
+    c = 0.0;
+    s = (b >= 0.0 ? 1.0 : -1.0);
+    r = absB;
+  } else if (absB >= absA) {
+    const double tau = a / b;
+    s = (b >= 0.0 ? 1.0 : -1.0) / sqrt(1.0 + tau * tau);
+    c = s * tau;
+    r = b / s;
+  } else {
+    const double tau = b / a;
+    c = (a >= 0.0 ? 1.0 : -1.0) / sqrt(1.0 + tau * tau);
+    s = c * tau;
+    r = a / c;
+  }
+}
+
+__device__ void fin_scalars(const FinArgs &F, double total) {
+  KrylovState *st = F.st;
+  switch (F.what) {
+    case FIN_DOT:
+      F.out[0] = total;
+      break;
+    case FIN_MINRES_INIT: {
+      KrylovState s;
+      memset(&s, 0, sizeof(s));
+      s.tol = F.tol;
+      s.maxit = F.maxit;
+      if (total <= 0.0) {
+        s.done = 1;
+        s.converged = 1;
+        s.inv_beta = 0.0;
+      } else {
+        s.beta1 = sqrt(total);
+        s.beta = s.beta1;
+        s.phibar = s.beta1;
+        s.cs = -1.0;
+        s.sn = 0.0;
+        s.inv_beta = 1.0 / s.beta1;
+        s.relres = 1.0;
+        if (F.maxit <= 0 || 1.0 <= F.tol) {
+          s.done = 1;
+          s.converged = 1.0 <= F.tol;
+        }
+      }
+      *st = s;
+      if (F.hist) F.hist[0] = 1.0;
+      break;
+    }
+    case FIN_MINRES_ALPHA:
+      st->alpha = total;
+      st->f_r2 = total / st->beta;
+      break;
+    case FIN_MINRES_BETA: {
+      if (total < 0.0) {
+        st->done = 1;
+        st->breakdown = 1;
+        break;
+      }
+      const double betaNew = sqrt(total);
+      const double oldeps = st->epsln;
+      const double delta = st->cs * st->dbar + st->sn * st->alpha;
+      const double gbar = st->sn * st->dbar - st->cs * st->alpha;
+      st->epsln = st->sn * betaNew;
+      st->dbar = -st->cs * betaNew;
+      double cs, sn, gamma;
+      sym_ortho(gbar, betaNew, cs, sn, gamma);
+      st->cs = cs;
+      st->sn = sn;
+      st->gamma = gamma;
+      st->gbar = gbar;
+      st->phi = cs * st->phibar;
+      st->phibar = sn * st->phibar;
+      if (gamma == 0.0) {
+        st->done = 1;
+        st->breakdown = 1;
+        break;
+      }
+      st->oldeps = oldeps;
+      st->delta = delta;
+      st->inv_gamma = 1.0 / gamma;
+      st->inv_beta_prev = st->inv_beta;
+      st->oldBeta = st->beta;
+      st->beta = betaNew;
+      st->inv_beta = 1.0 / betaNew;
+      st->f_r1 = betaNew / st->oldBeta;
+      st->iter += 1;
+      st->relres = st->phibar / st->beta1;
+      if (F.hist) F.hist[st->iter] = st->relres;
+      if (st->relres <= st->tol) {
+        st->done = 1;
+        st->converged = 1;
+      } else if (st->iter >= st->maxit) {
+        st->done = 1;
+      }
+      break;
+    }
+    case FIN_CG_INIT: {
+      KrylovState s;
+      memset(&s, 0, sizeof(s));
+      s.tol = F.tol;
+      s.maxit = F.maxit;
+      s.rho = total;
+      s.r0norm = sqrt(total);
+      s.relres = 1.0;
+      if (s.r0norm == 0.0) {
+        s.done = 1;
+        s.converged = 1;
+        s.relres = 0.0;
+      } else if (F.maxit <= 0 || 1.0 <= F.tol) {
+        s.done = 1;
+        s.converged = 1.0 <= F.tol;
+      }
+      *st = s;
+      if (F.hist) F.hist[0] = 1.0;
+      break;
+    }
+    case FIN_CG_PAP:
+      st->pAp = total;
+      st->cg_alpha = st->rho / total;
+      break;
+    case FIN_CG_RHO: {
+      st->cg_beta = total / st->rho;
+      st->rho = total;
+      st->iter += 1;
+      st->relres = sqrt(total) / st->r0norm;
+      if (F.hist) F.hist[st->iter] = st->relres;
+      if (st->relres <= st->tol) {
+        st->done = 1;
+        st->converged = 1;
+      } else if (st->iter >= st->maxit) {
+        st->done = 1;
+      }
+      break;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_finalize(const FinArgs F) {
+  const bool iterative = F.what == FIN_MINRES_ALPHA || F.what == FIN_MINRES_BETA || F.what == FIN_CG_PAP ||
+                         F.what == FIN_CG_RHO;
+  if (iterative && (F.st->done || F.st->iter != F.host_iter - 1)) return;
+  __shared__ double sm[32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (F.stage != 2) {
+    // level 2: one warp per group, each lane a fixed run of consecutive chunk partials
+    const int per = (F.cpg + 31) / 32;
+    for (int64_t g = w; g < F.n_groups_local; g += 32) {
+      const int64_t base = g * F.cpg;
+      double s = 0.0;
+      for (int t = 0; t < per; t++) {
+        const int k = l * per + t;
+        if (k < F.cpg && base + k < F.n_chunks) s += F.partials[base + k];
+      }
+      s = warp_sum(s);
+      if (l == 0) F.gsend[F.group_begin + g] = s;
+    }
+    if (F.stage == 1) return;
+    __syncthreads();
+  }
+  // level 3: fixed tree over the (<= 1024) group sums of the whole mesh
+  const double *gs = F.stage == 2 ? F.grecv : F.gsend;
+  double v = (int)threadIdx.x < F.n_groups_global ? gs[threadIdx.x] : 0.0;
+  v = warp_sum(v);
+  if (l == 0) sm[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double t = sm[l];
+    t = warp_sum(t);
+    if (l == 0) fin_scalars(F, t);
+  }
+}
+
+void finalize(Ctx *ctx, int which_partials, int what, int host_iter, double tol, int maxit, double *out) {
+  FinArgs F;
+  F.partials = ctx->partials.p + which_partials * ctx->n_chunks;
+  F.n_chunks = ctx->n_chunks;
+  F.cpg = ctx->chunks_per_group;
+  F.group_begin = ctx->group_begin;
+  F.n_groups_local = ctx->n_groups_local;
+  F.n_groups_global = (int)ctx->n_groups_global;
+  F.gsend = ctx->group_sums.p;
+  F.grecv = ctx->group_sums.p + MAX_GROUPS;
+  F.st = ctx->kstate.p;
+  F.out = out;
+  F.hist = ctx->hist.p;
+  F.what = what;
+  F.host_iter = host_iter;
+  F.tol = tol;
+  F.maxit = maxit;
+  if (ctx->nranks == 1) {
+    F.stage = 0;
+    KLAUNCH(ctx, k_finalize, 1, 1024, F);
+  } else {
+    F.stage = 1;
+    KLAUNCH(ctx, k_finalize, 1, 1024, F);
+    comm_allreduce_sum(ctx, F.gsend, ctx->group_sums.p + MAX_GROUPS, ctx->n_groups_global);
+    F.stage = 2;
+    KLAUNCH(ctx, k_finalize, 1, 1024, F);
+  }
+}
+
+ApplyArgs base_args(Ctx *ctx, const double2 *val, const double2 *x, double2 *y) {
+  ApplyArgs A;
+  memset(&A, 0, sizeof(A));
+  A.No = ctx->No;
+  A.nslices = ctx->nslices;
+  A.rowptr = ctx->rowptr.p;
+  A.slice_off = ctx->slice_off.p;
+  A.col = ctx->col.p;
+  A.val = val;
+  A.x = x;
+  A.y = y;
+  A.a = 1.0;
+  A.b = 0.0;
+  A.st = ctx->kstate.p;
+  A.partials = ctx->partials.p;
+  return A;
+}
+
+void op_args(Ctx *ctx, int op, ApplyArgs &A, int *epi) {
+  if (!ctx->keo_filled) NOSH_THROW(NOSH_ESTATE, "KEO not filled (call nosh_keo_fill / nosh_jac_rebuild first)");
+  A.val = ctx->Kval.p;
+  switch (op) {
+    case NOSH_OP_JACOBIAN:
+      if (!ctx->jac_ok) NOSH_THROW(NOSH_ESTATE, "Jacobian not built (call nosh_jac_rebuild first)");
+      A.d0 = ctx->jd0.p;
+      A.d1 = ctx->jd1.p;
+      *epi = EPI_DIAG;
+      break;
+    case NOSH_OP_KEO:
+      *epi = EPI_NONE;
+      break;
+    case NOSH_OP_KEOREG:
+      if (!ctx->keoreg_ok) NOSH_THROW(NOSH_ESTATE, "regularised KEO not built (call nosh_keoreg_rebuild first)");
+      A.d0 = ctx->pd0.p;
+      A.d1 = ctx->pd1.p;
+      *epi = EPI_DIAG;
+      break;
+    default:
+      NOSH_THROW(NOSH_EINVAL, "unknown operator id %d", op);
+  }
+}
+
+int poll_done(Ctx *ctx, KrylovState *host) {
+  CUDA_CHECK(cudaMemcpyAsync(host, ctx->kstate.p, sizeof(KrylovState), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return host->done;
+}
+
+}  // namespace
+
+void ensure_work(Ctx *ctx) {
+  if (!ctx->has_mesh) NOSH_THROW(NOSH_ESTATE, "no mesh set");
+  const int64_t n = ctx->Nl > 0 ? ctx->Nl : 1;
+  for (auto &w : ctx->work)
+    if (w.n < (size_t)n) {
+      w.alloc(n);
+      CUDA_CHECK(cudaMemsetAsync(w.p, 0, sizeof(double2) * n, ctx->stream));
+    }
+  ctx->n_chunks = cdiv(ctx->No, CHUNK);
+  ctx->partials.ensure(2 * (ctx->n_chunks > 0 ? ctx->n_chunks : 1));
+  if (!ctx->group_sums.p) {
+    ctx->group_sums.alloc(2 * MAX_GROUPS);
+    CUDA_CHECK(cudaMemsetAsync(ctx->group_sums.p, 0, sizeof(double) * 2 * MAX_GROUPS, ctx->stream));
+  }
+  if (!ctx->kstate.p) ctx->kstate.alloc(1);
+  if (!ctx->scalar_out.p) ctx->scalar_out.alloc(8);
+}
+
+double dot_dev(Ctx *ctx, const double2 *x, const double2 *y) {
+  ensure_work(ctx);
+  if (ctx->n_chunks) KLAUNCH(ctx, k_dot, (unsigned)ctx->n_chunks, TPB, x, y, ctx->No, ctx->partials.p);
+  finalize(ctx, 0, FIN_DOT, 0, 0.0, 0, ctx->scalar_out.p);
+  double h;
+  CUDA_CHECK(cudaMemcpyAsync(&h, ctx->scalar_out.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return h;
+}
+
+void jac_diags_dev(Ctx *ctx, double g, const double2 *psi) {
+  ctx->jd0.ensure(ctx->No);
+  ctx->jd1.ensure(ctx->No);
+  if (ctx->No)
+    KLAUNCH(ctx, k_jac_diags, (unsigned)cdiv(ctx->No, 256), 256, g, ctx->cv.p, ctx->thick.p, ctx->Vcur.p, psi,
+            ctx->No, ctx->jd0.p, ctx->jd1.p);
+  ctx->jac_ok = true;
+}
+
+void keoreg_diags_dev(Ctx *ctx, double g, const double2 *psi) {
+  ctx->pd0.ensure(ctx->No);
+  ctx->pd1.ensure(ctx->No);
+  if (ctx->No)
+    KLAUNCH(ctx, k_keoreg_diags, (unsigned)cdiv(ctx->No, 256), 256, g, ctx->cv.p, ctx->thick.p, psi, ctx->No,
+            ctx->pd0.p, ctx->pd1.p);
+  ctx->keoreg_ok = true;
+}
+
+void axpy_dev(Ctx *ctx, double a, const double2 *x, double2 *y) {
+  if (ctx->No) KLAUNCH(ctx, k_axpy, (unsigned)cdiv(ctx->No, 256), 256, a, x, y, ctx->No);
+}
+
+// y = op(x) with the plain/diag epilogues; x must have Nl entries when nranks > 1
+void apply_op_dev(Ctx *ctx, int op, double2 *x, double2 *y) {
+  ensure_work(ctx);
+  ApplyArgs A = base_args(ctx, nullptr, x, y);
+  int epi;
+  op_args(ctx, op, A, &epi);
+  halo_exchange(ctx, x);
+  launch_apply(ctx, epi, FUSE_NONE, A);
+}
+
+// F(psi) = K psi + c t (V + g |psi|^2) psi   (nls::compute_f_)
+void compute_f_dev(Ctx *ctx, double g, double2 *psi, double2 *f) {
+  ensure_work(ctx);
+  ApplyArgs A = base_args(ctx, ctx->Kval.p, psi, f);
+  A.cv = ctx->cv.p;
+  A.thick = ctx->thick.p;
+  A.V = ctx->Vcur.p;
+  A.g = g;
+  halo_exchange(ctx, psi);
+  launch_apply(ctx, EPI_F, FUSE_NONE, A);
+}
+
+void minres_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_out, double tol, int maxit,
+                nosh_krylov_result *res, double *hist_host) {
+  ensure_work(ctx);
+  if (maxit < 0) NOSH_THROW(NOSH_EINVAL, "maxit < 0");
+  ApplyArgs A = base_args(ctx, nullptr, nullptr, nullptr);
+  int epi;
+  op_args(ctx, op, A, &epi);
+  ctx->hist.ensure((size_t)maxit + 2);
+  double2 *R[2] = {ctx->work[0].p, ctx->work[1].p};
+  double2 *Pv = ctx->work[2].p;
+  double2 *W[3] = {ctx->work[3].p, ctx->work[4].p, ctx->work[5].p};
+  double2 *X = x_out;
+  const unsigned grid = (unsigned)ctx->n_chunks;
+  const int64_t No = ctx->No;
+  if (grid) KLAUNCH(ctx, k_minres_init, grid, TPB, b, bscale, No, R[0], W[0], W[1], W[2], X, ctx->partials.p);
+  finalize(ctx, 0, FIN_MINRES_INIT, 0, tol, maxit, nullptr);
+  KrylovState hs;
+  int check = 4;
+  for (int h = 1; h <= maxit; h++) {
+    double2 *rcur = R[(h - 1) & 1], *rprev = R[h & 1];
+    // A: y = J v - (beta/oldBeta) r_prev, partials <v,y>
+    halo_exchange(ctx, rcur);
+    A.x = rcur;
+    A.y = Pv;
+    A.r1 = rprev;
+    A.host_iter = h;
+    A.partials = ctx->partials.p;
+    launch_apply(ctx, epi, FUSE_MINRES, A);
+    finalize(ctx, 0, FIN_MINRES_ALPHA, h, tol, maxit, nullptr);
+    // B: r_next = y - (alpha/beta) r_cur  (written over r_prev)
+    if (grid) KLAUNCH(ctx, k_minres_B, grid, TPB, ctx->kstate.p, h, Pv, rcur, rprev, No, ctx->partials.p);
+    finalize(ctx, 0, FIN_MINRES_BETA, h, tol, maxit, nullptr);
+    // C: w_h, x
+    if (grid)
+      KLAUNCH(ctx, k_minres_C, grid, TPB, ctx->kstate.p, h, rcur, W[(h + 1) % 3], W[(h + 2) % 3], W[h % 3], X, No);
+    if (h % check == 0 || h == maxit) {
+      if (poll_done(ctx, &hs)) break;
+      if (check < 32) check *= 2;
+    }
+  }
+  poll_done(ctx, &hs);
+  if (res) {
+    res->iterations = hs.iter;
+    res->converged = hs.converged;
+    res->relres = hs.relres;
+  }
+  if (hist_host) {
+    CUDA_CHECK(cudaMemcpyAsync(hist_host, ctx->hist.p, sizeof(double) * (hs.iter + 1), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+}
+
+void cg_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_out, double tol, int maxit,
+            nosh_krylov_result *res, double *hist_host) {
+  ensure_work(ctx);
+  if (maxit < 0) NOSH_THROW(NOSH_EINVAL, "maxit < 0");
+  ApplyArgs A = base_args(ctx, nullptr, nullptr, nullptr);
+  int epi;
+  op_args(ctx, op, A, &epi);
+  ctx->hist.ensure((size_t)maxit + 2);
+  double2 *Rv = ctx->work[0].p, *Pd = ctx->work[1].p, *AP = ctx->work[2].p, *X = x_out;
+  const unsigned grid = (unsigned)ctx->n_chunks;
+  const int64_t No = ctx->No;
+  if (grid) KLAUNCH(ctx, k_cg_init, grid, TPB, b, bscale, No, Rv, Pd, X, ctx->partials.p);
+  finalize(ctx, 0, FIN_CG_INIT, 0, tol, maxit, nullptr);
+  KrylovState hs;
+  int check = 4;
+  for (int h = 1; h <= maxit; h++) {
+    halo_exchange(ctx, Pd);
+    A.x = Pd;
+    A.y = AP;
+    A.host_iter = h;
+    launch_apply(ctx, epi, FUSE_CG, A);
+    finalize(ctx, 0, FIN_CG_PAP, h, tol, maxit, nullptr);
+    if (grid) KLAUNCH(ctx, k_cg_update, grid, TPB, ctx->kstate.p, h, Pd, AP, Rv, X, No, ctx->partials.p);
+    finalize(ctx, 0, FIN_CG_RHO, h, tol, maxit, nullptr);
+    if (grid) KLAUNCH(ctx, k_cg_direction, grid, TPB, ctx->kstate.p, h, Rv, Pd, No);
+    if (h % check == 0 || h == maxit) {
+      if (poll_done(ctx, &hs)) break;
+      if (check < 32) check *= 2;
+    }
+  }
+  poll_done(ctx, &hs);
+  if (res) {
+    res->iterations = hs.iter;
+    res->converged = hs.converged;
+    res->relres = hs.relres;
+  }
+  if (hist_host) {
+    CUDA_CHECK(cudaMemcpyAsync(hist_host, ctx->hist.p, sizeof(double) * (hs.iter + 1), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+}
+
+// Newton, full step.  psi: device vector with Nl entries, updated in place.
+void newton_dev(Ctx *ctx, int np, const char *const *names, const double *values, double2 *psi, double nl_tol,
+                int nl_maxit, double lin_tol, int lin_maxit, nosh_newton_result *res, int32_t *lin_iters,
+                double *fnorms) {
+  ensure_work(ctx);
+  const double g = param_at(np, names, values, "g");
+  keo_fill(ctx, np, names, values, false);
+  update_potential(ctx, np, names, values);
+  double2 *F = ctx->work[6].p, *D = ctx->work[7].p;
+  int k = 0, total = 0;
+  compute_f_dev(ctx, g, psi, F);
+  double fn = sqrt(dot_dev(ctx, F, F));
+  if (fnorms) fnorms[0] = fn;
+  while (k < nl_maxit && !(fn < nl_tol)) {
+    // evalModel(W_op): jacobian_operator::rebuild (KEO refill is a cache hit) + diagonals
+    jac_diags_dev(ctx, g, psi);
+    nosh_krylov_result kr;
+    minres_dev(ctx, NOSH_OP_JACOBIAN, F, -1.0, D, lin_tol, lin_maxit, &kr, nullptr);
+    if (lin_iters) lin_iters[k] = kr.iterations;
+    total += kr.iterations;
+    axpy_dev(ctx, 1.0, D, psi);
+    compute_f_dev(ctx, g, psi, F);
+    fn = sqrt(dot_dev(ctx, F, F));
+    k++;
+    if (fnorms) fnorms[k] = fn;
+  }
+  if (res) {
+    res->steps = k;
+    res->converged = fn < nl_tol;
+    res->total_linear_iterations = total;
+    res->fnorm = fn;
+  }
+}
+
+}  // namespace nosh

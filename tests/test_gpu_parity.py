@@ -1,0 +1,374 @@
+"""GPU parity: every entry point of the C ABI against the CPU oracle on identical inputs.
+
+Tolerances (north_star: "F(psi), J.x and KEO entries within 1e-12 relative in fp64, Newton/
+MINRES iteration counts identical"):
+  * integer / index work (edges, cells, graph columns): bit-exact
+  * synthetic coordinates: bit-exact (device generator vs numpy restatement)
+  * fp64 vectors and matrix entries: max|gpu-oracle| <= 1e-12 * max|oracle|  (norm-wise
+    relative; the oracle and the device sum rows in different orders)
+  * iteration counts: identical
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def relerr(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    s = np.abs(b).max()
+    return np.abs(a - b).max() / (s if s > 0 else 1.0)
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import nosh_b200
+    return nosh_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    import oracle
+    return oracle
+
+
+LAYOUTS = [0, 1]
+PARAMS = {"g": 1.0, "mu": 0.01}
+
+
+def make_pair(nb, orc, coords, cells, layout, mvp="explicit", V=-1.0, thickness=1.0, group=None):
+    psi, A = orc.meshgen.plain_gl_fields(coords)
+    ctx = nb.Context(layout=layout, group_vertices=group)
+    ctx.mesh_set(coords, cells)
+    N = coords.shape[0]
+    t = None if np.isscalar(thickness) else thickness
+    ctx.set_thickness(t, thickness if t is None else 1.0)
+    ctx.set_potential_constant(V)
+    if mvp == "explicit":
+        ctx.set_mvp_explicit(A)
+        P = orc.OracleProblem(coords, cells, ("explicit", A), V=V, thickness=thickness)
+    elif mvp == "curl":
+        ctx.set_mvp_explicit_curl((0.0, 0.0, 1.0))
+        P = orc.OracleProblem(coords, cells, ("explicit", A), V=V, thickness=thickness)
+    else:
+        b, u = mvp
+        ctx.set_mvp_constcurl(b, u)
+        P = orc.OracleProblem(coords, cells, ("constcurl", b, u), V=V, thickness=thickness)
+    assert N == P.N
+    return ctx, P, psi
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("name", ["rectanglesmall", "cubesmall"])
+def test_reference_fixtures(nb, orc, golden, name, layout):
+    """The reference's own known answers, through the C ABI on the GPU."""
+    coords, cells = getattr(orc.meshgen, name)()
+    ctx, P, psi = make_pair(nb, orc, coords, cells, layout)
+    g = golden[name]
+    mi = ctx.info()
+    assert mi.n_owned == g["mesh"]["num_nodes"] and mi.n_ghost == 0
+    cv = ctx.control_volumes()
+    assert np.abs(cv).sum() == pytest.approx(g["mesh"]["cv_norm1"], rel=1e-13)
+    assert np.linalg.norm(cv) == pytest.approx(g["mesh"]["cv_norm2"], rel=1e-13)
+    assert np.abs(cv).max() == pytest.approx(g["mesh"]["cv_norminf"], rel=1e-13)
+    N = mi.n_owned
+    one = np.ones(2 * N)
+    er = np.zeros(2 * N)
+    er[0::2] = 1
+    ei = np.zeros(2 * N)
+    ei[1::2] = 1
+    ctx.keo_fill({"mu": 0.01})
+    assert one @ ctx.keo_apply(one) == pytest.approx(g["keo"]["sum"], rel=1e-9)
+    assert er @ ctx.keo_apply(er) == pytest.approx(g["keo"]["sum_real"], rel=1e-9)
+    assert abs(er @ ctx.keo_apply(ei)) < 1e-15
+    f = ctx.compute_f(PARAMS, psi)
+    assert np.abs(f).sum() == pytest.approx(g["compute_f"]["norm1"], rel=1e-9)
+    assert np.linalg.norm(f) == pytest.approx(g["compute_f"]["norm2"], rel=1e-9)
+    assert np.abs(f).max() == pytest.approx(g["compute_f"]["norminf"], rel=1e-9)
+    ctx.jac_rebuild(PARAMS, psi)
+    assert one @ ctx.jac_apply(one) == pytest.approx(g["jac"]["t0"], rel=1e-12)
+    assert er @ ctx.jac_apply(er) == pytest.approx(g["jac"]["t1"], rel=1e-12)
+    assert ei @ ctx.jac_apply(ei) == pytest.approx(g["jac"]["t2"], rel=1e-9)
+    ctx.close()
+
+
+@pytest.mark.parametrize("n", [5, 12])
+def test_tetgrid_generator_bit_exact(nb, orc, n):
+    ctx = nb.Context()
+    mi = ctx.mesh_tetgrid(n, n + 1, n + 2, jitter=0.2, seed=1234)
+    coords, cells = orc.meshgen.tetgrid(n, n + 1, n + 2, jitter=0.2, seed=1234)
+    assert mi.n_owned == coords.shape[0] and mi.n_cells == cells.shape[0]
+    assert np.array_equal(ctx.coords(), coords)
+    assert np.array_equal(ctx.cells(), cells)
+    assert np.array_equal(ctx.local_gids(), np.arange(coords.shape[0]))
+    ctx.close()
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("mesh", ["tet7", "tet16", "tri"])
+def test_geometry_and_structure(nb, orc, mesh, layout):
+    if mesh == "tri":
+        coords, cells = orc.meshgen.trigrid(23, 7)
+    else:
+        coords, cells = orc.meshgen.tetgrid(int(mesh[3:]))
+    t = 1.0 + 0.3 * np.sin(coords[:, 0]) * np.cos(coords[:, 1])
+    ctx, P, psi = make_pair(nb, orc, coords, cells, layout, thickness=t)
+    e, ln, cov = ctx.edges()
+    assert np.array_equal(e, P.edges)                       # a1: bit-exact
+    assert relerr(ln, P.length) <= 1e-15                    # a2
+    assert relerr(cov, P.covolume) <= RTOL
+    assert relerr(ctx.control_volumes(), P.cv) <= RTOL      # a3
+    assert relerr(ctx.alpha_cache(), P.alpha) <= RTOL       # a8
+    a, da = ctx.edge_projection({"mu": 0.37}, "mu")         # a5
+    ao, dao = P.edge_projection(0.37, 0.0, "mu")
+    assert relerr(a, ao) <= RTOL and relerr(da, dao) <= RTOL
+    rp, cols, _ = ctx.block_csr(values=False)               # a4: bit-exact graph
+    P.keo_fill(0.37)
+    orp, ocols, oK = P.complex_blocks(P.vals)
+    assert np.array_equal(rp, orp) and np.array_equal(cols, ocols)
+    ctx.keo_fill({"mu": 0.37})                              # a9: entry-wise
+    _, _, K = ctx.block_csr()
+    assert relerr(K, oK) <= RTOL
+    ctx.dkeo_fill({"mu": 0.37}, "mu")                       # a10
+    _, _, dK = ctx.block_csr(nb.MAT_DKEO)
+    P.dkeo_fill(0.37, 0.0, "mu")
+    _, _, odK = P.complex_blocks(P.dvals)
+    assert relerr(dK, odK) <= RTOL
+    ctx.close()
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_operators(nb, orc, layout):
+    coords, cells = orc.meshgen.tetgrid(14)
+    ctx, P, psi = make_pair(nb, orc, coords, cells, layout, mvp="curl")
+    N = P.N
+    par = {"g": 1.3, "mu": 0.8}
+    x = orc.meshgen.random_state(N, 42)
+    y = orc.meshgen.random_state(N, 7)
+    P.keo_fill(par["mu"])
+    ctx.keo_fill(par)
+    # a19: K x, and the general alpha/beta contract of CrsMatrix::apply
+    assert relerr(ctx.keo_apply(x), P.keo_apply(x)) <= RTOL
+    y2 = y.copy()
+    ctx.keo_apply(x, y2, alpha=-0.5, beta=2.0)
+    assert relerr(y2, -0.5 * P.keo_apply(x) + 2.0 * y) <= RTOL
+    # a13: F
+    assert relerr(ctx.compute_f(par, x), P.compute_f(par["g"], x)) <= RTOL
+    # a12 + a11: J
+    ctx.jac_rebuild(par, x)
+    P.jac_rebuild(par["g"], x)
+    d0, d1 = ctx.jac_diags()
+    assert relerr(d0, P.d0) <= 1e-14 and relerr(d1, P.d1b) <= 1e-14
+    assert relerr(ctx.jac_apply(y), P.jac_apply(y)) <= RTOL
+    X = np.stack([x, y, x - y])          # 3 columns of a column-major multi-vector
+    assert relerr(ctx.jac_apply(X), P.jac_apply(X)) <= RTOL
+    # symmetry of J in the real inner product
+    assert x @ ctx.jac_apply(y) == pytest.approx(y @ ctx.jac_apply(x), rel=1e-12)
+    # a14: dF/dp for g and mu
+    P.dkeo_fill(par["mu"], 0.0, "g")
+    assert relerr(ctx.compute_dfdp(par, "g", x), P.compute_dfdp(x, True)) <= RTOL
+    P.dkeo_fill(par["mu"], 0.0, "mu")
+    assert relerr(ctx.compute_dfdp(par, "mu", x), P.compute_dfdp(x, False, np.zeros(N))) <= RTOL
+    # a16: regularised KEO = K + diagonal blocks
+    ctx.keoreg_rebuild(par, x)
+    pv = P.keoreg_fill(par["mu"], par["g"], x)
+    assert relerr(ctx.keoreg_matrix_apply(y), P.csr_apply(pv, y)) <= RTOL
+    # reductions
+    assert ctx.dot(x, y) == pytest.approx(x @ y, rel=1e-13)
+    assert ctx.norm2(x) == pytest.approx(np.linalg.norm(x), rel=1e-13)
+    ctx.close()
+
+
+def test_constcurl_field(nb, orc):
+    coords, cells = orc.meshgen.tetgrid(9)
+    b, u = (0.0, 0.0, 1.0), (1.0, 0.0, 0.0)
+    ctx, P, psi = make_pair(nb, orc, coords, cells, 1, mvp=(b, u))
+    par = {"g": 1.0, "mu": 0.6, "theta": 0.4}
+    for dn in ("mu", "theta"):
+        a, da = ctx.edge_projection(par, dn)
+        ao, dao = P.edge_projection(par["mu"], par["theta"], dn)
+        assert relerr(a, ao) <= RTOL and relerr(da, dao) <= RTOL
+    ctx.keo_fill(par)
+    P.keo_fill(par["mu"], par["theta"])
+    _, _, K = ctx.block_csr()
+    _, _, oK = P.complex_blocks(P.vals)
+    assert relerr(K, oK) <= RTOL
+    ctx.dkeo_fill(par, "theta")
+    P.dkeo_fill(par["mu"], par["theta"], "theta")
+    _, _, dK = ctx.block_csr(nb.MAT_DKEO)
+    _, _, odK = P.complex_blocks(P.dvals)
+    assert relerr(dK, odK) <= RTOL
+    with pytest.raises(ValueError):      # constant_curl.cpp:135-139 throws on unknown names
+        ctx.dkeo_fill(par, "g")
+    with pytest.raises(KeyError):        # params.at("theta")
+        ctx.keo_fill({"mu": 1.0})
+    with pytest.raises(ValueError):      # not normalised (:35-38)
+        ctx.set_mvp_constcurl((0.0, 0.0, 2.0))
+    ctx.close()
+
+
+def test_potential_parameter_and_values(nb, orc):
+    coords, cells = orc.meshgen.tetgrid(8)
+    psi, A = orc.meshgen.plain_gl_fields(coords)
+    N = coords.shape[0]
+    x = orc.meshgen.random_state(N, 5)
+    P = orc.OracleProblem(coords, cells, ("explicit", A), V=-1.0)
+    P.keo_fill(0.2)
+    ctx = nb.Context()
+    ctx.mesh_set(coords, cells)
+    ctx.set_thickness(None, 1.0)
+    ctx.set_mvp_explicit(A)
+    # scalar_field::constant(mesh, -1, "T", 0): V = -1 + T, dV/dT = 1
+    ctx.set_potential_constant(-1.0, "T")
+    par = {"g": 1.0, "mu": 0.2, "T": 0.25}
+    assert relerr(ctx.compute_f(par, x), P.compute_f(1.0, x, V=np.full(N, -0.75))) <= RTOL
+    P.dkeo_fill(0.2, 0.0, "T")
+    assert relerr(ctx.compute_dfdp(par, "T", x), P.compute_dfdp(x, False, np.ones(N))) <= RTOL
+    # scalar_field::explicit_values: V = beta * values
+    vals = np.cos(coords[:, 2])
+    ctx.set_potential_values(vals)
+    par = {"g": 1.0, "mu": 0.2, "beta": 1.5}
+    assert relerr(ctx.compute_f(par, x), P.compute_f(1.0, x, V=1.5 * vals)) <= RTOL
+    assert relerr(ctx.compute_dfdp(par, "beta", x), P.compute_dfdp(x, False, vals)) <= RTOL
+    with pytest.raises(KeyError):
+        ctx.compute_f({"g": 1.0, "mu": 0.2}, x)
+    ctx.close()
+
+
+def test_error_contract(nb, orc):
+    coords, cells = orc.meshgen.cubesmall()
+    ctx, P, psi = make_pair(nb, orc, coords, cells, 1)
+    with pytest.raises(nb.NoshError):          # apply before rebuild
+        ctx.jac_apply(psi)
+    ctx.jac_rebuild(PARAMS, psi)
+    for kw in ({"mode": nb.TRANS}, {"alpha": 2.0}, {"beta": 1.0}):   # jacobian_operator.cpp:48-59
+        with pytest.raises(ValueError):
+            ctx.jac_apply(psi, **kw)
+    with pytest.raises(KeyError):              # params.at("g")
+        ctx.jac_rebuild({"mu": 0.01}, psi)
+    with pytest.raises(nb.NoshError):          # MueLu V-cycle: out of scope, says so
+        ctx.keoreg_apply(psi)
+    # a flat tetrahedron is rejected like the reference does (mesh_tetra.cpp:359-372)
+    bad = coords.copy()
+    bad[:, 2] *= 1e-9
+    c2 = nb.Context()
+    with pytest.raises(nb.NoshError):
+        c2.mesh_set(bad, cells)
+    c2.close()
+    ctx.close()
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_minres_cg_iteration_counts(nb, orc, layout):
+    coords, cells = orc.meshgen.tetgrid(12)
+    ctx, P, psi = make_pair(nb, orc, coords, cells, layout, group=512)
+    par = {"g": 1.0, "mu": 0.5}
+    x0 = orc.meshgen.random_state(P.N, 3)
+    b = orc.meshgen.random_state(P.N, 4)
+    P.keo_fill(par["mu"])
+    P.jac_rebuild(par["g"], x0)
+    ctx.jac_rebuild(par, x0)
+    for tol in (1e-6, 1e-10):
+        xo, ito, rro, ho = P.krylov(b, tol, 3000, history=True)
+        xg, res, hg = ctx.minres(b, tol=tol, maxit=3000, history=True)
+        assert res.converged == 1
+        assert res.iterations == ito                      # identical iteration count
+        assert relerr(hg, ho) <= 1e-6                     # same residual history
+        assert relerr(xg, xo) <= 1e-8
+        assert np.linalg.norm(P.jac_apply(xg) - b) / np.linalg.norm(b) <= 10 * tol
+    # maxit cap
+    xg, res = ctx.minres(b, tol=1e-14, maxit=17)
+    xo, ito, _ = P.krylov(b, 1e-14, 17)
+    assert res.iterations == 17 == ito and res.converged == 0
+    assert relerr(xg, xo) <= 1e-10
+    # KEO alone (singular-free here: mu != 0) with CG, the live reference default
+    xo, ito, _ = P.krylov(b, 1e-8, 3000, solver="cg", jacobian=False)
+    xg, res = ctx.cg(b, op=nb.OP_KEO, tol=1e-8, maxit=3000)
+    assert res.iterations == ito and res.converged == 1
+    assert relerr(xg, xo) <= 1e-8
+    # zero right-hand side
+    xg, res = ctx.minres(np.zeros(2 * P.N), tol=1e-10, maxit=10)
+    assert res.iterations == 0 and np.all(xg == 0)
+    ctx.close()
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_newton(nb, orc, layout):
+    coords, cells = orc.meshgen.tetgrid(10)
+    ctx, P, psi = make_pair(nb, orc, coords, cells, layout, group=512)
+    par = {"g": 1.0, "mu": 0.1}
+    P.keo_fill(par["mu"])
+    xo, steps, lin, fn = P.newton(par["g"], psi, 1e-8, 20, 1e-10, 3000)
+    x = psi.copy()
+    res, glin, gfn = ctx.newton(par, x, 1e-8, 20, 1e-10, 3000)
+    assert res.converged == 1
+    assert res.steps == steps                               # identical Newton count
+    assert list(glin) == list(lin)                          # identical MINRES counts per step
+    assert relerr(gfn[:-1], fn[:-1]) <= 1e-6
+    assert relerr(x, xo) <= 1e-8
+    assert np.linalg.norm(P.compute_f(par["g"], x)) < 1e-8
+    ctx.close()
+
+
+def test_device_pointers_in_place(nb, orc):
+    """torch CUDA tensors are used in place (no staging) and give the same bits as host vectors."""
+    import torch
+    coords, cells = orc.meshgen.tetgrid(10)
+    ctx, P, psi = make_pair(nb, orc, coords, cells, 1)
+    par = {"g": 1.0, "mu": 0.3}
+    x = orc.meshgen.random_state(P.N, 11)
+    ctx.jac_rebuild(par, x)
+    yh = ctx.jac_apply(x)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    ctx.jac_apply(xd, yd)
+    ctx.synchronize()
+    assert np.array_equal(yd.cpu().numpy(), yh)
+    fd = ctx.compute_f(par, xd)
+    ctx.synchronize()
+    assert np.array_equal(fd.cpu().numpy(), ctx.compute_f(par, x))
+    ctx.close()
+
+
+def test_layouts_agree_bitwise_on_structure(nb, orc):
+    coords, cells = orc.meshgen.tetgrid(9)
+    outs = []
+    for layout in LAYOUTS:
+        ctx, P, psi = make_pair(nb, orc, coords, cells, layout)
+        ctx.keo_fill({"mu": 0.4})
+        outs.append(ctx.block_csr())
+        mi = ctx.info()
+        assert mi.n_stored >= mi.n_blocks
+        ctx.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+
+
+def test_medium_mesh_parity(nb, orc):
+    """64k vertices: geometry, assembly, F, J.x against the oracle."""
+    coords, cells = orc.meshgen.tetgrid(40)
+    ctx = nb.Context()
+    ctx.mesh_tetgrid(40)
+    ctx.set_thickness(None, 1.0)
+    ctx.set_potential_constant(-1.0)
+    ctx.set_mvp_constcurl((0.0, 0.0, 1.0))
+    P = orc.OracleProblem(coords, cells, ("constcurl", (0.0, 0.0, 1.0), None), nthreads=8)
+    par = {"g": 1.0, "mu": 1.0, "theta": 0.0}
+    x = orc.meshgen.random_state(P.N, 42)
+    y = orc.meshgen.random_state(P.N, 43)
+    P.keo_fill(1.0)
+    ctx.keo_fill(par)
+    _, _, K = ctx.block_csr()
+    _, _, oK = P.complex_blocks(P.vals)
+    assert relerr(K, oK) <= RTOL
+    assert relerr(ctx.compute_f(par, x), P.compute_f(1.0, x)) <= RTOL
+    ctx.jac_rebuild(par, x)
+    P.jac_rebuild(1.0, x)
+    assert relerr(ctx.jac_apply(y), P.jac_apply(y)) <= RTOL
+    cv = ctx.control_volumes()
+    assert cv.sum() == pytest.approx(1000.0, rel=1e-12) and cv.min() > 0
+    ctx.close()
