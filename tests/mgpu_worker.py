@@ -1,0 +1,127 @@
+"""Multi-GPU parity worker (launched by torchrun, one rank per GPU; see test_multi_gpu.py).
+
+Checks, on a vertex-partitioned tetgrid with NCCL halo exchange and group-sum all-reduces:
+  * every rank's owned slice of cv / F / J.x / dF/dp matches the oracle on the GLOBAL mesh
+  * MINRES / CG / Newton iteration counts equal the oracle's
+  * partition independence: results are BIT-IDENTICAL to a single-GPU context on the same mesh
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import nosh_b200  # noqa: E402
+from oracle import OracleProblem, meshgen  # noqa: E402
+
+RTOL = 1e-12
+
+
+def relerr(a, b):
+    s = np.abs(b).max()
+    return np.abs(a - b).max() / (s if s > 0 else 1.0)
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = int(os.environ.get("NOSH_TEST_N", "20"))
+    group = 512
+    par = {"g": 1.0, "mu": 0.3, "theta": 0.0}
+
+    ctx = nosh_b200.Context(device=local, group_vertices=group)
+    obj = [nosh_b200.Context.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    ctx.comm_init(obj[0], rank, world)
+    mi = ctx.mesh_tetgrid(n, n, n + 3)
+    ctx.set_thickness(None, 1.0)
+    ctx.set_potential_constant(-1.0)
+    ctx.set_mvp_constcurl((0.0, 0.0, 1.0))
+    vb, No = int(mi.owned_begin), int(mi.n_owned)
+    sl = slice(2 * vb, 2 * (vb + No))
+    assert mi.n_ghost > 0 and No > 0, (mi.n_ghost, No)
+
+    coords, cells = meshgen.tetgrid(n, n, n + 3)
+    N = coords.shape[0]
+    assert mi.n_global == N
+    P = OracleProblem(coords, cells, ("constcurl", (0.0, 0.0, 1.0), None), nthreads=2)
+    gids = ctx.local_gids()
+    assert np.array_equal(gids[:No], np.arange(vb, vb + No))
+    assert np.array_equal(ctx.coords(), coords[gids])
+    assert relerr(ctx.control_volumes(), P.cv[vb:vb + No]) <= RTOL
+    # local edges <-> global edges
+    e, ln, cov = ctx.edges()
+    ge = gids[e]
+    key = ge[:, 0] * N + ge[:, 1]
+    okey = P.edges[:, 0].astype(np.int64) * N + P.edges[:, 1]
+    pos = np.searchsorted(okey, key)
+    assert np.array_equal(okey[pos], key)
+    assert relerr(cov, P.covolume[pos]) <= RTOL and relerr(ctx.alpha_cache(), P.alpha[pos]) <= RTOL
+
+    x = meshgen.random_state(N, 42)
+    y = meshgen.random_state(N, 43)
+    P.keo_fill(par["mu"])
+    P.jac_rebuild(par["g"], x)
+    ctx.keo_fill(par)
+    ctx.jac_rebuild(par, x[sl].copy())
+    F = ctx.compute_f(par, x[sl].copy())
+    Jy = ctx.jac_apply(y[sl].copy())
+    assert relerr(F, P.compute_f(par["g"], x)[sl]) <= RTOL
+    assert relerr(Jy, P.jac_apply(y)[sl]) <= RTOL
+    P.dkeo_fill(par["mu"], 0.0, "mu")
+    assert relerr(ctx.compute_dfdp(par, "mu", x[sl].copy()), P.compute_dfdp(x, False, np.zeros(N))[sl]) <= RTOL
+    d = ctx.dot(x[sl].copy(), y[sl].copy())
+    assert abs(d - x @ y) <= 1e-12 * abs(x @ y)
+
+    b = meshgen.random_state(N, 4)
+    xo, ito, _ = P.krylov(b, 1e-10, 3000)
+    xg, res = ctx.minres(b[sl].copy(), tol=1e-10, maxit=3000)
+    assert res.iterations == ito and res.converged == 1, (res.iterations, ito)
+    assert relerr(xg, xo[sl]) <= 1e-8
+    xo2, ito2, _ = P.krylov(b, 1e-8, 3000, solver="cg", jacobian=False)
+    xg2, res2 = ctx.cg(b[sl].copy(), op=nosh_b200.OP_KEO, tol=1e-8, maxit=3000)
+    assert res2.iterations == ito2, (res2.iterations, ito2)
+
+    psi0, _ = meshgen.plain_gl_fields(coords)
+    parn = {"g": 1.0, "mu": 0.1, "theta": 0.0}
+    P.keo_fill(parn["mu"])
+    xn, steps, lin, fn = P.newton(1.0, psi0, 1e-8, 20, 1e-10, 3000)
+    psi = psi0[sl].copy()
+    nres, glin, gfn = ctx.newton(parn, psi, 1e-8, 20, 1e-10, 3000)
+    assert nres.steps == steps and list(glin) == list(lin), (nres.steps, steps, glin, lin)
+    assert relerr(psi, xn[sl]) <= 1e-8
+
+    # ---- partition independence: bit-identical to one GPU -----------------------------------
+    single = nosh_b200.Context(device=local, group_vertices=group)
+    single.mesh_tetgrid(n, n, n + 3)
+    single.set_thickness(None, 1.0)
+    single.set_potential_constant(-1.0)
+    single.set_mvp_constcurl((0.0, 0.0, 1.0))
+    single.keo_fill(par)
+    single.jac_rebuild(par, x)
+    assert np.array_equal(single.compute_f(par, x)[sl], F)
+    assert np.array_equal(single.jac_apply(y)[sl], Jy)
+    assert single.dot(x, y) == d
+    xs, rs, hs = single.minres(b, tol=1e-10, maxit=3000, history=True)
+    ctx.keo_fill(par)                      # Newton above left mu=0.1 and its own Jacobian in ctx
+    ctx.jac_rebuild(par, x[sl].copy())
+    xg, res, hg = ctx.minres(b[sl].copy(), tol=1e-10, maxit=3000, history=True)
+    assert rs.iterations == res.iterations
+    assert np.array_equal(hs, hg), "residual history differs between 1 and %d GPUs" % world
+    assert np.array_equal(xs[sl], xg)
+    single.close()
+    ctx.close()
+    dist.barrier()
+    if rank == 0:
+        print("MGPU OK world=%d n=%d minres=%d newton=%s" % (world, n, ito, list(lin)))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
