@@ -86,6 +86,12 @@ NOSH_API nosh_status nosh_ctx_synchronize(nosh_ctx *ctx);
 /* ---- multi-GPU (one process per GPU).  Replaces Teuchos::MpiComm / Tpetra
  * Import / reduceAll (src/mesh_reader.cpp:53-57; Tpetra, not in tree). ---------- */
 NOSH_API nosh_status nosh_comm_unique_id(void *id128 /* 128 bytes out */);
+/* host-only helper (no GPU needed): the contiguous, group-aligned global vertex range
+ * [begin,end) owned by `rank` of `nranks`, and the group size actually used (the requested one
+ * doubled until at most 1024 groups cover the mesh).  This is the partition every ctx uses. */
+NOSH_API nosh_status nosh_partition_range(int64_t n_global, int nranks, int rank,
+                                          int64_t group_vertices, int64_t *begin, int64_t *end,
+                                          int64_t *group_used);
 NOSH_API nosh_status nosh_ctx_comm_init(nosh_ctx *ctx, const void *id128, int rank, int nranks);
 
 /* ---- mesh (a1-a3).  Replaces nosh::read + mesh_tetra/mesh_tri ctor:

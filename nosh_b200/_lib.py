@@ -73,6 +73,8 @@ def lib():
         "nosh_ctx_synchronize": (C.c_int, [vp]),
         "nosh_comm_unique_id": (C.c_int, [vp]),
         "nosh_ctx_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "nosh_partition_range": (C.c_int, [i64, C.c_int, C.c_int, i64, C.POINTER(i64), C.POINTER(i64),
+                                           C.POINTER(i64)]),
         "nosh_mesh_set": (C.c_int, [vp, C.c_int, i64, vp, i64, vp]),
         "nosh_mesh_tetgrid": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, dbl, C.c_uint64]),
         "nosh_mesh_info": (C.c_int, [vp, C.POINTER(MeshInfo)]),

@@ -41,6 +41,16 @@ def _params(p):
     return len(p), names, vals
 
 
+def partition_range(n_global, nranks, rank, group_vertices=65536):
+    """Host-only: (begin, end, group_used) of the vertex range `rank` owns."""
+    b, e, g = C.c_int64(), C.c_int64(), C.c_int64()
+    rc = _lib.lib().nosh_partition_range(int(n_global), int(nranks), int(rank), int(group_vertices),
+                                         C.byref(b), C.byref(e), C.byref(g))
+    if rc != 0:
+        raise ValueError("nosh_partition_range: bad arguments")
+    return b.value, e.value, g.value
+
+
 class Context:
     """One nosh_ctx: one process, one GPU."""
 

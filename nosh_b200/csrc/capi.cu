@@ -190,6 +190,15 @@ nosh_status nosh_comm_unique_id(void *id128) {
   return NOSH_OK;
 }
 
+nosh_status nosh_partition_range(int64_t n_global, int nranks, int rank, int64_t group_vertices, int64_t *begin,
+                                 int64_t *end, int64_t *group_used) {
+  if (n_global <= 0 || nranks < 1 || rank < 0 || rank >= nranks || group_vertices < CHUNK ||
+      group_vertices % CHUNK)
+    return NOSH_EINVAL;
+  partition_range(n_global, nranks, rank, group_vertices, begin, end, group_used, nullptr, nullptr, nullptr);
+  return NOSH_OK;
+}
+
 nosh_status nosh_ctx_comm_init(nosh_ctx *ctx, const void *id128, int rank, int nranks) {
   API_BEGIN(ctx)
   CUDA_CHECK(cudaSetDevice(ctx->device));

@@ -752,24 +752,35 @@ void build_from_cells(Ctx *ctx, DBuf<int32_t> &cellsG, int64_t ncand, const doub
 }  // namespace
 
 // ---- partition of the global vertex range into contiguous, group-aligned pieces -------------
+void partition_range(int64_t n_global, int nranks, int rank, int64_t group, int64_t *begin, int64_t *end,
+                     int64_t *group_used, int64_t *ngroups_out, int64_t *gbegin, int64_t *gcount) {
+  int64_t G = group;
+  while (cdiv(n_global, G) > MAX_GROUPS) G *= 2;
+  const int64_t ngroups = cdiv(n_global, G);
+  const int64_t g0 = ngroups * rank / nranks, g1 = ngroups * (rank + 1) / nranks;
+  if (begin) *begin = std::min(n_global, g0 * G);
+  if (end) *end = std::min(n_global, g1 * G);
+  if (group_used) *group_used = G;
+  if (ngroups_out) *ngroups_out = ngroups;
+  if (gbegin) *gbegin = g0;
+  if (gcount) *gcount = g1 - g0;
+}
+
 void setup_partition(Ctx *ctx, int64_t n_global) {
   if (n_global >= (int64_t)2147483647) NOSH_THROW(NOSH_EINVAL, "n_vertices must be < 2^31");
   ctx->n_global = n_global;
-  int64_t G = ctx->group_vertices;
-  while (cdiv(n_global, G) > MAX_GROUPS) G *= 2;
-  ctx->group_vertices = G;
-  const int64_t ngroups = cdiv(n_global, G);
-  ctx->n_groups_global = ngroups;
-  ctx->chunks_per_group = (int)(G / CHUNK);
   ctx->part_begin.assign(ctx->nranks + 1, 0);
-  for (int r = 0; r <= ctx->nranks; r++) {
-    const int64_t g = ngroups * r / ctx->nranks;
-    ctx->part_begin[r] = std::min(n_global, g * G);
+  int64_t G = 0;
+  for (int r = 0; r < ctx->nranks; r++) {
+    int64_t b, e;
+    partition_range(n_global, ctx->nranks, r, ctx->group_vertices, &b, &e, &G, nullptr, nullptr, nullptr);
+    ctx->part_begin[r] = b;
+    ctx->part_begin[r + 1] = e;
   }
-  ctx->vb = ctx->part_begin[ctx->rank];
-  ctx->ve = ctx->part_begin[ctx->rank + 1];
-  ctx->group_begin = ngroups * ctx->rank / ctx->nranks;
-  ctx->n_groups_local = ngroups * (ctx->rank + 1) / ctx->nranks - ctx->group_begin;
+  partition_range(n_global, ctx->nranks, ctx->rank, ctx->group_vertices, &ctx->vb, &ctx->ve, &G,
+                  &ctx->n_groups_global, &ctx->group_begin, &ctx->n_groups_local);
+  ctx->group_vertices = G;
+  ctx->chunks_per_group = (int)(G / CHUNK);
 }
 
 void mesh_from_host(Ctx *ctx, int dim, int64_t nv, const double *coords, int64_t ncells,

@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 namespace nosh {
+void partition_range(int64_t n_global, int nranks, int rank, int64_t group, int64_t *begin, int64_t *end,
+                     int64_t *group_used, int64_t *ngroups_out, int64_t *gbegin, int64_t *gcount);
 void setup_partition(Ctx *ctx, int64_t n_global);
 void mesh_from_host(Ctx *ctx, int dim, int64_t nv, const double *coords, int64_t ncells,
                     const int32_t *cells);

@@ -1,0 +1,466 @@
+// nosh.hpp -- C++ mirror of the reference's hot-path classes over the C ABI
+// (include/nosh_b200.h).  Same class names, constructor arguments, method names and error
+// behaviour as the reference, so that code written against
+//   nosh::parameter_matrix::keo        (src/parameter_matrix_keo.hpp:37-60)
+//   nosh::parameter_matrix::DkeoDP     (src/parameter_matrix_dkeo_dp.hpp)
+//   nosh::jacobian_operator            (src/jacobian_operator.hpp:26-65)
+//   nosh::keo_regularized              (src/keo_regularized.hpp:37-74)
+//   nosh::model_evaluator::nls         (src/model_evaluator_nls.hpp:59-167)
+//   nosh::scalar_field::constant / explicit_values, nosh::vector_field::explicit_values /
+//   constantCurl                       (src/scalar_field_*.hpp, src/vector_field_*.hpp)
+// compiles and runs with every operation executed by the sm_100a kernels.  No arithmetic
+// happens in this header: each method forwards to one C-ABI call.
+//
+// Differences, all forced by the device boundary and documented in DESIGN.md section 2:
+//  * a nosh::mesh owns ONE device context, hence one set of fields and one KEO buffer: the
+//    field objects handed to the first operator built on a mesh are bound to it (the
+//    reference shares one keo_ between the model evaluator and its Jacobian anyway,
+//    src/model_evaluator_nls.cpp:258-263)
+//  * meshes come from arrays or the synthetic generator (nosh::read needs MOAB)
+//  * the Thyra InArgs/OutArgs protocol is reduced to plain structs with the same members
+#pragma once
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/nosh_b200.h"
+#include "tpetra_shim.hpp"
+
+namespace nosh {
+
+// status -> the exception type the reference throws at the corresponding place
+inline void check(nosh_ctx *ctx, nosh_status st) {
+  if (st == NOSH_OK) return;
+  const std::string msg = nosh_last_error(ctx);
+  switch (st) {
+    case NOSH_EKEY: throw std::out_of_range(msg);        // std::map::at
+    case NOSH_EINVAL: throw std::logic_error(msg);       // TEUCHOS_TEST_FOR_EXCEPT_MSG
+    default: throw std::runtime_error(msg);              // moab_wrap / CUDA
+  }
+}
+
+struct param_list {
+  std::vector<const char *> names;
+  std::vector<double> values;
+  explicit param_list(const std::map<std::string, double> &m) {
+    for (const auto &kv : m) {
+      names.push_back(kv.first.c_str());
+      values.push_back(kv.second);
+    }
+  }
+  int size() const { return (int)names.size(); }
+};
+
+// ---------------------------------------------------------------------------------------
+class mesh {
+public:
+  // general mesh from arrays (coords: n x 3, cells: nc x (dim+1), 0-based)
+  mesh(int dim, const std::vector<double> &coords, const std::vector<int> &cells, int device = 0) {
+    create(device);
+    check(ctx_, nosh_mesh_set(ctx_, dim, (int64_t)coords.size() / 3, coords.data(),
+                              (int64_t)cells.size() / (dim + 1), cells.data()));
+    finish();
+  }
+  // synthetic structured tetrahedral grid
+  mesh(int nx, int ny, int nz, double jitter = 0.2, uint64_t seed = 1234, int device = 0) {
+    create(device);
+    const double lo[3] = {-5, -5, -5}, hi[3] = {5, 5, 5};
+    check(ctx_, nosh_mesh_tetgrid(ctx_, nx, ny, nz, lo, hi, jitter, seed));
+    finish();
+  }
+  ~mesh() { nosh_ctx_destroy(ctx_); }
+  mesh(const mesh &) = delete;
+  mesh &operator=(const mesh &) = delete;
+
+  nosh_ctx *ctx() const { return ctx_; }
+  std::shared_ptr<const Tpetra::Map<int, int>> map() const { return map_; }
+  std::shared_ptr<const Tpetra::Map<int, int>> complex_map() const { return complex_map_; }
+  // src/mesh.hpp:178: control volumes on the owned map
+  std::shared_ptr<const Tpetra::Vector<double, int, int>> control_volumes() const {
+    if (!cv_) {
+      auto v = std::make_shared<Tpetra::Vector<double, int, int>>(map_);
+      check(ctx_, nosh_mesh_get_control_volumes(ctx_, v->getDataNonConst()));
+      cv_ = v;
+    }
+    return cv_;
+  }
+  const nosh_mesh_info_t &info() const { return info_; }
+
+  // field binding (one field set per device context)
+  mutable const void *bound_thickness = nullptr, *bound_mvp = nullptr, *bound_potential = nullptr;
+
+private:
+  void create(int device) { if (nosh_ctx_create(device, nullptr, &ctx_) != NOSH_OK) throw std::runtime_error("nosh_ctx_create failed: no CUDA device (there is no CPU fallback)"); }
+  void finish() {
+    check(ctx_, nosh_mesh_info(ctx_, &info_));
+    map_ = std::make_shared<Tpetra::Map<int, int>>(info_.n_owned, info_.n_global, 1 + (int)info_.owned_begin);
+    complex_map_ = std::make_shared<Tpetra::Map<int, int>>(2 * info_.n_owned, 2 * info_.n_global,
+                                                           2 * (1 + (int)info_.owned_begin));
+  }
+  nosh_ctx *ctx_ = nullptr;
+  nosh_mesh_info_t info_;
+  std::shared_ptr<const Tpetra::Map<int, int>> map_, complex_map_;
+  mutable std::shared_ptr<const Tpetra::Vector<double, int, int>> cv_;
+};
+
+// ---------------------------------------------------------------------------------------
+namespace scalar_field {
+class base {
+public:
+  virtual ~base() = default;
+  virtual const std::map<std::string, double> get_scalar_parameters() const = 0;
+  virtual void bind_as_thickness(const mesh &m) const = 0;
+  virtual void bind_as_potential(const mesh &m) const = 0;
+};
+// src/scalar_field_constant.hpp: constant(mesh, c, param1_name = "", param1_init_value = 0)
+class constant : public base {
+public:
+  constant(const nosh::mesh &, double c, std::string param1_name = "", double param1_init_value = 0.0)
+      : c_(c), name_(std::move(param1_name)), init_(param1_init_value) {}
+  const std::map<std::string, double> get_scalar_parameters() const override {
+    std::map<std::string, double> m;
+    if (!name_.empty()) m[name_] = init_;
+    return m;
+  }
+  void bind_as_thickness(const mesh &m) const override { check(m.ctx(), nosh_set_thickness(m.ctx(), nullptr, c_)); }
+  void bind_as_potential(const mesh &m) const override {
+    check(m.ctx(), nosh_set_potential_constant(m.ctx(), c_, name_.empty() ? nullptr : name_.c_str()));
+  }
+
+private:
+  double c_;
+  std::string name_;
+  double init_;
+};
+// src/scalar_field_explicit_values.hpp, values given directly (local numbering)
+class explicit_values : public base {
+public:
+  explicit_values(const nosh::mesh &, std::vector<double> values) : v_(std::move(values)) {}
+  const std::map<std::string, double> get_scalar_parameters() const override { return {{"beta", 1.0}}; }
+  void bind_as_thickness(const mesh &m) const override { check(m.ctx(), nosh_set_thickness(m.ctx(), v_.data(), 0.0)); }
+  void bind_as_potential(const mesh &m) const override { check(m.ctx(), nosh_set_potential_values(m.ctx(), v_.data())); }
+
+private:
+  std::vector<double> v_;
+};
+}  // namespace scalar_field
+
+namespace vector_field {
+class base {
+public:
+  virtual ~base() = default;
+  virtual void set_parameters(const std::map<std::string, double> &params) = 0;
+  virtual const std::map<std::string, double> get_scalar_parameters() const = 0;
+  virtual void bind(const mesh &m) const = 0;
+};
+// src/vector_field_explicit_values.hpp: explicit_values(mesh, field_name, mu); the nodal
+// values (mesh tag "A" in the reference) are passed directly, n x 3
+class explicit_values : public base {
+public:
+  explicit_values(const nosh::mesh &, std::vector<double> A, double mu) : A_(std::move(A)), mu_(mu) {}
+  void set_parameters(const std::map<std::string, double> &p) override { mu_ = p.at("mu"); }
+  const std::map<std::string, double> get_scalar_parameters() const override { return {{"mu", mu_}}; }
+  void bind(const mesh &m) const override { check(m.ctx(), nosh_set_mvp_explicit(m.ctx(), A_.data())); }
+
+private:
+  std::vector<double> A_;
+  double mu_;
+};
+// src/vector_field_constant_curl.hpp: constantCurl(mesh, b, u)
+class constantCurl : public base {
+public:
+  constantCurl(const std::shared_ptr<nosh::mesh> &m, const std::vector<double> &b, const std::vector<double> &u = {})
+      : b_(b), u_(u) {
+    // normalisation is checked at construction like the reference (constant_curl.cpp:35-44)
+    check(m->ctx(), nosh_set_mvp_constcurl(m->ctx(), b_.data(), u_.empty() ? nullptr : u_.data()));
+    m->bound_mvp = this;
+  }
+  void set_parameters(const std::map<std::string, double> &p) override {
+    mu_ = p.at("mu");
+    theta_ = p.at("theta");
+  }
+  const std::map<std::string, double> get_scalar_parameters() const override { return {{"mu", mu_}, {"theta", theta_}}; }
+  void bind(const mesh &m) const override {
+    check(m.ctx(), nosh_set_mvp_constcurl(m.ctx(), b_.data(), u_.empty() ? nullptr : u_.data()));
+  }
+
+private:
+  std::vector<double> b_, u_;
+  double mu_ = 0.0, theta_ = 0.0;
+};
+}  // namespace vector_field
+
+inline void bind_fields(const mesh &m, const scalar_field::base *thickness, const vector_field::base *mvp,
+                        const scalar_field::base *potential) {
+  if (thickness && m.bound_thickness != thickness) {
+    thickness->bind_as_thickness(m);
+    m.bound_thickness = thickness;
+  }
+  if (mvp && m.bound_mvp != mvp) {
+    mvp->bind(m);
+    m.bound_mvp = mvp;
+  }
+  if (potential && m.bound_potential != potential) {
+    potential->bind_as_potential(m);
+    m.bound_potential = potential;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// src/parameter_object.hpp:26-34
+class parameter_object {
+public:
+  virtual ~parameter_object() = default;
+  void set_parameters(const std::map<std::string, double> &scalar_params,
+                      const std::map<std::string, std::shared_ptr<const Tpetra::Vector<double, int, int>>> &vector_params) {
+    this->refill_(scalar_params, vector_params);  // the reference's cache never hits (parameter_object.cpp:17-44)
+  }
+  virtual std::map<std::string, double> get_scalar_parameters() const { return {}; }
+
+protected:
+  virtual void refill_(const std::map<std::string, double> &,
+                       const std::map<std::string, std::shared_ptr<const Tpetra::Vector<double, int, int>>> &) = 0;
+};
+
+namespace parameter_matrix {
+
+class matrix_base : public parameter_object, public Tpetra::Operator<double, int, int> {
+public:
+  matrix_base(const std::shared_ptr<const nosh::mesh> &mesh, const std::shared_ptr<const nosh::scalar_field::base> &thickness,
+              const std::shared_ptr<nosh::vector_field::base> &mvp, nosh_matrix_id id)
+      : mesh_(mesh), thickness_(thickness), mvp_(mvp), id_(id) {
+    bind_fields(*mesh_, thickness_.get(), mvp_.get(), nullptr);
+  }
+  std::map<std::string, double> get_scalar_parameters() const override { return mvp_->get_scalar_parameters(); }
+  // Tpetra::CrsMatrix::apply: Y = alpha*op(A)*X + beta*Y
+  void apply(const Tpetra::MultiVector<double, int, int> &X, Tpetra::MultiVector<double, int, int> &Y,
+             Teuchos::ETransp mode = Teuchos::NO_TRANS, double alpha = 1.0, double beta = 0.0) const override {
+    check(mesh_->ctx(), nosh_matrix_apply(mesh_->ctx(), id_, X.getData(), (int64_t)X.getStride(), Y.getDataNonConst(),
+                                          (int64_t)Y.getStride(), (int)X.getNumVectors(), (nosh_transp)mode, alpha, beta));
+  }
+  Teuchos::RCP<const Tpetra::Map<int, int>> getDomainMap() const override { return mesh_->complex_map(); }
+  Teuchos::RCP<const Tpetra::Map<int, int>> getRangeMap() const override { return mesh_->complex_map(); }
+  const std::shared_ptr<const nosh::mesh> &get_mesh() const { return mesh_; }
+
+protected:
+  const std::shared_ptr<const nosh::mesh> mesh_;
+  const std::shared_ptr<const nosh::scalar_field::base> thickness_;
+  const std::shared_ptr<nosh::vector_field::base> mvp_;
+  nosh_matrix_id id_;
+};
+
+// src/parameter_matrix_keo.hpp:37-60
+class keo : public matrix_base {
+public:
+  keo(const std::shared_ptr<const nosh::mesh> &mesh, const std::shared_ptr<const nosh::scalar_field::base> &thickness,
+      const std::shared_ptr<nosh::vector_field::base> &mvp)
+      : matrix_base(mesh, thickness, mvp, NOSH_MAT_KEO) {}
+
+protected:
+  void refill_(const std::map<std::string, double> &p,
+               const std::map<std::string, std::shared_ptr<const Tpetra::Vector<double, int, int>>> &) override {
+    bind_fields(*mesh_, thickness_.get(), mvp_.get(), nullptr);
+    mvp_->set_parameters(p);  // src/parameter_matrix_keo.cpp:88
+    param_list pl(p);
+    check(mesh_->ctx(), nosh_keo_fill(mesh_->ctx(), pl.size(), pl.names.data(), pl.values.data()));
+  }
+};
+
+// src/parameter_matrix_dkeo_dp.hpp
+class DkeoDP : public matrix_base {
+public:
+  DkeoDP(const std::shared_ptr<const nosh::mesh> &mesh, const std::shared_ptr<const nosh::scalar_field::base> &thickness,
+         const std::shared_ptr<nosh::vector_field::base> &mvp, const std::string &param_name)
+      : matrix_base(mesh, thickness, mvp, NOSH_MAT_DKEO), param_name_(param_name) {}
+
+protected:
+  void refill_(const std::map<std::string, double> &p,
+               const std::map<std::string, std::shared_ptr<const Tpetra::Vector<double, int, int>>> &) override {
+    bind_fields(*mesh_, thickness_.get(), mvp_.get(), nullptr);
+    mvp_->set_parameters(p);
+    param_list pl(p);
+    check(mesh_->ctx(), nosh_dkeo_fill(mesh_->ctx(), pl.size(), pl.names.data(), pl.values.data(), param_name_.c_str()));
+  }
+  const std::string param_name_;
+};
+}  // namespace parameter_matrix
+
+// ---------------------------------------------------------------------------------------
+// src/jacobian_operator.hpp:26-65
+class jacobian_operator : public Tpetra::Operator<double, int, int> {
+public:
+  jacobian_operator(const std::shared_ptr<const nosh::mesh> &mesh,
+                    const std::shared_ptr<const nosh::scalar_field::base> &scalar_potential,
+                    const std::shared_ptr<const nosh::scalar_field::base> &thickness,
+                    const std::shared_ptr<nosh::parameter_matrix::keo> &keo)
+      : mesh_(mesh), scalar_potential_(scalar_potential), thickness_(thickness), keo_(keo) {
+    bind_fields(*mesh_, thickness_.get(), nullptr, scalar_potential_.get());
+  }
+  void apply(const Tpetra::MultiVector<double, int, int> &X, Tpetra::MultiVector<double, int, int> &Y,
+             Teuchos::ETransp mode = Teuchos::NO_TRANS, double alpha = 1.0, double beta = 0.0) const override {
+    // unsupported mode/alpha/beta -> NOSH_EINVAL -> std::logic_error, as jacobian_operator.cpp:48-59
+    check(mesh_->ctx(), nosh_jac_apply(mesh_->ctx(), X.getData(), (int64_t)X.getStride(), Y.getDataNonConst(),
+                                       (int64_t)Y.getStride(), (int)X.getNumVectors(), (nosh_transp)mode, alpha, beta));
+  }
+  Teuchos::RCP<const Tpetra::Map<int, int>> getDomainMap() const override { return keo_->getDomainMap(); }
+  Teuchos::RCP<const Tpetra::Map<int, int>> getRangeMap() const override { return keo_->getRangeMap(); }
+  void rebuild(const std::map<std::string, double> &params, const Tpetra::Vector<double, int, int> &current_x) {
+    bind_fields(*mesh_, thickness_.get(), nullptr, scalar_potential_.get());
+    param_list pl(params);
+    check(mesh_->ctx(), nosh_jac_rebuild(mesh_->ctx(), pl.size(), pl.names.data(), pl.values.data(), current_x.getData()));
+  }
+
+private:
+  const std::shared_ptr<const nosh::mesh> mesh_;
+  const std::shared_ptr<const nosh::scalar_field::base> scalar_potential_, thickness_;
+  const std::shared_ptr<nosh::parameter_matrix::keo> keo_;
+};
+
+// src/keo_regularized.hpp:37-74
+class keo_regularized : public Tpetra::Operator<double, int, int> {
+public:
+  keo_regularized(const std::shared_ptr<const nosh::mesh> &mesh, const std::shared_ptr<const nosh::scalar_field::base> &thickness,
+                  const std::shared_ptr<nosh::vector_field::base> &mvp)
+      : mesh_(mesh), thickness_(thickness), mvp_(mvp) {
+    bind_fields(*mesh_, thickness_.get(), mvp_.get(), nullptr);
+  }
+  // the inverse is a MueLu V-cycle in the reference (out of scope): throws std::runtime_error
+  void apply(const Tpetra::MultiVector<double, int, int> &X, Tpetra::MultiVector<double, int, int> &Y,
+             Teuchos::ETransp mode = Teuchos::NO_TRANS, double alpha = 1.0, double beta = 0.0) const override {
+    check(mesh_->ctx(), nosh_keoreg_apply(mesh_->ctx(), X.getData(), (int64_t)X.getStride(), Y.getDataNonConst(),
+                                          (int64_t)Y.getStride(), (int)X.getNumVectors(), (nosh_transp)mode, alpha, beta));
+  }
+  // the matrix K + diagonal blocks itself
+  void apply_matrix(const Tpetra::MultiVector<double, int, int> &X, Tpetra::MultiVector<double, int, int> &Y) const {
+    check(mesh_->ctx(), nosh_keoreg_matrix_apply(mesh_->ctx(), X.getData(), (int64_t)X.getStride(), Y.getDataNonConst(),
+                                                 (int64_t)Y.getStride(), (int)X.getNumVectors()));
+  }
+  Teuchos::RCP<const Tpetra::Map<int, int>> getDomainMap() const override { return mesh_->complex_map(); }
+  Teuchos::RCP<const Tpetra::Map<int, int>> getRangeMap() const override { return mesh_->complex_map(); }
+  void rebuild(const std::map<std::string, double> &params, const Tpetra::Vector<double, int, int> &x) {
+    mvp_->set_parameters(params);
+    param_list pl(params);
+    check(mesh_->ctx(), nosh_keoreg_rebuild(mesh_->ctx(), pl.size(), pl.names.data(), pl.values.data(), x.getData()));
+  }
+
+private:
+  const std::shared_ptr<const nosh::mesh> mesh_;
+  const std::shared_ptr<const nosh::scalar_field::base> thickness_;
+  const std::shared_ptr<nosh::vector_field::base> mvp_;
+};
+
+// ---------------------------------------------------------------------------------------
+namespace model_evaluator {
+
+// the members of Thyra::ModelEvaluatorBase::InArgs / OutArgs that nls supports
+// (src/model_evaluator_nls.cpp:331-390)
+struct InArgs {
+  std::shared_ptr<const Tpetra::Vector<double, int, int>> x;
+  std::vector<double> p;  // p(0), ordered like get_p_names(0)
+  double alpha = 0.0, beta = 0.0;
+  void set_x(const std::shared_ptr<const Tpetra::Vector<double, int, int>> &v) { x = v; }
+  void set_p(int l, const std::vector<double> &v) {
+    if (l != 0) throw std::logic_error("LOCA can only deal with one parameter vector.");
+    p = v;
+  }
+};
+struct OutArgs {
+  std::shared_ptr<Tpetra::Vector<double, int, int>> f;
+  std::shared_ptr<Tpetra::MultiVector<double, int, int>> DfDp;  // DERIV_MV_BY_COL
+  std::shared_ptr<Tpetra::Operator<double, int, int>> W_op, W_prec;
+  void set_f(const std::shared_ptr<Tpetra::Vector<double, int, int>> &v) { f = v; }
+  void set_DfDp(int, const std::shared_ptr<Tpetra::MultiVector<double, int, int>> &v) { DfDp = v; }
+  void set_W_op(const std::shared_ptr<Tpetra::Operator<double, int, int>> &v) { W_op = v; }
+  void set_W_prec(const std::shared_ptr<Tpetra::Operator<double, int, int>> &v) { W_prec = v; }
+};
+
+// src/model_evaluator_nls.hpp:59-167
+class nls {
+public:
+  nls(const std::shared_ptr<const nosh::mesh> &mesh, const std::shared_ptr<nosh::vector_field::base> &mvp,
+      const std::shared_ptr<const nosh::scalar_field::base> &scalar_potential, const double g,
+      const std::shared_ptr<const nosh::scalar_field::base> &thickness,
+      const std::shared_ptr<const Tpetra::Vector<double, int, int>> &initial_x, const std::string &deriv_parameter)
+      : mesh_(mesh), mvp_(mvp), scalar_potential_(scalar_potential), thickness_(thickness),
+        keo_(std::make_shared<nosh::parameter_matrix::keo>(mesh_, thickness_, mvp_)),
+        dkeo_dp_(std::make_shared<nosh::parameter_matrix::DkeoDP>(mesh_, thickness_, mvp_, deriv_parameter)),
+        initial_x_(initial_x) {
+    bind_fields(*mesh_, thickness_.get(), mvp_.get(), scalar_potential_.get());
+    // merge all parameters; earlier keys win; std::map keeps them name-sorted (:101-130)
+    std::map<std::string, double> params;
+    params["g"] = g;
+    auto sp = scalar_potential_->get_scalar_parameters();
+    params.insert(sp.begin(), sp.end());
+    auto mb = keo_->get_scalar_parameters();
+    params.insert(mb.begin(), mb.end());
+    for (const auto &kv : params) {
+      p_names_.push_back(kv.first);
+      p_init_.push_back(kv.second);
+    }
+  }
+  Teuchos::RCP<const Teuchos::Array<std::string>> get_p_names(int l) const {
+    if (l != 0) throw std::logic_error("LOCA can only deal with one parameter vector.");
+    return std::make_shared<const Teuchos::Array<std::string>>(p_names_);
+  }
+  InArgs createInArgs() const { return InArgs(); }
+  OutArgs createOutArgs() const { return OutArgs(); }
+  InArgs getNominalValues() const {
+    InArgs a;
+    a.x = initial_x_;
+    a.p = p_init_;
+    return a;
+  }
+  std::shared_ptr<Tpetra::Operator<double, int, int>> create_W_op() const {
+    return std::make_shared<nosh::jacobian_operator>(mesh_, scalar_potential_, thickness_, keo_);  // :253-267
+  }
+  std::shared_ptr<Tpetra::Operator<double, int, int>> create_W_prec() const {
+    return std::make_shared<nosh::keo_regularized>(mesh_, thickness_, mvp_);  // :301-314
+  }
+  const std::shared_ptr<const nosh::mesh> mesh() const { return mesh_; }
+
+  // evalModelImpl (:392-525)
+  void evalModel(const InArgs &in, const OutArgs &out) const {
+    double alpha = in.alpha, beta = in.beta;
+    if (alpha == 0.0 && beta == 0.0) beta = 1.0;
+    if (alpha != 0.0 || beta != 1.0) throw std::logic_error("nls::evalModel: only alpha == 0, beta == 1 supported");
+    if (!in.x) throw std::logic_error("nls::evalModel: x is null");
+    if (in.p.size() != p_names_.size()) throw std::logic_error("nls::evalModel: p(0) has the wrong size");
+    std::map<std::string, double> params;
+    for (size_t k = 0; k < p_names_.size(); k++) params[p_names_[k]] = in.p[k];
+    param_list pl(params);
+    nosh_ctx *c = mesh_->ctx();
+    bind_fields(*mesh_, thickness_.get(), mvp_.get(), scalar_potential_.get());
+    if (out.f)  // compute_f_ (:527-628)
+      check(c, nosh_compute_f(c, pl.size(), pl.names.data(), pl.values.data(), in.x->getData(), out.f->getDataNonConst()));
+    if (out.DfDp) {  // computeDFDP_ for every parameter (:464-489)
+      if (out.DfDp->getNumVectors() != p_names_.size()) throw std::logic_error("DfDp has the wrong number of columns");
+      for (size_t k = 0; k < p_names_.size(); k++)
+        check(c, nosh_compute_dfdp(c, pl.size(), pl.names.data(), pl.values.data(), p_names_[k].c_str(), in.x->getData(),
+                                   out.DfDp->getDataNonConst(k)));
+    }
+    if (out.W_op) {  // :492-504
+      auto jac = std::dynamic_pointer_cast<nosh::jacobian_operator>(out.W_op);
+      if (!jac) throw std::logic_error("W_op is not a nosh::jacobian_operator");
+      jac->rebuild(params, *in.x);
+    }
+    if (out.W_prec) {  // :507-522
+      auto prec = std::dynamic_pointer_cast<nosh::keo_regularized>(out.W_prec);
+      if (!prec) throw std::logic_error("W_prec is not a nosh::keo_regularized");
+      prec->rebuild(params, *in.x);
+    }
+  }
+
+private:
+  const std::shared_ptr<const nosh::mesh> mesh_;
+  const std::shared_ptr<nosh::vector_field::base> mvp_;
+  const std::shared_ptr<const nosh::scalar_field::base> scalar_potential_, thickness_;
+  const std::shared_ptr<nosh::parameter_matrix::keo> keo_;
+  const std::shared_ptr<nosh::parameter_matrix::DkeoDP> dkeo_dp_;
+  const std::shared_ptr<const Tpetra::Vector<double, int, int>> initial_x_;
+  std::vector<std::string> p_names_;
+  std::vector<double> p_init_;
+};
+}  // namespace model_evaluator
+}  // namespace nosh
