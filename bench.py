@@ -30,6 +30,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints "NCCL version ..." on stdout at NCCL_DEBUG=VERSION; stdout must carry ONE JSON line
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 ITERS = 200
 PARAMS = {"g": 1.0, "mu": 1.0, "theta": 0.0}
@@ -185,6 +188,9 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: park everything else (NCCL banners ...) on stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -335,7 +341,10 @@ def run_b200(args):
                 "value": r["gdofs"], "unit": "GDOF/s", "cores": th, "kind": "port",
                 "sample": "tetgrid n=%d (%d vertices), 1 step of the same workload after 1 warm-up; "
                           "oracle = reference algorithm restated in Tpetra layout" % (args.cpu_n, r["N"])}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -50,7 +50,8 @@ template <int EPI, int FUSE, int U>
 __global__ void __launch_bounds__(CHUNK, 2) k_apply_sell(const ApplyArgs A) {
   if (krylov_skip<FUSE>(A)) return;
   __shared__ double red[CHUNK / 32];
-  const int64_t row = (int64_t)blockIdx.x * CHUNK + threadIdx.x;
+  const int chunk = A.chunk_list ? __ldg(A.chunk_list + blockIdx.x) : (int)blockIdx.x;
+  const int64_t row = (int64_t)chunk * CHUNK + threadIdx.x;
   const int64_t slice = row >> 5;
   const int lane = threadIdx.x & 31;
   const double scale = (FUSE == FUSE_MINRES) ? A.st->inv_beta : 1.0;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(CHUNK, 2) k_apply_sell(const ApplyArgs A) {
   }
   if (FUSE == FUSE_MINRES || FUSE == FUSE_CG) {
     const double s = block_sum<CHUNK / 32>(contrib, red);
-    if (threadIdx.x == 0) A.partials[blockIdx.x] = s;
+    if (threadIdx.x == 0) A.partials[chunk] = s;
   }
 }
 
@@ -131,12 +132,13 @@ __global__ void __launch_bounds__(CHUNK, 2) k_apply_csr(const ApplyArgs A) {
   if (krylov_skip<FUSE>(A)) return;
   __shared__ double red[CHUNK / 32];
   constexpr int RPP = CHUNK / LPR;  // rows per pass
+  const int chunk = A.chunk_list ? __ldg(A.chunk_list + blockIdx.x) : (int)blockIdx.x;
   const int sub = threadIdx.x / LPR, sl = threadIdx.x % LPR;
   const double scale = (FUSE == FUSE_MINRES) ? A.st->inv_beta : 1.0;
   double contrib = 0.0;
 #pragma unroll 2
   for (int pass = 0; pass < LPR; pass++) {
-    const int64_t row = (int64_t)blockIdx.x * CHUNK + pass * RPP + sub;
+    const int64_t row = (int64_t)chunk * CHUNK + pass * RPP + sub;
     double2 acc = make_double2(0.0, 0.0);
     if (row < A.No) {
       const int b = __ldg(A.rowptr + row), e = __ldg(A.rowptr + row + 1);
@@ -187,13 +189,13 @@ __global__ void __launch_bounds__(CHUNK, 2) k_apply_csr(const ApplyArgs A) {
   }
   if (FUSE == FUSE_MINRES || FUSE == FUSE_CG) {
     const double s = block_sum<CHUNK / 32>(contrib, red);
-    if (threadIdx.x == 0) A.partials[blockIdx.x] = s;
+    if (threadIdx.x == 0) A.partials[chunk] = s;
   }
 }
 
 template <int EPI, int FUSE>
 void launch2(Ctx *ctx, const ApplyArgs &A) {
-  const unsigned grid = (unsigned)cdiv(A.No, CHUNK);
+  const unsigned grid = A.chunk_list ? (unsigned)A.n_list : (unsigned)cdiv(A.No, CHUNK);
   if (grid == 0) return;
   if (ctx->layout == NOSH_LAYOUT_SELL32)
     k_apply_sell<EPI, FUSE, 4><<<grid, CHUNK, 0, ctx->stream>>>(A);

@@ -47,6 +47,9 @@ struct ApplyArgs {
   const double2 *r1;
   double *partials;
   int host_iter;
+  // optional list of chunks to process (interior / boundary split); NULL = all chunks
+  const int32_t *chunk_list;
+  int n_list;
 };
 
 void launch_apply(Ctx *ctx, int epi, int fuse, const ApplyArgs &A);

@@ -95,6 +95,7 @@ __global__ void k_widen(const int32_t *in, int64_t n, int64_t *out) {
 void after_mesh(Ctx *ctx) {
   halo_setup(ctx);
   ensure_work(ctx);
+  p2p_setup(ctx);
   ctx->thick_set = false;
   ctx->mvp_kind = MVP_NONE;
   ctx->alpha_ok = ctx->keo_filled = ctx->dkeo_filled = ctx->jac_ok = ctx->keoreg_ok = false;

@@ -96,7 +96,28 @@ struct KrylovState {
   int breakdown;
 };
 
-struct NcclApi;  // comm.cpp
+struct NcclApi;  // comm.cu
+
+constexpr int MAX_RANKS = 8;
+
+// Peer-memory (NVLink/NVSwitch) view of the other ranks' buffers, opened through CUDA IPC:
+// lets one kernel push halo entries / group sums straight into a peer's HBM and signal it.
+struct P2PView {
+  double *red[MAX_RANKS];               // rank r's gather buffer: 2 slots x MAX_GROUPS doubles
+  unsigned long long *flags[MAX_RANKS]; // rank r's arrival flags: one per source rank
+  int P, me;
+  unsigned long long epoch;
+  int *err;                             // local: set on a spin time-out
+};
+struct P2P {
+  bool ok = false;
+  DBuf<unsigned long long> local;       // [2*MAX_GROUPS | MAX_RANKS flags | err]
+  void *opened[3][MAX_RANKS] = {};
+  P2PView view;
+  double2 *R[2][MAX_RANKS] = {};        // rank r's MINRES r-buffers (work[0], work[1])
+  int64_t ghost_base[MAX_RANKS] = {};   // where my block starts inside rank r's vectors
+  unsigned long long epoch = 0;
+};
 
 enum MvpKind { MVP_NONE = 0, MVP_EXPLICIT = 1, MVP_CONSTCURL = 2 };
 enum PotKind { POT_NONE = 0, POT_CONSTANT = 1, POT_VALUES = 2 };
@@ -108,6 +129,9 @@ struct Ctx {
   std::string err;
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // multi-GPU overlap: communication / side stream and the events that order it against `stream`
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t e_b = nullptr, e_halo = nullptr, e_finb = nullptr, e_c = nullptr;
 
   // comm
   int rank = 0, nranks = 1;
@@ -187,6 +211,10 @@ struct Ctx {
   DBuf<int32_t> send_idx;           // owned local ids to pack, grouped by peer
   DBuf<double2> send_buf;
   int64_t n_send = 0;
+  P2P p2p;
+  // chunks (512 rows) whose rows reference no ghost column can be applied before the halo lands
+  DBuf<int32_t> chunks_int, chunks_bnd;
+  int64_t n_chunks_int = 0, n_chunks_bnd = 0;
 };
 
 // ---- parameter map helpers ---------------------------------------------------

@@ -236,9 +236,11 @@ struct FinArgs {
   KrylovState *st;
   double *out;
   double *hist;
-  int what, host_iter, stage;  // stage 0: single GPU; 1: level 2 only; 2: level 3 + scalars
+  int what, host_iter, stage;  // stage 0: single GPU; 1: level 2 only; 2: level 3 + scalars;
+                               // 3: one kernel, group sums exchanged through peer memory
   double tol;
   int maxit;
+  P2PView p2p;
 };
 
 __device__ __forceinline__ void sym_ortho(double a, double b, double &c, double &s, double &r) {
@@ -407,9 +409,38 @@ __global__ void __launch_bounds__(1024) k_finalize(const FinArgs F) {
     if (F.stage == 1) return;
     __syncthreads();
   }
-  // level 3: fixed tree over the (<= 1024) group sums of the whole mesh
   const double *gs = F.stage == 2 ? F.grecv : F.gsend;
-  double v = (int)threadIdx.x < F.n_groups_global ? gs[threadIdx.x] : 0.0;
+  if (F.stage == 3) {
+    // all-gather of the group sums over NVLink: store mine into every rank's slot (own included),
+    // publish an epoch flag to every rank, wait for everybody's flag.  Ranks are never more
+    // than one reduction apart, so two slots are enough.  Peer r's flag also tells me that all
+    // NVLink stores r issued before it (its halo push) have landed.
+    const P2PView &q = F.p2p;
+    const int slot = (int)(q.epoch & 1ull);
+    const int nloc = (int)F.n_groups_local;
+    for (int i = threadIdx.x; i < nloc * q.P; i += blockDim.x) {
+      const int r = i / nloc, g = (int)F.group_begin + i % nloc;
+      q.red[r][slot * MAX_GROUPS + g] = F.gsend[g];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < q.P) {
+      *((volatile unsigned long long *)&q.flags[threadIdx.x][q.me]) = q.epoch;
+      const volatile unsigned long long *mine = (const volatile unsigned long long *)&q.flags[q.me][threadIdx.x];
+      const long long t0 = clock64();
+      while (*mine < q.epoch) {
+        if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer is gone; fail instead of hanging
+          *q.err = 1;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    __threadfence_system();
+    gs = q.red[q.me] + slot * MAX_GROUPS;
+  }
+  // level 3: fixed tree over the (<= 1024) group sums of the whole mesh
+  double v = (int)threadIdx.x < F.n_groups_global ? __ldcg(gs + threadIdx.x) : 0.0;
   v = warp_sum(v);
   if (l == 0) sm[w] = v;
   __syncthreads();
@@ -439,6 +470,11 @@ void finalize(Ctx *ctx, int which_partials, int what, int host_iter, double tol,
   F.maxit = maxit;
   if (ctx->nranks == 1) {
     F.stage = 0;
+    KLAUNCH(ctx, k_finalize, 1, 1024, F);
+  } else if (ctx->p2p.ok) {
+    F.stage = 3;
+    F.p2p = ctx->p2p.view;
+    F.p2p.epoch = ++ctx->p2p.epoch;
     KLAUNCH(ctx, k_finalize, 1, 1024, F);
   } else {
     F.stage = 1;
@@ -586,32 +622,83 @@ void minres_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_ou
   const unsigned grid = (unsigned)ctx->n_chunks;
   const int64_t No = ctx->No;
   if (grid) KLAUNCH(ctx, k_minres_init, grid, TPB, b, bscale, No, R[0], W[0], W[1], W[2], X, ctx->partials.p);
+  if (ctx->nranks > 1 && ctx->p2p.ok) p2p_halo_push(ctx, 0, R[0]);  // r_1 ghosts; ordered by the reduction below
   finalize(ctx, 0, FIN_MINRES_INIT, 0, tol, maxit, nullptr);
   KrylovState hs;
   int check = 4;
+  // Multi-GPU schedule (same arithmetic, two streams): the halo of r_h travels on stream2
+  // while the interior chunks of A(h) run; C(h-1) also runs on stream2, next to A(h) and the
+  // alpha all-reduce, and must only be finished before B(h) overwrites the buffer it reads.
+  const bool p2p = ctx->nranks > 1 && ctx->p2p.ok;
+  const bool overlap = ctx->nranks > 1 && !p2p;
+  cudaStream_t S0 = ctx->stream, S1 = ctx->stream2;
+  if (overlap) CUDA_CHECK(cudaEventRecord(ctx->e_b, S0));  // r_1 is ready
+  int h_last = 0;
   for (int h = 1; h <= maxit; h++) {
     double2 *rcur = R[(h - 1) & 1], *rprev = R[h & 1];
-    // A: y = J v - (beta/oldBeta) r_prev, partials <v,y>
-    halo_exchange(ctx, rcur);
     A.x = rcur;
     A.y = Pv;
     A.r1 = rprev;
     A.host_iter = h;
     A.partials = ctx->partials.p;
-    launch_apply(ctx, epi, FUSE_MINRES, A);
-    finalize(ctx, 0, FIN_MINRES_ALPHA, h, tol, maxit, nullptr);
-    // B: r_next = y - (alpha/beta) r_cur  (written over r_prev)
-    if (grid) KLAUNCH(ctx, k_minres_B, grid, TPB, ctx->kstate.p, h, Pv, rcur, rprev, No, ctx->partials.p);
-    finalize(ctx, 0, FIN_MINRES_BETA, h, tol, maxit, nullptr);
-    // C: w_h, x
-    if (grid)
-      KLAUNCH(ctx, k_minres_C, grid, TPB, ctx->kstate.p, h, rcur, W[(h + 1) % 3], W[(h + 2) % 3], W[h % 3], X, No);
+    if (overlap) {
+      CUDA_CHECK(cudaStreamWaitEvent(S1, ctx->e_b, 0));
+      halo_exchange(ctx, rcur, S1);
+      CUDA_CHECK(cudaEventRecord(ctx->e_halo, S1));
+      if (h > 1) {
+        CUDA_CHECK(cudaStreamWaitEvent(S1, ctx->e_finb, 0));
+        if (grid) {
+          k_minres_C<<<grid, TPB, 0, S1>>>(ctx->kstate.p, h - 1, rprev, W[h % 3], W[(h + 1) % 3], W[(h + 2) % 3], X,
+                                           No);
+          ctx->launches++;
+          CUDA_CHECK(cudaGetLastError());
+        }
+        CUDA_CHECK(cudaEventRecord(ctx->e_c, S1));
+      }
+      // A on the chunks that need no ghost value, then (halo landed) on the rest
+      A.chunk_list = ctx->chunks_int.p;
+      A.n_list = (int)ctx->n_chunks_int;
+      launch_apply(ctx, epi, FUSE_MINRES, A);
+      CUDA_CHECK(cudaStreamWaitEvent(S0, ctx->e_halo, 0));
+      A.chunk_list = ctx->chunks_bnd.p;
+      A.n_list = (int)ctx->n_chunks_bnd;
+      launch_apply(ctx, epi, FUSE_MINRES, A);
+      finalize(ctx, 0, FIN_MINRES_ALPHA, h, tol, maxit, nullptr);
+      if (h > 1) CUDA_CHECK(cudaStreamWaitEvent(S0, ctx->e_c, 0));
+      if (grid) KLAUNCH(ctx, k_minres_B, grid, TPB, ctx->kstate.p, h, Pv, rcur, rprev, No, ctx->partials.p);
+      CUDA_CHECK(cudaEventRecord(ctx->e_b, S0));
+      finalize(ctx, 0, FIN_MINRES_BETA, h, tol, maxit, nullptr);
+      CUDA_CHECK(cudaEventRecord(ctx->e_finb, S0));
+    } else {
+      // A: y = J v - (beta/oldBeta) r_prev, partials <v,y>
+      launch_apply(ctx, epi, FUSE_MINRES, A);
+      finalize(ctx, 0, FIN_MINRES_ALPHA, h, tol, maxit, nullptr);
+      // B: r_next = y - (alpha/beta) r_cur  (written over r_prev)
+      if (grid) KLAUNCH(ctx, k_minres_B, grid, TPB, ctx->kstate.p, h, Pv, rcur, rprev, No, ctx->partials.p);
+      // multi-GPU, peer-memory path: push the boundary entries of r_next into the neighbours'
+      // ghost segments; the beta reduction that follows is also the barrier that orders them
+      if (p2p) p2p_halo_push(ctx, h & 1, rprev);
+      finalize(ctx, 0, FIN_MINRES_BETA, h, tol, maxit, nullptr);
+      // C: w_h, x
+      if (grid)
+        KLAUNCH(ctx, k_minres_C, grid, TPB, ctx->kstate.p, h, rcur, W[(h + 1) % 3], W[(h + 2) % 3], W[h % 3], X, No);
+    }
+    h_last = h;
     if (h % check == 0 || h == maxit) {
       if (poll_done(ctx, &hs)) break;
       if (check < 32) check *= 2;
     }
   }
+  if (overlap && h_last >= 1) {
+    // the update of the last launched iteration (a no-op if the solver stopped earlier)
+    const int h = h_last;
+    if (h > 1) CUDA_CHECK(cudaStreamWaitEvent(S0, ctx->e_c, 0));
+    if (grid)
+      KLAUNCH(ctx, k_minres_C, grid, TPB, ctx->kstate.p, h, R[(h - 1) & 1], W[(h + 1) % 3], W[(h + 2) % 3], W[h % 3],
+              X, No);
+  }
   poll_done(ctx, &hs);
+  if (p2p_check_error(ctx)) NOSH_THROW(NOSH_ECOMM, "peer-memory reduction timed out (a rank is not responding)");
   if (res) {
     res->iterations = hs.iter;
     res->converged = hs.converged;
