@@ -49,6 +49,12 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=56, help="sample mesh of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--apply-reps", type=int, default=50)
+    ap.add_argument("--workload", default="minres200", choices=["minres200", "newton", "continuation"],
+                    help="minres200: the default step (configs[1]); newton: one full Newton-MINRES solve per "
+                         "step (configs[2]); continuation: a mu sweep with tangent predictor (configs[3])")
+    ap.add_argument("--strong", action="store_true",
+                    help="keep the mesh at n^3 for any number of GPUs (configs[4]) instead of growing it")
+    ap.add_argument("--lin-maxit", type=int, default=20000)
     return ap.parse_args()
 
 
@@ -207,9 +213,10 @@ def run_b200(args):
         ctx.comm_init(obj[0], rank, world)
 
     n = args.n
-    nz = n * world  # weak scaling: the brick grows along z with the number of GPUs
+    zs = 1 if args.strong else world
+    nz = n * zs  # weak scaling: the brick grows along z with the number of GPUs
     t_setup = time.perf_counter()
-    mi = ctx.mesh_tetgrid(n, n, nz, lo=(-5.0, -5.0, -5.0 * world), hi=(5.0, 5.0, 5.0 * world))
+    mi = ctx.mesh_tetgrid(n, n, nz, lo=(-5.0, -5.0, -5.0 * zs), hi=(5.0, 5.0, 5.0 * zs))
     ctx.set_thickness(None, 1.0)
     ctx.set_potential_constant(-1.0)
     ctx.set_mvp_constcurl((0.0, 0.0, 1.0))
@@ -263,6 +270,13 @@ def run_b200(args):
             ms = float(t.item())
         return ms / steps, ctx.launch_count() - l0
 
+    if args.workload != "minres200":
+        run_solver_workload(args, ctx, mi, world, rank, local, barrier, real_stdout, t_setup)
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -308,7 +322,7 @@ def run_b200(args):
             "value": 2.0 * Nglob * ITERS / (ms_step * 1e-3) / 1e9,
             "unit": "GDOF/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": "tetgrid %dx%dx%d = %d vertices (%d per GPU), 6 Kuhn tets/hex, jitter 0.2, "
@@ -348,6 +362,63 @@ def run_b200(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_solver_workload(args, ctx, mi, world, rank, local, barrier, real_stdout, t_setup):
+    """configs[2] / configs[3]: full Newton-MINRES solve, or a continuation sweep in mu."""
+    import torch
+    import torch.distributed as dist
+    No, Nglob = int(mi.n_owned), int(mi.n_global)
+    psi0 = torch.zeros(2 * No, device="cuda", dtype=torch.float64)
+    psi0[0::2] = 1.0                       # plain-gl initial state psi = 1
+    results = []
+    for k in range(args.warmup + args.steps):
+        psi = psi0.clone()
+        barrier()
+        l0 = ctx.launch_count()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if args.workload == "newton":
+            res, lin, fn = ctx.newton({"g": 1.0, "mu": 0.1, "theta": 0.0}, psi, 1e-8, 20, 1e-10, args.lin_maxit)
+            its = int(res.total_linear_iterations)
+            detail = {"newton_steps": int(res.steps), "converged": int(res.converged),
+                      "minres_iterations_per_step": [int(v) for v in lin], "fnorms": [float(v) for v in fn]}
+        else:
+            steps = ctx.continuation({"g": 1.0, "mu": 0.0, "theta": 0.0}, "mu", 0.05, 4, psi, 1e-8, 20, 1e-10,
+                                     args.lin_maxit)
+            its = sum(s.linear_iterations + s.predictor_linear_iterations for s in steps)
+            detail = {"continuation": [{"step": s.step, "mu": s.param, "gibbs_energy": s.gibbs_energy,
+                                        "norm": s.norm, "newton_steps": s.newton_steps,
+                                        "minres": s.linear_iterations,
+                                        "predictor_minres": s.predictor_linear_iterations,
+                                        "converged": s.converged} for s in steps]}
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        if k >= args.warmup:
+            results.append((ms, its, ctx.launch_count() - l0, detail))
+    if rank == 0:
+        ms = float(np.mean([r[0] for r in results]))
+        its = results[-1][1]
+        out = {"metric": "jacobian_apply_gdof_per_s", "value": 2.0 * Nglob * its / (ms * 1e-3) / 1e9,
+               "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "%s on tetgrid %d vertices (%d per GPU), psi0 = 1, g = 1, V = -1, const-curl "
+                                      "B = (0,0,1); tolerances: ||F|| < 1e-8, MINRES 1e-10"
+                                      % (args.workload, Nglob, No), "setup_s": t_setup},
+               "minres_iterations": its, "minres_iters_per_s": its / (ms * 1e-3),
+               "solve_seconds": ms * 1e-3, "gpu_launches": int(results[-1][2])}
+        out.update(results[-1][3])
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
 
 
 if __name__ == "__main__":

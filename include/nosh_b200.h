@@ -244,6 +244,38 @@ NOSH_API nosh_status nosh_newton(nosh_ctx *ctx, int np, const char *const *names
                                  double lin_tol, int lin_maxit, nosh_newton_result *res,
                                  int32_t *lin_iters, double *fnorms);
 
+/* ---- model-evaluator scalars.  nls::inner_product / norm / gibbs_energy
+ * (src/model_evaluator_nls.cpp:699-770, src/model_evaluator_base.hpp:50-60).  The reference
+ * computes the local sums, leaves the global reduction as a TODO and returns 0.0; these return
+ * what its commented code states: sum_k c_k Re(conj(phi_k) psi_k) / sum_k c_k, its square root,
+ * and -sum_k c_k |psi_k|^4 / sum_k c_k. */
+NOSH_API nosh_status nosh_inner_product(nosh_ctx *ctx, const double *phi, const double *psi,
+                                        double *result);
+NOSH_API nosh_status nosh_gibbs_energy(nosh_ctx *ctx, const double *psi, double *result);
+
+/* ---- parameter continuation ("next" row f2; nosh-cont, executables/nosh-cont/nosh-cont.cpp:206-344
+ * with the LOCA settings of examples/conf.xml:35-75): natural continuation in `pname` with a
+ * tangent predictor (J t = -dF/dp by MINRES, psi += dp t) and the Newton corrector, nsteps steps
+ * of size dp starting at the value of `pname` in the parameter list.  steps: nsteps+1 records --
+ * the columns src/observer.cpp:134-159 writes (step, parameter, Gibbs energy, ||x||) plus solver
+ * counts.  Stops at the first step whose Newton corrector fails (later records have step = -1). */
+typedef struct {
+  int32_t step;
+  int32_t converged;
+  int32_t newton_steps;
+  int32_t linear_iterations;           /* MINRES iterations of the corrector */
+  int32_t predictor_linear_iterations; /* MINRES iterations of the tangent solve */
+  int32_t reserved;
+  double param;
+  double gibbs_energy;
+  double norm;  /* sqrt(inner_product(psi, psi)) */
+  double fnorm;
+} nosh_continuation_step;
+NOSH_API nosh_status nosh_continuation(nosh_ctx *ctx, int np, const char *const *names,
+                                       const double *values, const char *pname, double dp, int nsteps,
+                                       double *psi, double nl_tol, int nl_maxit, double lin_tol,
+                                       int lin_maxit, nosh_continuation_step *steps);
+
 /* ---- measurement helpers: device-resident scratch vectors so that benchmarks can
  * time kernels with inputs already in HBM.  slot in [0,8). Returns a device pointer to
  * 2*(n_owned+n_ghost) doubles owned by the ctx. */

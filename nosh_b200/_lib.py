@@ -29,6 +29,13 @@ class KrylovResult(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("relres", C.c_double)]
 
 
+class ContinuationStep(C.Structure):
+    _fields_ = [("step", C.c_int32), ("converged", C.c_int32), ("newton_steps", C.c_int32),
+                ("linear_iterations", C.c_int32), ("predictor_linear_iterations", C.c_int32),
+                ("reserved", C.c_int32), ("param", C.c_double), ("gibbs_energy", C.c_double),
+                ("norm", C.c_double), ("fnorm", C.c_double)]
+
+
 class NewtonResult(C.Structure):
     _fields_ = [("steps", C.c_int32), ("converged", C.c_int32),
                 ("total_linear_iterations", C.c_int32), ("fnorm", C.c_double)]
@@ -110,6 +117,10 @@ def lib():
         "nosh_cg": (C.c_int, [vp, C.c_int, vp, vp, dbl, C.c_int, C.POINTER(KrylovResult), vp]),
         "nosh_newton": (C.c_int, [vp, C.c_int, cpp, vp, vp, dbl, C.c_int, dbl, C.c_int,
                                   C.POINTER(NewtonResult), vp, vp]),
+        "nosh_inner_product": (C.c_int, [vp, vp, vp, C.POINTER(dbl)]),
+        "nosh_gibbs_energy": (C.c_int, [vp, vp, C.POINTER(dbl)]),
+        "nosh_continuation": (C.c_int, [vp, C.c_int, cpp, vp, C.c_char_p, dbl, C.c_int, vp, dbl, C.c_int, dbl,
+                                        C.c_int, vp]),
         "nosh_scratch_vector": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
         "nosh_launch_count": (i64, [vp]),
         "nosh_timer_start": (C.c_int, [vp]),

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (LAYOUT_CSR, LAYOUT_SELL32, MAT_DKEO, MAT_KEO, NO_TRANS, OP_JACOBIAN, OP_KEO,  # noqa: F401
-                   OP_KEOREG, KrylovResult, MeshInfo, NewtonResult)
+                   OP_KEOREG, ContinuationStep, KrylovResult, MeshInfo, NewtonResult)
 
 
 class NoshError(RuntimeError):
@@ -334,6 +334,34 @@ class Context:
                                     int(nl_maxit), float(lin_tol), int(lin_maxit), C.byref(res),
                                     _ptr(lin), _ptr(fn)))
         return res, lin[:res.steps].copy(), fn[:res.steps + 1].copy()
+
+    def inner_product(self, phi, psi):
+        r = C.c_double()
+        self._ck(self.L.nosh_inner_product(self.h, _ptr(phi), _ptr(psi), C.byref(r)))
+        return r.value
+
+    def gibbs_energy(self, psi):
+        r = C.c_double()
+        self._ck(self.L.nosh_gibbs_energy(self.h, _ptr(psi), C.byref(r)))
+        return r.value
+
+    def continuation(self, params, pname, dp, nsteps, psi, nl_tol=1e-8, nl_maxit=20, lin_tol=1e-10,
+                     lin_maxit=1000):
+        """Natural continuation in `pname`; psi is updated in place.  Returns the step records."""
+        n, names, vals = _params(params)
+        steps = (ContinuationStep * (nsteps + 1))()
+        self._ck(self.L.nosh_continuation(self.h, n, names, _ptr(vals), pname.encode(), float(dp),
+                                          int(nsteps), _ptr(psi), float(nl_tol), int(nl_maxit),
+                                          float(lin_tol), int(lin_maxit), steps))
+        return [s for s in steps if s.step >= 0]
+
+    @staticmethod
+    def write_continuation_csv(path, steps, pname):
+        """The CSV the reference's observer writes (src/observer.cpp:134-159, src/csv_writer.cpp)."""
+        with open(path, "w") as f:
+            f.write("(0) step,(1) %s,(2) Gibbs energy,(2) ||x||_2 scaled\n" % pname)
+            for s in steps:
+                f.write("%d,%.15e,%.15e,%.15e\n" % (s.step, s.param, s.gibbs_energy, s.norm))
 
     # ---- measurement ------------------------------------------------------------------
     def scratch_vector(self, slot):

@@ -493,35 +493,9 @@ nosh_status nosh_compute_dfdp(nosh_ctx *ctx, int np, const char *const *names, c
   API_BEGIN(ctx)
   require_mesh(ctx);
   if (!pname) NOSH_THROW(NOSH_EINVAL, "NULL parameter name");
-  // dK/dp for the column's own parameter
-  dkeo_fill(ctx, np, names, values, pname);
-  ensure_work(ctx);
   double2 *x = stage_in(ctx, psi, ctx->stage_x, ctx->nranks > 1);
   OutVec o = stage_out(ctx, dfdp, ctx->stage_y);
-  ApplyArgs A;
-  memset(&A, 0, sizeof(A));
-  A.No = ctx->No;
-  A.nslices = ctx->nslices;
-  A.rowptr = ctx->rowptr.p;
-  A.slice_off = ctx->slice_off.p;
-  A.col = ctx->col.p;
-  A.val = ctx->dKval.p;
-  A.x = x;
-  A.y = o.dev;
-  A.cv = ctx->cv.p;
-  A.thick = ctx->thick.p;
-  A.a = 1.0;
-  halo_exchange(ctx, x);
-  if (strcmp(pname, "g") == 0) {  // src/model_evaluator_nls.cpp:665-674
-    launch_apply(ctx, EPI_DG, FUSE_NONE, A);
-  } else {  // :676-691
-    DBuf<double> dv;
-    dv.alloc(ctx->No);
-    potential_dvdp(ctx, pname, dv.p);
-    A.V = dv.p;
-    launch_apply(ctx, EPI_DV, FUSE_NONE, A);
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  }
+  compute_dfdp_dev(ctx, np, names, values, pname, x, o.dev);
   finish_out(ctx, o);
   API_END(ctx)
 }
@@ -626,6 +600,46 @@ nosh_status nosh_newton(nosh_ctx *ctx, int np, const char *const *names, const d
   CUDA_CHECK(cudaMemcpyAsync(x, psi, sizeof(double2) * ctx->No, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                              ctx->stream));
   newton_dev(ctx, np, names, values, x, nl_tol, nl_maxit, lin_tol, lin_maxit, res, lin_iters, fnorms);
+  CUDA_CHECK(cudaMemcpyAsync(psi, x, sizeof(double2) * ctx->No, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                             ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+nosh_status nosh_inner_product(nosh_ctx *ctx, const double *phi, const double *psi, double *result) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  if (!result) NOSH_THROW(NOSH_EINVAL, "NULL result");
+  const double2 *a = stage_in(ctx, phi, ctx->stage_x, false);
+  const double2 *b = (psi == phi) ? a : stage_in(ctx, psi, ctx->stage_y, false);
+  const double vol = weighted_sum_dev(ctx, 0, nullptr, nullptr);
+  *result = weighted_sum_dev(ctx, 1, a, b) / vol;
+  API_END(ctx)
+}
+
+nosh_status nosh_gibbs_energy(nosh_ctx *ctx, const double *psi, double *result) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  if (!result) NOSH_THROW(NOSH_EINVAL, "NULL result");
+  const double2 *a = stage_in(ctx, psi, ctx->stage_x, false);
+  const double vol = weighted_sum_dev(ctx, 0, nullptr, nullptr);
+  *result = weighted_sum_dev(ctx, 2, a, a) / vol;
+  API_END(ctx)
+}
+
+nosh_status nosh_continuation(nosh_ctx *ctx, int np, const char *const *names, const double *values,
+                              const char *pname, double dp, int nsteps, double *psi, double nl_tol, int nl_maxit,
+                              double lin_tol, int lin_maxit, nosh_continuation_step *steps) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  ensure_work(ctx);
+  if (!psi || !pname) NOSH_THROW(NOSH_EINVAL, "NULL argument");
+  if (nsteps < 0 || nl_maxit < 0) NOSH_THROW(NOSH_EINVAL, "negative step count");
+  const bool dev = is_device_ptr(psi);
+  double2 *x = ctx->work[8].p;
+  CUDA_CHECK(cudaMemcpyAsync(x, psi, sizeof(double2) * ctx->No, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                             ctx->stream));
+  continuation_dev(ctx, np, names, values, pname, dp, nsteps, x, nl_tol, nl_maxit, lin_tol, lin_maxit, steps);
   CUDA_CHECK(cudaMemcpyAsync(psi, x, sizeof(double2) * ctx->No, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                              ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

@@ -176,6 +176,7 @@ struct Ctx {
   std::string pot_param;
   DBuf<double> pot_values;          // No (POT_VALUES)
   DBuf<double> Vcur;                // No: V for the current parameters
+  DBuf<double> dvdp;                // No: dV/dp scratch
   int mvp_kind = MVP_NONE;
   DBuf<double> ecache;              // E (explicit) or 3E (constcurl)
   double cc_b[3] = {0, 0, 1}, cc_u[3] = {0, 0, 0};

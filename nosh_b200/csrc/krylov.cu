@@ -47,6 +47,30 @@ __global__ void __launch_bounds__(TPB) k_dot(const double2 *x, const double2 *y,
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
+// control-volume weighted sums: mode 0: sum c_k; 1: sum c_k Re(conj(a_k) b_k)  (nls::inner_product,
+// src/model_evaluator_nls.cpp:699-739); 2: -sum c_k |a_k|^4  (nls::gibbs_energy, :742-770)
+__global__ void __launch_bounds__(TPB) k_weighted(int mode, const double *cv, const double2 *a, const double2 *b,
+                                                  int64_t No, double *partials) {
+  __shared__ double red[TPB / 32];
+  double c = 0.0;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int64_t i = (int64_t)blockIdx.x * CHUNK + threadIdx.x + h * TPB;
+    if (i < No) {
+      if (mode == 0) {
+        c += cv[i];
+      } else if (mode == 1) {
+        c += cv[i] * cdot(a[i], b[i]);
+      } else {
+        const double al = cdot(a[i], a[i]);
+        c -= cv[i] * al * al;
+      }
+    }
+  }
+  const double s = block_sum<TPB / 32>(c, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(TPB) k_minres_init(const double2 *b, double bscale, int64_t No, double2 *r0,
                                                      double2 *w0, double2 *w1, double2 *w2, double2 *x,
                                                      double *partials) {
@@ -563,6 +587,16 @@ double dot_dev(Ctx *ctx, const double2 *x, const double2 *y) {
   return h;
 }
 
+double weighted_sum_dev(Ctx *ctx, int mode, const double2 *a, const double2 *b) {
+  ensure_work(ctx);
+  if (ctx->n_chunks) KLAUNCH(ctx, k_weighted, (unsigned)ctx->n_chunks, TPB, mode, ctx->cv.p, a, b, ctx->No, ctx->partials.p);
+  finalize(ctx, 0, FIN_DOT, 0, 0.0, 0, ctx->scalar_out.p);
+  double h;
+  CUDA_CHECK(cudaMemcpyAsync(&h, ctx->scalar_out.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return h;
+}
+
 void jac_diags_dev(Ctx *ctx, double g, const double2 *psi) {
   ctx->jd0.ensure(ctx->No);
   ctx->jd1.ensure(ctx->No);
@@ -754,6 +788,25 @@ void cg_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_out, d
   }
 }
 
+// dF/dp = (dK/dp) psi + { c t |psi|^2 psi  (p == "g")  |  c t dV/dp psi }   (nls::computeDFDP_)
+void compute_dfdp_dev(Ctx *ctx, int np, const char *const *names, const double *values, const char *pname,
+                      double2 *psi, double2 *out) {
+  ensure_work(ctx);
+  dkeo_fill(ctx, np, names, values, pname);  // dK/dp for the column's own parameter
+  ApplyArgs A = base_args(ctx, ctx->dKval.p, psi, out);
+  A.cv = ctx->cv.p;
+  A.thick = ctx->thick.p;
+  halo_exchange(ctx, psi);
+  if (strcmp(pname, "g") == 0) {  // src/model_evaluator_nls.cpp:665-674
+    launch_apply(ctx, EPI_DG, FUSE_NONE, A);
+  } else {  // :676-691
+    ctx->dvdp.ensure(ctx->No > 0 ? ctx->No : 1);
+    potential_dvdp(ctx, pname, ctx->dvdp.p);
+    A.V = ctx->dvdp.p;
+    launch_apply(ctx, EPI_DV, FUSE_NONE, A);
+  }
+}
+
 // Newton, full step.  psi: device vector with Nl entries, updated in place.
 void newton_dev(Ctx *ctx, int np, const char *const *names, const double *values, double2 *psi, double nl_tol,
                 int nl_maxit, double lin_tol, int lin_maxit, nosh_newton_result *res, int32_t *lin_iters,
@@ -785,6 +838,59 @@ void newton_dev(Ctx *ctx, int np, const char *const *names, const double *values
     res->converged = fn < nl_tol;
     res->total_linear_iterations = total;
     res->fnorm = fn;
+  }
+}
+
+// Natural-parameter continuation with a tangent predictor (LOCA "Natural" stepper + "Tangent"
+// predictor of examples/conf.xml:35-47, constant step; the arc-length variant needs bordered solves
+// and is a later row).  Step k: p_k = p_0 + k dp; for k > 0 the predictor solves J t = -dF/dp at the
+// previous solution and sets psi += dp t; then the Newton corrector runs at p_k.
+void continuation_dev(Ctx *ctx, int np, const char *const *names, const double *values, const char *pname,
+                      double dp, int nsteps, double2 *psi, double nl_tol, int nl_maxit, double lin_tol,
+                      int lin_maxit, nosh_continuation_step *out) {
+  ensure_work(ctx);
+  int ip = -1;
+  for (int i = 0; i < np; i++)
+    if (names[i] && strcmp(names[i], pname) == 0) ip = i;
+  if (ip < 0) NOSH_THROW(NOSH_EKEY, "continuation parameter \"%s\" missing", pname);
+  std::vector<double> vals(values, values + np);
+  const double p0 = vals[ip];
+  const double volume = weighted_sum_dev(ctx, 0, nullptr, nullptr);  // control_volumes->norm1()
+  double2 *T = ctx->work[9].p, *dF = ctx->work[10].p;
+  for (int k = 0; k <= nsteps; k++) {
+    nosh_continuation_step st;
+    memset(&st, 0, sizeof(st));
+    if (k > 0) {
+      // tangent predictor at the previous solution / parameter
+      const double g = param_at(np, names, vals.data(), "g");
+      keo_fill(ctx, np, names, vals.data(), false);
+      update_potential(ctx, np, names, vals.data());
+      jac_diags_dev(ctx, g, psi);
+      compute_dfdp_dev(ctx, np, names, vals.data(), pname, psi, dF);
+      nosh_krylov_result kr;
+      minres_dev(ctx, NOSH_OP_JACOBIAN, dF, -1.0, T, lin_tol, lin_maxit, &kr, nullptr);
+      st.predictor_linear_iterations = kr.iterations;
+      axpy_dev(ctx, dp, T, psi);
+    }
+    vals[ip] = p0 + k * dp;
+    nosh_newton_result nr;
+    newton_dev(ctx, np, names, vals.data(), psi, nl_tol, nl_maxit, lin_tol, lin_maxit, &nr, nullptr, nullptr);
+    st.step = k;
+    st.param = vals[ip];
+    st.newton_steps = nr.steps;
+    st.converged = nr.converged;
+    st.linear_iterations = nr.total_linear_iterations;
+    st.fnorm = nr.fnorm;
+    st.gibbs_energy = weighted_sum_dev(ctx, 2, psi, psi) / volume;
+    st.norm = sqrt(weighted_sum_dev(ctx, 1, psi, psi) / volume);
+    if (out) out[k] = st;
+    if (!nr.converged) {
+      for (int j = k + 1; j <= nsteps && out; j++) {
+        memset(&out[j], 0, sizeof(st));
+        out[j].step = -1;
+      }
+      break;
+    }
   }
 }
 

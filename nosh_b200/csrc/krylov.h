@@ -16,4 +16,10 @@ void cg_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_out, d
 void newton_dev(Ctx *ctx, int np, const char *const *names, const double *values, double2 *psi, double nl_tol,
                 int nl_maxit, double lin_tol, int lin_maxit, nosh_newton_result *res, int32_t *lin_iters,
                 double *fnorms);
+double weighted_sum_dev(Ctx *ctx, int mode, const double2 *a, const double2 *b);
+void compute_dfdp_dev(Ctx *ctx, int np, const char *const *names, const double *values, const char *pname,
+                      double2 *psi, double2 *out);
+void continuation_dev(Ctx *ctx, int np, const char *const *names, const double *values, const char *pname,
+                      double dp, int nsteps, double2 *psi, double nl_tol, int nl_maxit, double lin_tol,
+                      int lin_maxit, nosh_continuation_step *out);
 }  // namespace nosh

@@ -274,6 +274,43 @@ class OracleProblem:
                              fn, self.nt)
         return x, int(k), lin[:k].copy(), fn[:k + 1].copy()
 
+    # -- model-evaluator scalars as the reference's commented code states them
+    # (model_evaluator_nls.cpp:699-770; the live code returns 0.0)
+    def inner_product(self, phi, psi):
+        return float(np.sum(self.cv * (phi[0::2] * psi[0::2] + phi[1::2] * psi[1::2])) / self.cv.sum())
+
+    def gibbs_energy(self, psi):
+        a = psi[0::2] ** 2 + psi[1::2] ** 2
+        return float(-np.sum(self.cv * a * a) / self.cv.sum())
+
+    def continuation(self, g, pname, p0, dp, nsteps, psi0, theta=0.0, nl_tol=1e-8, nl_maxit=20,
+                     lin_tol=1e-10, lin_maxit=1000):
+        """Natural continuation in mu (pname == "mu") with tangent predictor -- the restatement
+        the device driver nosh_continuation is compared against.  [LOCA is not in the reference
+        tree: unpinned.]"""
+        assert pname == "mu"
+        x = np.array(psi0, np.float64)
+        recs = []
+        mu = p0
+        for k in range(nsteps + 1):
+            pred_its = 0
+            if k > 0:
+                self.keo_fill(mu, theta)
+                self.jac_rebuild(g, x)
+                self.dkeo_fill(mu, theta, "mu")
+                dF = self.compute_dfdp(x, False, np.zeros(self.N))
+                t, pred_its, _ = self.krylov(-dF, lin_tol, lin_maxit)
+                x = x + dp * t
+            mu = p0 + k * dp
+            self.keo_fill(mu, theta)
+            x, steps, lin, fn = self.newton(g, x, nl_tol, nl_maxit, lin_tol, lin_maxit)
+            recs.append(dict(step=k, param=mu, newton_steps=steps, linear_iterations=int(lin.sum()),
+                             predictor_linear_iterations=pred_its, fnorm=float(fn[-1]),
+                             gibbs_energy=self.gibbs_energy(x), norm=np.sqrt(self.inner_product(x, x))))
+            if not fn[-1] < nl_tol:
+                break
+        return x, recs
+
     # -- complex block view (for entry-wise parity with the device block-CSR) ----
     def complex_blocks(self, vals):
         """Return (rowptr_v (N+1), colv, K complex) of the complex N x N matrix the real

@@ -314,6 +314,35 @@ def test_newton(nb, orc, layout):
     ctx.close()
 
 
+def test_continuation_and_energy(nb, orc, tmp_path):
+    """Natural continuation in mu with tangent predictor: same step records as the oracle."""
+    coords, cells = orc.meshgen.tetgrid(9)
+    ctx, P, psi = make_pair(nb, orc, coords, cells, 1, group=512)
+    x = orc.meshgen.random_state(P.N, 9)
+    y = orc.meshgen.random_state(P.N, 10)
+    assert ctx.gibbs_energy(x) == pytest.approx(P.gibbs_energy(x), rel=1e-13)
+    assert ctx.inner_product(x, y) == pytest.approx(P.inner_product(x, y), rel=1e-12)
+    par = {"g": 1.0, "mu": 0.0}
+    xo, recs = P.continuation(1.0, "mu", 0.0, 0.05, 4, psi)
+    xg = psi.copy()
+    steps = ctx.continuation(par, "mu", 0.05, 4, xg)
+    assert len(steps) == len(recs) == 5
+    for s, r in zip(steps, recs):
+        assert s.step == r["step"] and s.converged == 1
+        assert s.param == pytest.approx(r["param"], abs=1e-15)
+        assert s.newton_steps == r["newton_steps"]
+        assert s.linear_iterations == r["linear_iterations"]
+        assert s.predictor_linear_iterations == r["predictor_linear_iterations"]
+        assert s.gibbs_energy == pytest.approx(r["gibbs_energy"], rel=1e-9)
+        assert s.norm == pytest.approx(r["norm"], rel=1e-9)
+    assert relerr(xg, xo) <= 1e-8
+    ctx.write_continuation_csv(str(tmp_path / "continuationData.dat"), steps, "mu")
+    assert len(open(str(tmp_path / "continuationData.dat")).read().splitlines()) == 6
+    with pytest.raises(KeyError):
+        ctx.continuation({"g": 1.0, "mu": 0.0}, "nu", 0.1, 1, xg)
+    ctx.close()
+
+
 def test_device_pointers_in_place(nb, orc):
     """torch CUDA tensors are used in place (no staging) and give the same bits as host vectors."""
     import torch
