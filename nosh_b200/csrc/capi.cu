@@ -44,12 +44,13 @@ void require_mesh(Ctx *ctx) {
 
 // input vector of 2*No doubles -> device pointer with room for ghosts when needed
 double2 *stage_in(Ctx *ctx, const double *p, DBuf<double2> &buf, bool need_ghost_room) {
-  if (!p) NOSH_THROW(NOSH_EINVAL, "NULL vector");
-  const bool dev = is_device_ptr(p);
+  if (!p && ctx->No > 0) NOSH_THROW(NOSH_EINVAL, "NULL vector");
+  const bool dev = p && is_device_ptr(p);
   if (dev && !need_ghost_room) return (double2 *)p;
   buf.ensure(ctx->Nl > 0 ? ctx->Nl : 1);
-  CUDA_CHECK(cudaMemcpyAsync(buf.p, p, sizeof(double2) * ctx->No, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                             ctx->stream));
+  if (ctx->No > 0)
+    CUDA_CHECK(cudaMemcpyAsync(buf.p, p, sizeof(double2) * ctx->No, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                               ctx->stream));
   return buf.p;
 }
 struct OutVec {
@@ -58,10 +59,10 @@ struct OutVec {
   bool host;
 };
 OutVec stage_out(Ctx *ctx, double *p, DBuf<double2> &buf) {
-  if (!p) NOSH_THROW(NOSH_EINVAL, "NULL vector");
+  if (!p && ctx->No > 0) NOSH_THROW(NOSH_EINVAL, "NULL vector");
   OutVec o;
   o.user = p;
-  o.host = !is_device_ptr(p);
+  o.host = !p || !is_device_ptr(p);
   if (o.host) {
     buf.ensure(ctx->Nl > 0 ? ctx->Nl : 1);
     o.dev = buf.p;
@@ -71,7 +72,7 @@ OutVec stage_out(Ctx *ctx, double *p, DBuf<double2> &buf) {
   return o;
 }
 void finish_out(Ctx *ctx, const OutVec &o) {
-  if (o.host) {
+  if (o.host && ctx->No > 0) {
     CUDA_CHECK(cudaMemcpyAsync(o.user, o.dev, sizeof(double2) * ctx->No, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   }

@@ -382,6 +382,45 @@ def test_layouts_agree_bitwise_on_structure(nb, orc):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_scrambled_unstructured_numbering(nb, orc, layout):
+    """Random vertex renumbering, shuffled cells, permuted cell-local vertex order (mixed
+    orientations) and one isolated vertex: irregular rows inside every SELL slice, no structure
+    for the kernels to lean on."""
+    rng = np.random.default_rng(7)
+    coords, cells = orc.meshgen.tetgrid(11)
+    N = coords.shape[0]
+    perm = rng.permutation(N)                     # old id -> new id
+    c2 = np.empty_like(coords)
+    c2[perm] = coords
+    cells2 = perm[cells].astype(np.int32)
+    cells2 = cells2[rng.permutation(cells2.shape[0])]
+    for k in range(cells2.shape[0]):
+        cells2[k] = cells2[k][rng.permutation(4)]
+    c2 = np.vstack([c2, [[20.0, 20.0, 20.0]]])    # a vertex that belongs to no cell
+    ctx, P, psi = make_pair(nb, orc, c2, cells2, layout)
+    e, ln, cov = ctx.edges()
+    assert np.array_equal(e, P.edges)
+    assert relerr(cov, P.covolume) <= RTOL and relerr(ctx.control_volumes(), P.cv) <= RTOL
+    assert ctx.control_volumes()[-1] == 0.0
+    par = {"g": 0.7, "mu": 0.9}
+    x = orc.meshgen.random_state(P.N, 1)
+    y = orc.meshgen.random_state(P.N, 2)
+    P.keo_fill(par["mu"])
+    ctx.keo_fill(par)
+    assert relerr(ctx.keo_apply(x), P.keo_apply(x)) <= RTOL
+    assert relerr(ctx.compute_f(par, x), P.compute_f(par["g"], x)) <= RTOL
+    ctx.jac_rebuild(par, x)
+    P.jac_rebuild(par["g"], x)
+    assert relerr(ctx.jac_apply(y), P.jac_apply(y)) <= RTOL
+    b = orc.meshgen.random_state(P.N, 3)
+    b[-2:] = 0.0                                   # the isolated vertex has a zero row in K
+    xo, ito, _ = P.krylov(b, 1e-8, 3000)
+    xg, res = ctx.minres(b, tol=1e-8, maxit=3000)
+    assert res.iterations == ito and relerr(xg, xo) <= 1e-7
+    ctx.close()
+
+
 def test_medium_mesh_parity(nb, orc):
     """64k vertices: geometry, assembly, F, J.x against the oracle."""
     coords, cells = orc.meshgen.tetgrid(40)
