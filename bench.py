@@ -44,9 +44,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=200, help="tetgrid vertices per axis (200 -> 8.0M vertices)")
+    # NB not "--n": torchrun's own argparse would claim it as an abbreviation of --nnodes/--nproc-per-node
+    ap.add_argument("--mesh-n", "--n", dest="n", type=int, default=200,
+                    help="tetgrid vertices per axis (200 -> 8.0M vertices)")
     ap.add_argument("--layout", default=None, choices=[None, "csr", "sell32"])
-    ap.add_argument("--cpu-n", type=int, default=56, help="sample mesh of the CPU baseline")
+    ap.add_argument("--cpu-n", type=int, default=100,
+                    help="sample mesh of the CPU baseline (100 -> 1.0M vertices = BASELINE.json configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--apply-reps", type=int, default=50)
     ap.add_argument("--workload", default="minres200", choices=["minres200", "newton", "continuation"],

@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nosh_b200  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=100)
+ap.add_argument("--n", "--mesh-n", dest="n", type=int, default=100)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--layout", default="sell32")
 a = ap.parse_args()
