@@ -49,7 +49,7 @@ __device__ __forceinline__ bool krylov_skip(const ApplyArgs &A) {
 template <int EPI, int FUSE, int U>
 __global__ void __launch_bounds__(CHUNK, 2) k_apply_sell(const ApplyArgs A) {
   if (krylov_skip<FUSE>(A)) return;
-  __shared__ double red[CHUNK / 32];
+  __shared__ double red[32];
   const int chunk = A.chunk_list ? __ldg(A.chunk_list + blockIdx.x) : (int)blockIdx.x;
   const int64_t row = (int64_t)chunk * CHUNK + threadIdx.x;
   const int64_t slice = row >> 5;
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(CHUNK, 2) k_apply_sell(const ApplyArgs A) {
   if (FUSE == FUSE_MINRES || FUSE == FUSE_CG) {
     const double s = block_sum<CHUNK / 32>(contrib, red);
     if (threadIdx.x == 0) A.partials[chunk] = s;
+    last_cta_finalize(A.fin, red);
   }
 }
 
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(CHUNK, 2) k_apply_sell(const ApplyArgs A) {
 template <int EPI, int FUSE, int LPR>
 __global__ void __launch_bounds__(CHUNK, 2) k_apply_csr(const ApplyArgs A) {
   if (krylov_skip<FUSE>(A)) return;
-  __shared__ double red[CHUNK / 32];
+  __shared__ double red[32];
   constexpr int RPP = CHUNK / LPR;  // rows per pass
   const int chunk = A.chunk_list ? __ldg(A.chunk_list + blockIdx.x) : (int)blockIdx.x;
   const int sub = threadIdx.x / LPR, sl = threadIdx.x % LPR;
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(CHUNK, 2) k_apply_csr(const ApplyArgs A) {
   if (FUSE == FUSE_MINRES || FUSE == FUSE_CG) {
     const double s = block_sum<CHUNK / 32>(contrib, red);
     if (threadIdx.x == 0) A.partials[chunk] = s;
+    last_cta_finalize(A.fin, red);
   }
 }
 

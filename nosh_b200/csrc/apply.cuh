@@ -20,6 +20,7 @@
 //   CSR     : LPR lanes per row + xor-shuffle reduction
 #pragma once
 #include "common.cuh"
+#include "reduce.cuh"
 
 namespace nosh {
 
@@ -50,6 +51,8 @@ struct ApplyArgs {
   // optional list of chunks to process (interior / boundary split); NULL = all chunks
   const int32_t *chunk_list;
   int n_list;
+  // FUSE_MINRES / FUSE_CG on one GPU: the last CTA finishes the reduction (fin.counter != NULL)
+  FinArgs fin;
 };
 
 void launch_apply(Ctx *ctx, int epi, int fuse, const ApplyArgs &A);

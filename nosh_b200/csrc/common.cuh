@@ -202,6 +202,7 @@ struct Ctx {
   DBuf<double> partials;            // 2 x n_chunks
   DBuf<double> group_sums;          // 2 x MAX_GROUPS (global group index)
   DBuf<KrylovState> kstate;
+  DBuf<unsigned int> ticket;        // last-CTA ticket counter of the in-kernel reductions
   DBuf<double> hist;
   DBuf<double> scalar_out;          // misc device scalars
   int64_t n_chunks = 0;

@@ -17,15 +17,16 @@
 // any number of GPUs.
 #include "krylov.h"
 
+#include <cstdlib>
+
 #include "apply.cuh"
 #include "comm.h"
+#include "reduce.cuh"
 #include "keo.h"
 
 namespace nosh {
 
 namespace {
-
-enum { FIN_DOT = 0, FIN_MINRES_INIT, FIN_MINRES_ALPHA, FIN_MINRES_BETA, FIN_CG_INIT, FIN_CG_PAP, FIN_CG_RHO };
 
 #define KLAUNCH(ctx, kernel, grid, block, ...)                    \
   do {                                                            \
@@ -37,21 +38,24 @@ enum { FIN_DOT = 0, FIN_MINRES_INIT, FIN_MINRES_ALPHA, FIN_MINRES_BETA, FIN_CG_I
 // ---- chunked vector kernels: one CTA (256 threads) per CHUNK = 512 vertices ------------------
 __device__ __forceinline__ double cdot(double2 a, double2 b) { return a.x * b.x + a.y * b.y; }
 
-__global__ void __launch_bounds__(TPB) k_dot(const double2 *x, const double2 *y, int64_t No, double *partials) {
-  __shared__ double red[TPB / 32];
+__global__ void __launch_bounds__(TPB) k_dot(const double2 *x, const double2 *y, int64_t No, double *partials,
+        const FinArgs fin) {
+  __shared__ double red[32];
   const int64_t i0 = (int64_t)blockIdx.x * CHUNK + threadIdx.x, i1 = i0 + TPB;
   double c = 0.0;
   if (i0 < No) c = cdot(x[i0], y[i0]);
   if (i1 < No) c += cdot(x[i1], y[i1]);
   const double s = block_sum<TPB / 32>(c, red);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
+  last_cta_finalize(fin, red);
 }
 
 // control-volume weighted sums: mode 0: sum c_k; 1: sum c_k Re(conj(a_k) b_k)  (nls::inner_product,
 // src/model_evaluator_nls.cpp:699-739); 2: -sum c_k |a_k|^4  (nls::gibbs_energy, :742-770)
 __global__ void __launch_bounds__(TPB) k_weighted(int mode, const double *cv, const double2 *a, const double2 *b,
-                                                  int64_t No, double *partials) {
-  __shared__ double red[TPB / 32];
+                                                  int64_t No, double *partials,
+        const FinArgs fin) {
+  __shared__ double red[32];
   double c = 0.0;
 #pragma unroll
   for (int h = 0; h < 2; h++) {
@@ -69,12 +73,14 @@ __global__ void __launch_bounds__(TPB) k_weighted(int mode, const double *cv, co
   }
   const double s = block_sum<TPB / 32>(c, red);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
+  last_cta_finalize(fin, red);
 }
 
 __global__ void __launch_bounds__(TPB) k_minres_init(const double2 *b, double bscale, int64_t No, double2 *r0,
                                                      double2 *w0, double2 *w1, double2 *w2, double2 *x,
-                                                     double *partials) {
-  __shared__ double red[TPB / 32];
+                                                     double *partials,
+        const FinArgs fin) {
+  __shared__ double red[32];
   double c = 0.0;
 #pragma unroll
   for (int h = 0; h < 2; h++) {
@@ -94,13 +100,15 @@ __global__ void __launch_bounds__(TPB) k_minres_init(const double2 *b, double bs
   }
   const double s = block_sum<TPB / 32>(c, red);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
+  last_cta_finalize(fin, red);
 }
 
 __global__ void __launch_bounds__(TPB) k_minres_B(const KrylovState *st, int host_iter, const double2 *p,
                                                   const double2 *r2, double2 *rnew, int64_t No,
-                                                  double *partials) {
+                                                  double *partials,
+        const FinArgs fin) {
   if (st->done || st->iter != host_iter - 1) return;
-  __shared__ double red[TPB / 32];
+  __shared__ double red[32];
   const double f = st->f_r2;
   const int64_t i0 = (int64_t)blockIdx.x * CHUNK + threadIdx.x, i1 = i0 + TPB;
   double2 p0, p1, q0, q1;
@@ -119,6 +127,7 @@ __global__ void __launch_bounds__(TPB) k_minres_B(const KrylovState *st, int hos
   }
   const double s = block_sum<TPB / 32>(c, red);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
+  last_cta_finalize(fin, red);
 }
 
 __global__ void __launch_bounds__(TPB) k_minres_C(const KrylovState *st, int host_iter, const double2 *rcur,
@@ -145,8 +154,9 @@ __global__ void __launch_bounds__(TPB) k_minres_C(const KrylovState *st, int hos
 
 // ---- CG vector kernels --------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_cg_init(const double2 *b, double bscale, int64_t No, double2 *r,
-                                                 double2 *p, double2 *x, double *partials) {
-  __shared__ double red[TPB / 32];
+                                                 double2 *p, double2 *x, double *partials,
+        const FinArgs fin) {
+  __shared__ double red[32];
   double c = 0.0;
 #pragma unroll
   for (int h = 0; h < 2; h++) {
@@ -163,12 +173,14 @@ __global__ void __launch_bounds__(TPB) k_cg_init(const double2 *b, double bscale
   }
   const double s = block_sum<TPB / 32>(c, red);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
+  last_cta_finalize(fin, red);
 }
 __global__ void __launch_bounds__(TPB) k_cg_update(const KrylovState *st, int host_iter, const double2 *p,
                                                    const double2 *ap, double2 *r, double2 *x, int64_t No,
-                                                   double *partials) {
+                                                   double *partials,
+        const FinArgs fin) {
   if (st->done || st->iter != host_iter - 1) return;
-  __shared__ double red[TPB / 32];
+  __shared__ double red[32];
   const double al = st->cg_alpha;
   double c = 0.0;
 #pragma unroll
@@ -188,6 +200,7 @@ __global__ void __launch_bounds__(TPB) k_cg_update(const KrylovState *st, int ho
   }
   const double s = block_sum<TPB / 32>(c, red);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
+  last_cta_finalize(fin, red);
 }
 __global__ void __launch_bounds__(TPB) k_cg_direction(const KrylovState *st, int host_iter, const double2 *r,
                                                       double2 *p, int64_t No) {
@@ -248,236 +261,26 @@ __global__ void k_keoreg_diags(double g, const double *cv, const double *thick, 
   d1[k] = be;
 }
 
-// ---- finalize: levels 2 and 3 of the reduction tree + the scalar recurrences ------------------------
-struct FinArgs {
-  const double *partials;
-  int64_t n_chunks;
-  int cpg;
-  int64_t group_begin, n_groups_local;
-  int n_groups_global;
-  double *gsend;        // MAX_GROUPS, global group index; zero outside the local groups
-  const double *grecv;  // all-reduced copy (== gsend on one GPU)
-  KrylovState *st;
-  double *out;
-  double *hist;
-  int what, host_iter, stage;  // stage 0: single GPU; 1: level 2 only; 2: level 3 + scalars;
-                               // 3: one kernel, group sums exchanged through peer memory
-  double tol;
-  int maxit;
-  P2PView p2p;
-};
-
-__device__ __forceinline__ void sym_ortho(double a, double b, double &c, double &s, double &r) {
-  const double absA = fabs(a), absB = fabs(b);
-  if (absB == 0.0) {
-    s = 0.0;
-    r = absA;
-    c = (absA == 0.0) ? 1.0 : (a >= 0.0 ? 1.0 : -1.0);
-  } else if (absA == 0.0) {
-    c = 0.0;
-    s = (b >= 0.0 ? 1.0 : -1.0);
-    r = absB;
-  } else if (absB >= absA) {
-    const double tau = a / b;
-    s = (b >= 0.0 ? 1.0 : -1.0) / sqrt(1.0 + tau * tau);
-    c = s * tau;
-    r = b / s;
-  } else {
-    const double tau = b / a;
-    c = (a >= 0.0 ? 1.0 : -1.0) / sqrt(1.0 + tau * tau);
-    s = c * tau;
-    r = a / c;
-  }
-}
-
-__device__ void fin_scalars(const FinArgs &F, double total) {
-  KrylovState *st = F.st;
-  switch (F.what) {
-    case FIN_DOT:
-      F.out[0] = total;
-      break;
-    case FIN_MINRES_INIT: {
-      KrylovState s;
-      memset(&s, 0, sizeof(s));
-      s.tol = F.tol;
-      s.maxit = F.maxit;
-      if (total <= 0.0) {
-        s.done = 1;
-        s.converged = 1;
-        s.inv_beta = 0.0;
-      } else {
-        s.beta1 = sqrt(total);
-        s.beta = s.beta1;
-        s.phibar = s.beta1;
-        s.cs = -1.0;
-        s.sn = 0.0;
-        s.inv_beta = 1.0 / s.beta1;
-        s.relres = 1.0;
-        if (F.maxit <= 0 || 1.0 <= F.tol) {
-          s.done = 1;
-          s.converged = 1.0 <= F.tol;
-        }
-      }
-      *st = s;
-      if (F.hist) F.hist[0] = 1.0;
-      break;
-    }
-    case FIN_MINRES_ALPHA:
-      st->alpha = total;
-      st->f_r2 = total / st->beta;
-      break;
-    case FIN_MINRES_BETA: {
-      if (total < 0.0) {
-        st->done = 1;
-        st->breakdown = 1;
-        break;
-      }
-      const double betaNew = sqrt(total);
-      const double oldeps = st->epsln;
-      const double delta = st->cs * st->dbar + st->sn * st->alpha;
-      const double gbar = st->sn * st->dbar - st->cs * st->alpha;
-      st->epsln = st->sn * betaNew;
-      st->dbar = -st->cs * betaNew;
-      double cs, sn, gamma;
-      sym_ortho(gbar, betaNew, cs, sn, gamma);
-      st->cs = cs;
-      st->sn = sn;
-      st->gamma = gamma;
-      st->gbar = gbar;
-      st->phi = cs * st->phibar;
-      st->phibar = sn * st->phibar;
-      if (gamma == 0.0) {
-        st->done = 1;
-        st->breakdown = 1;
-        break;
-      }
-      st->oldeps = oldeps;
-      st->delta = delta;
-      st->inv_gamma = 1.0 / gamma;
-      st->inv_beta_prev = st->inv_beta;
-      st->oldBeta = st->beta;
-      st->beta = betaNew;
-      st->inv_beta = 1.0 / betaNew;
-      st->f_r1 = betaNew / st->oldBeta;
-      st->iter += 1;
-      st->relres = st->phibar / st->beta1;
-      if (F.hist) F.hist[st->iter] = st->relres;
-      if (st->relres <= st->tol) {
-        st->done = 1;
-        st->converged = 1;
-      } else if (st->iter >= st->maxit) {
-        st->done = 1;
-      }
-      break;
-    }
-    case FIN_CG_INIT: {
-      KrylovState s;
-      memset(&s, 0, sizeof(s));
-      s.tol = F.tol;
-      s.maxit = F.maxit;
-      s.rho = total;
-      s.r0norm = sqrt(total);
-      s.relres = 1.0;
-      if (s.r0norm == 0.0) {
-        s.done = 1;
-        s.converged = 1;
-        s.relres = 0.0;
-      } else if (F.maxit <= 0 || 1.0 <= F.tol) {
-        s.done = 1;
-        s.converged = 1.0 <= F.tol;
-      }
-      *st = s;
-      if (F.hist) F.hist[0] = 1.0;
-      break;
-    }
-    case FIN_CG_PAP:
-      st->pAp = total;
-      st->cg_alpha = st->rho / total;
-      break;
-    case FIN_CG_RHO: {
-      st->cg_beta = total / st->rho;
-      st->rho = total;
-      st->iter += 1;
-      st->relres = sqrt(total) / st->r0norm;
-      if (F.hist) F.hist[st->iter] = st->relres;
-      if (st->relres <= st->tol) {
-        st->done = 1;
-        st->converged = 1;
-      } else if (st->iter >= st->maxit) {
-        st->done = 1;
-      }
-      break;
-    }
-  }
-}
-
 __global__ void __launch_bounds__(1024) k_finalize(const FinArgs F) {
-  const bool iterative = F.what == FIN_MINRES_ALPHA || F.what == FIN_MINRES_BETA || F.what == FIN_CG_PAP ||
-                         F.what == FIN_CG_RHO;
-  if (iterative && (F.st->done || F.st->iter != F.host_iter - 1)) return;
+  if (fin_is_iterative(F.what) && (F.st->done || F.st->iter != F.host_iter - 1)) return;
   __shared__ double sm[32];
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (F.stage != 2) {
-    // level 2: one warp per group, each lane a fixed run of consecutive chunk partials
-    const int per = (F.cpg + 31) / 32;
-    for (int64_t g = w; g < F.n_groups_local; g += 32) {
-      const int64_t base = g * F.cpg;
-      double s = 0.0;
-      for (int t = 0; t < per; t++) {
-        const int k = l * per + t;
-        if (k < F.cpg && base + k < F.n_chunks) s += F.partials[base + k];
-      }
-      s = warp_sum(s);
-      if (l == 0) F.gsend[F.group_begin + g] = s;
-    }
-    if (F.stage == 1) return;
-    __syncthreads();
-  }
-  const double *gs = F.stage == 2 ? F.grecv : F.gsend;
-  if (F.stage == 3) {
-    // all-gather of the group sums over NVLink: store mine into every rank's slot (own included),
-    // publish an epoch flag to every rank, wait for everybody's flag.  Ranks are never more
-    // than one reduction apart, so two slots are enough.  Peer r's flag also tells me that all
-    // NVLink stores r issued before it (its halo push) have landed.
-    const P2PView &q = F.p2p;
-    const int slot = (int)(q.epoch & 1ull);
-    const int nloc = (int)F.n_groups_local;
-    for (int i = threadIdx.x; i < nloc * q.P; i += blockDim.x) {
-      const int r = i / nloc, g = (int)F.group_begin + i % nloc;
-      q.red[r][slot * MAX_GROUPS + g] = F.gsend[g];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < q.P) {
-      *((volatile unsigned long long *)&q.flags[threadIdx.x][q.me]) = q.epoch;
-      const volatile unsigned long long *mine = (const volatile unsigned long long *)&q.flags[q.me][threadIdx.x];
-      const long long t0 = clock64();
-      while (*mine < q.epoch) {
-        if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer is gone; fail instead of hanging
-          *q.err = 1;
-          break;
-        }
-      }
-    }
-    __syncthreads();
-    __threadfence_system();
-    gs = q.red[q.me] + slot * MAX_GROUPS;
-  }
-  // level 3: fixed tree over the (<= 1024) group sums of the whole mesh
-  double v = (int)threadIdx.x < F.n_groups_global ? __ldcg(gs + threadIdx.x) : 0.0;
-  v = warp_sum(v);
-  if (l == 0) sm[w] = v;
-  __syncthreads();
-  if (w == 0) {
-    double t = sm[l];
-    t = warp_sum(t);
-    if (l == 0) fin_scalars(F, t);
-  }
+  finalize_levels<true>(F, sm);
 }
 
-void finalize(Ctx *ctx, int which_partials, int what, int host_iter, double tol, int maxit, double *out) {
+// Reduction descriptor.  Default: finalize_launch() runs the one-CTA k_finalize kernel after the
+// producer.  With NOSH_B200_INKERNEL_FIN=1 (one GPU) the producer's last CTA finishes the reduction
+// itself (fin.counter set).  MEASURED SLOWER on B200 (profiles/r1_summary.md, section 4): the
+// __threadfence() every CTA needs before taking its ticket invalidates the SM's L1 (CCTL.IVALL), which
+// the x gathers of the co-resident SpMV CTAs live on: 151.4 vs 140.4 ms per 200-iteration step.
+FinArgs fin_args(Ctx *ctx, int what, int host_iter, double tol, int maxit, double *out, bool in_kernel = true) {
+  static const bool enabled = [] {
+    const char *e = getenv("NOSH_B200_INKERNEL_FIN");
+    return e && atoi(e) != 0;
+  }();
+  in_kernel = in_kernel && enabled;
   FinArgs F;
-  F.partials = ctx->partials.p + which_partials * ctx->n_chunks;
+  memset(&F, 0, sizeof(F));
+  F.partials = ctx->partials.p;
   F.n_chunks = ctx->n_chunks;
   F.cpg = ctx->chunks_per_group;
   F.group_begin = ctx->group_begin;
@@ -492,6 +295,13 @@ void finalize(Ctx *ctx, int which_partials, int what, int host_iter, double tol,
   F.host_iter = host_iter;
   F.tol = tol;
   F.maxit = maxit;
+  F.stage = 0;
+  F.counter = (in_kernel && ctx->nranks == 1 && ctx->n_chunks > 0) ? ctx->ticket.p : nullptr;
+  return F;
+}
+
+void finalize_launch(Ctx *ctx, FinArgs &F) {
+  if (F.counter) return;  // already done by the producer's last CTA
   if (ctx->nranks == 1) {
     F.stage = 0;
     KLAUNCH(ctx, k_finalize, 1, 1024, F);
@@ -574,13 +384,18 @@ void ensure_work(Ctx *ctx) {
     CUDA_CHECK(cudaMemsetAsync(ctx->group_sums.p, 0, sizeof(double) * 2 * MAX_GROUPS, ctx->stream));
   }
   if (!ctx->kstate.p) ctx->kstate.alloc(1);
+  if (!ctx->ticket.p) {
+    ctx->ticket.alloc(1);
+    CUDA_CHECK(cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned int), ctx->stream));
+  }
   if (!ctx->scalar_out.p) ctx->scalar_out.alloc(8);
 }
 
 double dot_dev(Ctx *ctx, const double2 *x, const double2 *y) {
   ensure_work(ctx);
-  if (ctx->n_chunks) KLAUNCH(ctx, k_dot, (unsigned)ctx->n_chunks, TPB, x, y, ctx->No, ctx->partials.p);
-  finalize(ctx, 0, FIN_DOT, 0, 0.0, 0, ctx->scalar_out.p);
+  FinArgs F = fin_args(ctx, FIN_DOT, 0, 0.0, 0, ctx->scalar_out.p);
+  if (ctx->n_chunks) KLAUNCH(ctx, k_dot, (unsigned)ctx->n_chunks, TPB, x, y, ctx->No, ctx->partials.p, F);
+  finalize_launch(ctx, F);
   double h;
   CUDA_CHECK(cudaMemcpyAsync(&h, ctx->scalar_out.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -589,8 +404,10 @@ double dot_dev(Ctx *ctx, const double2 *x, const double2 *y) {
 
 double weighted_sum_dev(Ctx *ctx, int mode, const double2 *a, const double2 *b) {
   ensure_work(ctx);
-  if (ctx->n_chunks) KLAUNCH(ctx, k_weighted, (unsigned)ctx->n_chunks, TPB, mode, ctx->cv.p, a, b, ctx->No, ctx->partials.p);
-  finalize(ctx, 0, FIN_DOT, 0, 0.0, 0, ctx->scalar_out.p);
+  FinArgs F = fin_args(ctx, FIN_DOT, 0, 0.0, 0, ctx->scalar_out.p);
+  if (ctx->n_chunks)
+    KLAUNCH(ctx, k_weighted, (unsigned)ctx->n_chunks, TPB, mode, ctx->cv.p, a, b, ctx->No, ctx->partials.p, F);
+  finalize_launch(ctx, F);
   double h;
   CUDA_CHECK(cudaMemcpyAsync(&h, ctx->scalar_out.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -655,9 +472,10 @@ void minres_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_ou
   double2 *X = x_out;
   const unsigned grid = (unsigned)ctx->n_chunks;
   const int64_t No = ctx->No;
-  if (grid) KLAUNCH(ctx, k_minres_init, grid, TPB, b, bscale, No, R[0], W[0], W[1], W[2], X, ctx->partials.p);
+  FinArgs F = fin_args(ctx, FIN_MINRES_INIT, 0, tol, maxit, nullptr);
+  if (grid) KLAUNCH(ctx, k_minres_init, grid, TPB, b, bscale, No, R[0], W[0], W[1], W[2], X, ctx->partials.p, F);
   if (ctx->nranks > 1 && ctx->p2p.ok) p2p_halo_push(ctx, 0, R[0]);  // r_1 ghosts; ordered by the reduction below
-  finalize(ctx, 0, FIN_MINRES_INIT, 0, tol, maxit, nullptr);
+  finalize_launch(ctx, F);
   KrylovState hs;
   int check = 4;
   // Multi-GPU schedule (same arithmetic, two streams): the halo of r_h travels on stream2
@@ -690,6 +508,9 @@ void minres_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_ou
         CUDA_CHECK(cudaEventRecord(ctx->e_c, S1));
       }
       // A on the chunks that need no ghost value, then (halo landed) on the rest
+      FinArgs Fa = fin_args(ctx, FIN_MINRES_ALPHA, h, tol, maxit, nullptr, false);
+      FinArgs Fb = fin_args(ctx, FIN_MINRES_BETA, h, tol, maxit, nullptr, false);
+      A.fin = Fa;
       A.chunk_list = ctx->chunks_int.p;
       A.n_list = (int)ctx->n_chunks_int;
       launch_apply(ctx, epi, FUSE_MINRES, A);
@@ -697,22 +518,26 @@ void minres_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_ou
       A.chunk_list = ctx->chunks_bnd.p;
       A.n_list = (int)ctx->n_chunks_bnd;
       launch_apply(ctx, epi, FUSE_MINRES, A);
-      finalize(ctx, 0, FIN_MINRES_ALPHA, h, tol, maxit, nullptr);
+      finalize_launch(ctx, Fa);
       if (h > 1) CUDA_CHECK(cudaStreamWaitEvent(S0, ctx->e_c, 0));
-      if (grid) KLAUNCH(ctx, k_minres_B, grid, TPB, ctx->kstate.p, h, Pv, rcur, rprev, No, ctx->partials.p);
+      if (grid) KLAUNCH(ctx, k_minres_B, grid, TPB, ctx->kstate.p, h, Pv, rcur, rprev, No, ctx->partials.p, Fb);
       CUDA_CHECK(cudaEventRecord(ctx->e_b, S0));
-      finalize(ctx, 0, FIN_MINRES_BETA, h, tol, maxit, nullptr);
+      finalize_launch(ctx, Fb);
       CUDA_CHECK(cudaEventRecord(ctx->e_finb, S0));
     } else {
       // A: y = J v - (beta/oldBeta) r_prev, partials <v,y>
+      // (one GPU: the last CTA of A / B finishes the reduction and the scalar recurrences itself)
+      FinArgs Fa = fin_args(ctx, FIN_MINRES_ALPHA, h, tol, maxit, nullptr);
+      FinArgs Fb = fin_args(ctx, FIN_MINRES_BETA, h, tol, maxit, nullptr);
+      A.fin = Fa;
       launch_apply(ctx, epi, FUSE_MINRES, A);
-      finalize(ctx, 0, FIN_MINRES_ALPHA, h, tol, maxit, nullptr);
+      finalize_launch(ctx, Fa);
       // B: r_next = y - (alpha/beta) r_cur  (written over r_prev)
-      if (grid) KLAUNCH(ctx, k_minres_B, grid, TPB, ctx->kstate.p, h, Pv, rcur, rprev, No, ctx->partials.p);
+      if (grid) KLAUNCH(ctx, k_minres_B, grid, TPB, ctx->kstate.p, h, Pv, rcur, rprev, No, ctx->partials.p, Fb);
       // multi-GPU, peer-memory path: push the boundary entries of r_next into the neighbours'
       // ghost segments; the beta reduction that follows is also the barrier that orders them
       if (p2p) p2p_halo_push(ctx, h & 1, rprev);
-      finalize(ctx, 0, FIN_MINRES_BETA, h, tol, maxit, nullptr);
+      finalize_launch(ctx, Fb);
       // C: w_h, x
       if (grid)
         KLAUNCH(ctx, k_minres_C, grid, TPB, ctx->kstate.p, h, rcur, W[(h + 1) % 3], W[(h + 2) % 3], W[h % 3], X, No);
@@ -756,8 +581,9 @@ void cg_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_out, d
   double2 *Rv = ctx->work[0].p, *Pd = ctx->work[1].p, *AP = ctx->work[2].p, *X = x_out;
   const unsigned grid = (unsigned)ctx->n_chunks;
   const int64_t No = ctx->No;
-  if (grid) KLAUNCH(ctx, k_cg_init, grid, TPB, b, bscale, No, Rv, Pd, X, ctx->partials.p);
-  finalize(ctx, 0, FIN_CG_INIT, 0, tol, maxit, nullptr);
+  FinArgs F = fin_args(ctx, FIN_CG_INIT, 0, tol, maxit, nullptr);
+  if (grid) KLAUNCH(ctx, k_cg_init, grid, TPB, b, bscale, No, Rv, Pd, X, ctx->partials.p, F);
+  finalize_launch(ctx, F);
   KrylovState hs;
   int check = 4;
   for (int h = 1; h <= maxit; h++) {
@@ -765,10 +591,13 @@ void cg_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_out, d
     A.x = Pd;
     A.y = AP;
     A.host_iter = h;
+    FinArgs Fa = fin_args(ctx, FIN_CG_PAP, h, tol, maxit, nullptr);
+    FinArgs Fb = fin_args(ctx, FIN_CG_RHO, h, tol, maxit, nullptr);
+    A.fin = Fa;
     launch_apply(ctx, epi, FUSE_CG, A);
-    finalize(ctx, 0, FIN_CG_PAP, h, tol, maxit, nullptr);
-    if (grid) KLAUNCH(ctx, k_cg_update, grid, TPB, ctx->kstate.p, h, Pd, AP, Rv, X, No, ctx->partials.p);
-    finalize(ctx, 0, FIN_CG_RHO, h, tol, maxit, nullptr);
+    finalize_launch(ctx, Fa);
+    if (grid) KLAUNCH(ctx, k_cg_update, grid, TPB, ctx->kstate.p, h, Pd, AP, Rv, X, No, ctx->partials.p, Fb);
+    finalize_launch(ctx, Fb);
     if (grid) KLAUNCH(ctx, k_cg_direction, grid, TPB, ctx->kstate.p, h, Rv, Pd, No);
     if (h % check == 0 || h == maxit) {
       if (poll_done(ctx, &hs)) break;
