@@ -69,6 +69,17 @@ typedef enum { NOSH_MAT_KEO = 0, NOSH_MAT_DKEO = 1 } nosh_matrix_id;
 /* linear operator selector for the Krylov solvers */
 typedef enum { NOSH_OP_JACOBIAN = 0, NOSH_OP_KEO = 1, NOSH_OP_KEOREG = 2 } nosh_operator_id;
 
+/* preconditioner selector of the Krylov solvers: none (the live reference path,
+ * src/model_evaluator_nls.cpp:291) or one AMG V-cycle on the regularised KEO -- what
+ * create_W_prec hands to the solver (src/model_evaluator_nls.cpp:301-314) */
+typedef enum { NOSH_PREC_NONE = 0, NOSH_PREC_KEOREG_AMG = 1 } nosh_precond;
+
+/* hierarchy reuse across nosh_keoreg_rebuild calls: NONE = new hierarchy per rebuild; FULL = the
+ * reference's MueLu setting "reuse: type" = "full" (src/keo_regularized.cpp:300): aggregates,
+ * prolongators and coarse operators of the first build are kept, the finest level follows the
+ * current matrix */
+typedef enum { NOSH_AMG_REUSE_NONE = 0, NOSH_AMG_REUSE_FULL = 1 } nosh_amg_reuse;
+
 /* ---- lifecycle ------------------------------------------------------------- */
 NOSH_API const char *nosh_version(void);
 /* stream: a cudaStream_t (as void*) all work is enqueued on, or NULL for a
@@ -198,10 +209,16 @@ NOSH_API nosh_status nosh_compute_dfdp(nosh_ctx *ctx, int np, const char *const 
                                        const double *values, const char *pname, const double *psi,
                                        double *dfdp);
 
-/* ---- preconditioner matrix (a16).  keo_regularized::rebuild
+/* ---- preconditioner (a16, a17).  keo_regularized::rebuild
  * (src/keo_regularized.cpp:181-264): P = K + blockdiag([[al+ga, be],[be, al-ga]]), g > 0
- * only.  nosh_keoreg_matrix_apply applies P (not its inverse).  The inverse (one MueLu
- * V-cycle, :106-108) is third-party AMG: nosh_keoreg_apply returns NOSH_EUNSUPPORTED. */
+ * only.  nosh_keoreg_matrix_apply applies P.  nosh_keoreg_apply is keo_regularized::apply
+ * (:88-165): ONE V-cycle of a smoothed-aggregation AMG hierarchy for P with 2 equations per
+ * node.  The reference gets that hierarchy from MueLu (third party, not in its tree:
+ * parity unpinned); here it is built and applied on the device (nosh_b200/csrc/amg.cu,
+ * restated on the CPU in oracle/amg.py).  Like the reference's apply it supports only
+ * NO_TRANS, alpha == 1, beta == 0 (:98-100).  The hierarchy is built lazily by the first
+ * apply / preconditioned solve after a rebuild and kept according to the reuse policy.
+ * With several GPUs every rank preconditions its own diagonal block (no communication). */
 NOSH_API nosh_status nosh_keoreg_rebuild(nosh_ctx *ctx, int np, const char *const *names,
                                          const double *values, const double *psi);
 NOSH_API nosh_status nosh_keoreg_matrix_apply(nosh_ctx *ctx, const double *X, int64_t ldx,
@@ -210,6 +227,34 @@ NOSH_API nosh_status nosh_keoreg_get_diags(nosh_ctx *ctx, double *d0 /* 2n */, d
 NOSH_API nosh_status nosh_keoreg_apply(nosh_ctx *ctx, const double *X, int64_t ldx, double *Y,
                                        int64_t ldy, int nvec, nosh_transp mode, double alpha,
                                        double beta);
+
+/* AMG options (before the hierarchy is built; changing them drops it): Chebyshev degree of the
+ * pre-/post-smoother (>= 1; 1 = damped Jacobi), number of nodes at which coarsening stops and a
+ * dense inverse is used (<= 4096), maximum number of levels, reuse policy.  Values <= 0 (reuse
+ * < 0) keep the current setting.  Defaults: 1, 512, 10, FULL. */
+NOSH_API nosh_status nosh_amg_set_options(nosh_ctx *ctx, int degree, int coarse_max, int max_levels,
+                                          int reuse);
+/* (re)build the hierarchy now for the current regularised KEO */
+NOSH_API nosh_status nosh_amg_setup(nosh_ctx *ctx);
+#define NOSH_AMG_MAX_LEVELS 16
+typedef struct {
+  int32_t levels;
+  int32_t degree;
+  int64_t nodes[NOSH_AMG_MAX_LEVELS];     /* block rows per level */
+  int64_t blocks[NOSH_AMG_MAX_LEVELS];    /* 2x2 blocks per level (level 0: complex blocks of the owned columns) */
+  int64_t p_blocks[NOSH_AMG_MAX_LEVELS];  /* blocks of the prolongator from level l+1 to l */
+  double lambda_max[NOSH_AMG_MAX_LEVELS]; /* estimate of lambda_max(D^-1 A) */
+  double setup_seconds;
+} nosh_amg_info_t;
+NOSH_API nosh_status nosh_amg_info(nosh_ctx *ctx, nosh_amg_info_t *info);
+/* parity accessors (host outputs, any may be NULL): aggregate of every node of `level`;
+ * block CSR of the level matrix (level >= 1) / of the prolongator from level+1 to level:
+ * rowptr (rows+1, int64), cols, vals (4 doubles per block, row-major 2x2) */
+NOSH_API nosh_status nosh_amg_get_aggregates(nosh_ctx *ctx, int level, int32_t *agg);
+NOSH_API nosh_status nosh_amg_get_matrix(nosh_ctx *ctx, int level, int64_t *rowptr, int32_t *cols,
+                                         double *vals);
+NOSH_API nosh_status nosh_amg_get_prolongator(nosh_ctx *ctx, int level, int64_t *rowptr, int32_t *cols,
+                                              double *vals);
 
 /* ---- vector reductions (Tpetra::MultiVector::dot / norm2; partition independent) */
 NOSH_API nosh_status nosh_dot(nosh_ctx *ctx, const double *x, const double *y, double *result);
@@ -228,6 +273,19 @@ NOSH_API nosh_status nosh_minres(nosh_ctx *ctx, nosh_operator_id op, const doubl
                                  double tol, int maxit, nosh_krylov_result *res, double *hist);
 NOSH_API nosh_status nosh_cg(nosh_ctx *ctx, nosh_operator_id op, const double *b, double *x,
                              double tol, int maxit, nosh_krylov_result *res, double *hist);
+/* The same solvers with a preconditioner M (Belos with a left preconditioner from
+ * Thyra::nonconstUnspecifiedPrec, src/model_evaluator_nls.cpp:313).  MINRES: beta_k^2 = <r_k, M r_k>,
+ * stop on the implicit M-norm residual phibar / beta_1 <= tol.  CG: stop on ||r||_2 / ||r_0||_2. */
+NOSH_API nosh_status nosh_minres_prec(nosh_ctx *ctx, nosh_operator_id op, nosh_precond prec,
+                                      const double *b, double *x, double tol, int maxit,
+                                      nosh_krylov_result *res, double *hist);
+NOSH_API nosh_status nosh_cg_prec(nosh_ctx *ctx, nosh_operator_id op, nosh_precond prec, const double *b,
+                                  double *x, double tol, int maxit, nosh_krylov_result *res,
+                                  double *hist);
+/* preconditioner the Newton / continuation drivers give their linear solves (default NONE);
+ * with KEOREG_AMG every Newton step also does keo_regularized::rebuild at the current state,
+ * the evalModel(W_prec) of src/model_evaluator_nls.cpp:507-522 */
+NOSH_API nosh_status nosh_ctx_set_preconditioner(nosh_ctx *ctx, nosh_precond prec);
 
 /* ---- Newton.  NOX "Line Search Based"/"Full Step" with a NormF test as configured in
  * examples/conf.xml:76-191, driving evalModel(f), evalModel(W_op) and the MINRES solve

@@ -17,6 +17,9 @@ NO_TRANS, TRANS, CONJ_TRANS = 0, 1, 2
 LAYOUT_CSR, LAYOUT_SELL32 = 0, 1
 MAT_KEO, MAT_DKEO = 0, 1
 OP_JACOBIAN, OP_KEO, OP_KEOREG = 0, 1, 2
+PREC_NONE, PREC_KEOREG_AMG = 0, 1
+AMG_REUSE_NONE, AMG_REUSE_FULL = 0, 1
+AMG_MAX_LEVELS = 16
 
 
 class MeshInfo(C.Structure):
@@ -34,6 +37,12 @@ class ContinuationStep(C.Structure):
                 ("linear_iterations", C.c_int32), ("predictor_linear_iterations", C.c_int32),
                 ("reserved", C.c_int32), ("param", C.c_double), ("gibbs_energy", C.c_double),
                 ("norm", C.c_double), ("fnorm", C.c_double)]
+
+
+class AmgInfo(C.Structure):
+    _fields_ = [("levels", C.c_int32), ("degree", C.c_int32), ("nodes", C.c_int64 * AMG_MAX_LEVELS),
+                ("blocks", C.c_int64 * AMG_MAX_LEVELS), ("p_blocks", C.c_int64 * AMG_MAX_LEVELS),
+                ("lambda_max", C.c_double * AMG_MAX_LEVELS), ("setup_seconds", C.c_double)]
 
 
 class NewtonResult(C.Structure):
@@ -111,10 +120,19 @@ def lib():
         "nosh_keoreg_matrix_apply": (C.c_int, [vp, vp, i64, vp, i64, C.c_int]),
         "nosh_keoreg_get_diags": (C.c_int, [vp, vp, vp]),
         "nosh_keoreg_apply": (C.c_int, [vp, vp, i64, vp, i64, C.c_int, C.c_int, dbl, dbl]),
+        "nosh_amg_set_options": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "nosh_amg_setup": (C.c_int, [vp]),
+        "nosh_amg_info": (C.c_int, [vp, C.POINTER(AmgInfo)]),
+        "nosh_amg_get_aggregates": (C.c_int, [vp, C.c_int, vp]),
+        "nosh_amg_get_matrix": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+        "nosh_amg_get_prolongator": (C.c_int, [vp, C.c_int, vp, vp, vp]),
         "nosh_dot": (C.c_int, [vp, vp, vp, C.POINTER(dbl)]),
         "nosh_norm2": (C.c_int, [vp, vp, C.POINTER(dbl)]),
         "nosh_minres": (C.c_int, [vp, C.c_int, vp, vp, dbl, C.c_int, C.POINTER(KrylovResult), vp]),
         "nosh_cg": (C.c_int, [vp, C.c_int, vp, vp, dbl, C.c_int, C.POINTER(KrylovResult), vp]),
+        "nosh_minres_prec": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, dbl, C.c_int, C.POINTER(KrylovResult), vp]),
+        "nosh_cg_prec": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, dbl, C.c_int, C.POINTER(KrylovResult), vp]),
+        "nosh_ctx_set_preconditioner": (C.c_int, [vp, C.c_int]),
         "nosh_newton": (C.c_int, [vp, C.c_int, cpp, vp, vp, dbl, C.c_int, dbl, C.c_int,
                                   C.POINTER(NewtonResult), vp, vp]),
         "nosh_inner_product": (C.c_int, [vp, vp, vp, C.POINTER(dbl)]),

@@ -15,8 +15,9 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (LAYOUT_CSR, LAYOUT_SELL32, MAT_DKEO, MAT_KEO, NO_TRANS, OP_JACOBIAN, OP_KEO,  # noqa: F401
-                   OP_KEOREG, ContinuationStep, KrylovResult, MeshInfo, NewtonResult)
+from ._lib import (AMG_REUSE_FULL, AMG_REUSE_NONE, LAYOUT_CSR, LAYOUT_SELL32, MAT_DKEO, MAT_KEO,  # noqa: F401
+                   NO_TRANS, OP_JACOBIAN, OP_KEO, OP_KEOREG, PREC_KEOREG_AMG, PREC_NONE, AmgInfo,
+                   ContinuationStep, KrylovResult, MeshInfo, NewtonResult)
 
 
 class NoshError(RuntimeError):
@@ -293,10 +294,52 @@ class Context:
         self._ck(self.L.nosh_keoreg_get_diags(self.h, _ptr(d0), _ptr(d1)))
         return d0, d1
 
-    def keoreg_apply(self, X, Y=None):
+    def keoreg_apply(self, X, Y=None, mode=NO_TRANS, alpha=1.0, beta=0.0):
+        """keo_regularized::apply: one AMG V-cycle on the regularised KEO."""
         Y = self._out_like(X) if Y is None else Y
-        self._ck(self.L.nosh_keoreg_apply(self.h, _ptr(X), 0, _ptr(Y), 0, 1, NO_TRANS, 1.0, 0.0))
+        nvec, ld = self._shape(X, 2 * self.n_owned)
+        self._ck(self.L.nosh_keoreg_apply(self.h, _ptr(X), ld, _ptr(Y), ld, nvec, mode, alpha, beta))
         return Y
+
+    # ---- AMG hierarchy ------------------------------------------------------------------
+    def amg_set_options(self, degree=0, coarse_max=0, max_levels=0, reuse=-1):
+        self._ck(self.L.nosh_amg_set_options(self.h, int(degree), int(coarse_max), int(max_levels),
+                                             int(reuse)))
+
+    def amg_setup(self):
+        self._ck(self.L.nosh_amg_setup(self.h))
+
+    def amg_info(self):
+        info = AmgInfo()
+        self._ck(self.L.nosh_amg_info(self.h, C.byref(info)))
+        return info
+
+    def amg_aggregates(self, level):
+        n = self.amg_info().nodes[level]
+        agg = np.empty(n, np.int32)
+        self._ck(self.L.nosh_amg_get_aggregates(self.h, int(level), _ptr(agg)))
+        return agg
+
+    def _amg_csr(self, fn, level, nrows, nnz):
+        rp = np.empty(nrows + 1, np.int64)
+        cols = np.empty(nnz, np.int32)
+        vals = np.empty((nnz, 2, 2))
+        self._ck(fn(self.h, int(level), _ptr(rp), _ptr(cols), _ptr(vals)))
+        return rp, cols, vals
+
+    def amg_matrix(self, level):
+        """block CSR (rowptr, cols, vals[nnz,2,2]) of the level matrix, level >= 1"""
+        info = self.amg_info()
+        return self._amg_csr(self.L.nosh_amg_get_matrix, level, info.nodes[level], info.blocks[level])
+
+    def amg_prolongator(self, level):
+        """block CSR of the prolongator from level+1 to level"""
+        info = self.amg_info()
+        return self._amg_csr(self.L.nosh_amg_get_prolongator, level, info.nodes[level],
+                             info.p_blocks[level])
+
+    def set_preconditioner(self, prec):
+        self._ck(self.L.nosh_ctx_set_preconditioner(self.h, int(prec)))
 
     # ---- reductions / solvers -----------------------------------------------------------
     def dot(self, x, y):
@@ -309,20 +352,25 @@ class Context:
         self._ck(self.L.nosh_norm2(self.h, _ptr(x), C.byref(r)))
         return r.value
 
-    def _krylov(self, fn, op, b, x, tol, maxit, history):
+    def _krylov(self, fn, fn_prec, op, prec, b, x, tol, maxit, history):
         x = self._out_like(b) if x is None else x
         res = KrylovResult()
         hist = np.full(maxit + 1, np.nan) if history else None
-        self._ck(fn(self.h, op, _ptr(b), _ptr(x), float(tol), int(maxit), C.byref(res), _ptr(hist)))
+        if prec == PREC_NONE:
+            self._ck(fn(self.h, op, _ptr(b), _ptr(x), float(tol), int(maxit), C.byref(res), _ptr(hist)))
+        else:
+            self._ck(fn_prec(self.h, op, int(prec), _ptr(b), _ptr(x), float(tol), int(maxit),
+                             C.byref(res), _ptr(hist)))
         if history:
             return x, res, hist[:res.iterations + 1]
         return x, res
 
-    def minres(self, b, x=None, op=OP_JACOBIAN, tol=1e-10, maxit=1000, history=False):
-        return self._krylov(self.L.nosh_minres, op, b, x, tol, maxit, history)
+    def minres(self, b, x=None, op=OP_JACOBIAN, tol=1e-10, maxit=1000, history=False, prec=PREC_NONE):
+        return self._krylov(self.L.nosh_minres, self.L.nosh_minres_prec, op, prec, b, x, tol, maxit,
+                            history)
 
-    def cg(self, b, x=None, op=OP_JACOBIAN, tol=1e-10, maxit=1000, history=False):
-        return self._krylov(self.L.nosh_cg, op, b, x, tol, maxit, history)
+    def cg(self, b, x=None, op=OP_JACOBIAN, tol=1e-10, maxit=1000, history=False, prec=PREC_NONE):
+        return self._krylov(self.L.nosh_cg, self.L.nosh_cg_prec, op, prec, b, x, tol, maxit, history)
 
     def newton(self, params, psi, nl_tol=1e-8, nl_maxit=20, lin_tol=1e-10, lin_maxit=1000):
         """psi is updated in place.  Returns (result, lin_iters, fnorms)."""

@@ -34,6 +34,22 @@ __device__ __forceinline__ void cfma(double2 &acc, double2 v, double2 x) {
   acc.y += v.x * x.y + v.y * x.x;
 }
 
+// AMG smoother tails on the finest level (amg.cu): yi = A x on entry
+template <int FUSE>
+__device__ __forceinline__ double2 smoother_tail(double2 yi, double2 xi, int64_t row, const ApplyArgs &A) {
+  const double2 bb = ld_stream2(A.bvec + row);
+  if (FUSE == FUSE_RESID) return make_double2(bb.x - yi.x, bb.y - yi.y);
+  const double2 di = ld_stream2(A.dinv + row);
+  double2 dd = make_double2(A.c2 * (di.x * (bb.x - yi.x)), A.c2 * (di.y * (bb.y - yi.y)));
+  if (A.c1 != 0.0) {
+    const double2 dold = A.dvec[row];
+    dd.x += A.c1 * dold.x;
+    dd.y += A.c1 * dold.y;
+  }
+  if (A.dvec) A.dvec[row] = dd;
+  return make_double2(xi.x + dd.x, xi.y + dd.y);
+}
+
 template <int FUSE>
 __device__ __forceinline__ bool krylov_skip(const ApplyArgs &A) {
   if (FUSE == FUSE_MINRES || FUSE == FUSE_CG) {
@@ -49,6 +65,7 @@ __device__ __forceinline__ bool krylov_skip(const ApplyArgs &A) {
 template <int EPI, int FUSE, int U>
 __global__ void __launch_bounds__(CHUNK, 2) k_apply_sell(const ApplyArgs A) {
   if (krylov_skip<FUSE>(A)) return;
+  if (A.gate && A.gate->done) return;
   __shared__ double red[32];
   const int chunk = A.chunk_list ? __ldg(A.chunk_list + blockIdx.x) : (int)blockIdx.x;
   const int64_t row = (int64_t)chunk * CHUNK + threadIdx.x;
@@ -115,6 +132,8 @@ __global__ void __launch_bounds__(CHUNK, 2) k_apply_sell(const ApplyArgs A) {
       contrib = xi.x * yi.x + xi.y * yi.y;
     } else if (FUSE == FUSE_CG) {
       contrib = xi.x * yi.x + xi.y * yi.y;
+    } else if (FUSE == FUSE_RESID || FUSE == FUSE_CHEB) {
+      yi = smoother_tail<FUSE>(yi, xi, row, A);
     }
     A.y[row] = yi;
   }
@@ -131,6 +150,7 @@ __global__ void __launch_bounds__(CHUNK, 2) k_apply_sell(const ApplyArgs A) {
 template <int EPI, int FUSE, int LPR>
 __global__ void __launch_bounds__(CHUNK, 2) k_apply_csr(const ApplyArgs A) {
   if (krylov_skip<FUSE>(A)) return;
+  if (A.gate && A.gate->done) return;
   __shared__ double red[32];
   constexpr int RPP = CHUNK / LPR;  // rows per pass
   const int chunk = A.chunk_list ? __ldg(A.chunk_list + blockIdx.x) : (int)blockIdx.x;
@@ -184,6 +204,8 @@ __global__ void __launch_bounds__(CHUNK, 2) k_apply_csr(const ApplyArgs A) {
         contrib += xi.x * yi.x + xi.y * yi.y;
       } else if (FUSE == FUSE_CG) {
         contrib += xi.x * yi.x + xi.y * yi.y;
+      } else if (FUSE == FUSE_RESID || FUSE == FUSE_CHEB) {
+        yi = smoother_tail<FUSE>(yi, xi, row, A);
       }
       A.y[row] = yi;
     }
@@ -223,7 +245,11 @@ void launch1(Ctx *ctx, int fuse, const ApplyArgs &A) {
 void launch_apply(Ctx *ctx, int epi, int fuse, const ApplyArgs &A) {
   switch (epi) {
     case EPI_NONE: launch1<EPI_NONE>(ctx, fuse, A); break;
-    case EPI_DIAG: launch1<EPI_DIAG>(ctx, fuse, A); break;
+    case EPI_DIAG:
+      if (fuse == FUSE_RESID) launch2<EPI_DIAG, FUSE_RESID>(ctx, A);
+      else if (fuse == FUSE_CHEB) launch2<EPI_DIAG, FUSE_CHEB>(ctx, A);
+      else launch1<EPI_DIAG>(ctx, fuse, A);
+      break;
     case EPI_F: launch2<EPI_F, FUSE_NONE>(ctx, A); break;
     case EPI_DG: launch2<EPI_DG, FUSE_NONE>(ctx, A); break;
     case EPI_DV: launch2<EPI_DV, FUSE_NONE>(ctx, A); break;

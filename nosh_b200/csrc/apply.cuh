@@ -13,6 +13,9 @@
 //   FUSE_MINRES : input scaled by 1/beta (v = r/beta never materialised), y -= (beta/oldBeta) r1,
 //                 chunk partials of <v, y>
 //   FUSE_CG     : chunk partials of <p, A p>
+// and the smoother steps of the AMG V-cycle (amg.cu) on the finest level:
+//   FUSE_RESID  : y = b - A x
+//   FUSE_CHEB   : t = D^-1 (b - A x);  d = c1 d + c2 t;  y = x + d     (one Chebyshev/Jacobi step)
 //
 // Two storage layouts behind the same slots (chosen by measurement):
 //   SELL-32 : one thread per row, 32-row slices stored column-major -> every matrix load is a
@@ -25,7 +28,7 @@
 namespace nosh {
 
 enum { EPI_NONE = 0, EPI_DIAG = 1, EPI_F = 2, EPI_DG = 3, EPI_DV = 4 };
-enum { FUSE_NONE = 0, FUSE_AXPBY = 1, FUSE_MINRES = 2, FUSE_CG = 3 };
+enum { FUSE_NONE = 0, FUSE_AXPBY = 1, FUSE_MINRES = 2, FUSE_CG = 3, FUSE_RESID = 4, FUSE_CHEB = 5 };
 
 struct ApplyArgs {
   int64_t No;
@@ -53,6 +56,14 @@ struct ApplyArgs {
   int n_list;
   // FUSE_MINRES / FUSE_CG on one GPU: the last CTA finishes the reduction (fin.counter != NULL)
   FinArgs fin;
+  // FUSE_RESID / FUSE_CHEB
+  const double2 *bvec;
+  double2 *dvec;        // Chebyshev direction (read if c1 != 0, written if non-NULL)
+  const double2 *dinv;  // 1 / point diagonal
+  double c1, c2;
+  // optional: every variant returns immediately once gate->done is set (V-cycles launched after
+  // the Krylov solver has converged)
+  const KrylovState *gate;
 };
 
 void launch_apply(Ctx *ctx, int epi, int fuse, const ApplyArgs &A);

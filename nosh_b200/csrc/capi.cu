@@ -2,6 +2,7 @@
 // Thin: argument checks, host<->device staging, status codes.  Never throws.
 #include <cstdlib>
 
+#include "amg.h"
 #include "apply.cuh"
 #include "comm.h"
 #include "keo.h"
@@ -94,6 +95,7 @@ __global__ void k_widen(const int32_t *in, int64_t n, int64_t *out) {
 }
 
 void after_mesh(Ctx *ctx) {
+  amg_free(ctx);
   halo_setup(ctx);
   ensure_work(ctx);
   p2p_setup(ctx);
@@ -151,6 +153,7 @@ void nosh_ctx_destroy(nosh_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   comm_destroy(ctx);
+  amg_free(ctx);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   cudaStream_t s = ctx->own_stream ? ctx->stream : nullptr;
@@ -535,12 +538,118 @@ nosh_status nosh_keoreg_get_diags(nosh_ctx *ctx, double *d0, double *d1b) {
   API_END(ctx)
 }
 
-nosh_status nosh_keoreg_apply(nosh_ctx *ctx, const double *, int64_t, double *, int64_t, int, nosh_transp,
-                              double, double) {
+nosh_status nosh_keoreg_apply(nosh_ctx *ctx, const double *X, int64_t ldx, double *Y, int64_t ldy, int nvec,
+                              nosh_transp mode, double alpha, double beta) {
   API_BEGIN(ctx)
-  NOSH_THROW(NOSH_EUNSUPPORTED,
-             "keo_regularized::apply is one MueLu AMG V-cycle (src/keo_regularized.cpp:106-108): third-party, "
-             "out of scope; use nosh_keoreg_matrix_apply for the matrix itself");
+  require_mesh(ctx);
+  // src/keo_regularized.cpp:98-100 (TEUCHOS_ASSERT_EQUALITY on mode, alpha, beta)
+  if (mode != NOSH_NO_TRANS) NOSH_THROW(NOSH_EINVAL, "Only untransposed applies supported.");
+  if (alpha != 1.0) NOSH_THROW(NOSH_EINVAL, "Only alpha==1.0 supported.");
+  if (beta != 0.0) NOSH_THROW(NOSH_EINVAL, "Only beta==0.0 supported.");
+  check_apply_shape(ctx, ldx, ldy, nvec);
+  ensure_work(ctx);
+  amg_ensure(ctx);
+  for (int v = 0; v < nvec; v++) {
+    double2 *x = stage_in(ctx, X + (size_t)v * ldx, ctx->stage_x, false);
+    OutVec o = stage_out(ctx, Y + (size_t)v * ldy, ctx->stage_y);
+    double2 *out = o.dev;
+    if (!o.host && ctx->nranks > 1) out = ctx->work[11].p;  // the V-cycle needs ghost room
+    amg_vcycle(ctx, x, out, nullptr);
+    if (out != o.dev && ctx->No)
+      CUDA_CHECK(cudaMemcpyAsync(o.dev, out, sizeof(double2) * ctx->No, cudaMemcpyDeviceToDevice, ctx->stream));
+    finish_out(ctx, o);
+  }
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+nosh_status nosh_amg_set_options(nosh_ctx *ctx, int degree, int coarse_max, int max_levels, int reuse) {
+  API_BEGIN(ctx)
+  if (coarse_max > 4096) NOSH_THROW(NOSH_EINVAL, "coarse_max > 4096");
+  if (max_levels > NOSH_AMG_MAX_LEVELS) NOSH_THROW(NOSH_EINVAL, "max_levels > %d", NOSH_AMG_MAX_LEVELS);
+  if (reuse > 1) NOSH_THROW(NOSH_EINVAL, "unknown reuse policy %d", reuse);
+  if (degree > 0) ctx->amg_degree = degree;
+  if (coarse_max > 0) ctx->amg_coarse_max = coarse_max;
+  if (max_levels > 0) ctx->amg_max_levels = max_levels;
+  if (reuse >= 0) ctx->amg_reuse = reuse;
+  amg_free(ctx);
+  API_END(ctx)
+}
+
+nosh_status nosh_amg_setup(nosh_ctx *ctx) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  ensure_work(ctx);
+  ctx->amg_valid = false;
+  amg_ensure(ctx);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+nosh_status nosh_amg_info(nosh_ctx *ctx, nosh_amg_info_t *info) {
+  API_BEGIN(ctx)
+  if (!info) NOSH_THROW(NOSH_EINVAL, "NULL info");
+  if (!ctx->amg) NOSH_THROW(NOSH_ESTATE, "no AMG hierarchy built");
+  memset(info, 0, sizeof(*info));
+  info->levels = (int32_t)ctx->amg->levels.size();
+  info->degree = ctx->amg_degree;
+  info->setup_seconds = ctx->amg->setup_seconds;
+  for (int l = 0; l < info->levels && l < NOSH_AMG_MAX_LEVELS; l++) {
+    const AmgLevel &L = *ctx->amg->levels[l];
+    info->nodes[l] = L.n;
+    info->blocks[l] = L.nb;
+    info->p_blocks[l] = L.p_nnz;
+    info->lambda_max[l] = L.lam;
+  }
+  API_END(ctx)
+}
+
+static AmgLevel &amg_level(Ctx *ctx, int level) {
+  if (!ctx->amg) NOSH_THROW(NOSH_ESTATE, "no AMG hierarchy built");
+  if (level < 0 || level >= (int)ctx->amg->levels.size()) NOSH_THROW(NOSH_EINVAL, "no AMG level %d", level);
+  return *ctx->amg->levels[level];
+}
+static void export_csr(Ctx *ctx, int64_t nrows, int64_t nnz, const int32_t *rowptr_dev, const int32_t *col_dev,
+                       const B22 *val_dev, int64_t *rowptr, int32_t *cols, double *vals) {
+  if (rowptr) {
+    DBuf<int64_t> w;
+    w.alloc(nrows + 1);
+    k_widen<<<(unsigned)cdiv(nrows + 1, 256), 256, 0, ctx->stream>>>(rowptr_dev, nrows + 1, w.p);
+    ctx->launches++;
+    d2h(ctx, rowptr, w.p, nrows + 1);
+  }
+  d2h(ctx, cols, col_dev, nnz);
+  d2h(ctx, (B22 *)vals, val_dev, nnz);
+}
+
+nosh_status nosh_amg_get_aggregates(nosh_ctx *ctx, int level, int32_t *agg) {
+  API_BEGIN(ctx)
+  AmgLevel &L = amg_level(ctx, level);
+  if (!L.agg.p) NOSH_THROW(NOSH_EINVAL, "level %d is the coarsest level", level);
+  d2h(ctx, agg, L.agg.p, L.n);
+  API_END(ctx)
+}
+
+nosh_status nosh_amg_get_matrix(nosh_ctx *ctx, int level, int64_t *rowptr, int32_t *cols, double *vals) {
+  API_BEGIN(ctx)
+  AmgLevel &L = amg_level(ctx, level);
+  if (level == 0) NOSH_THROW(NOSH_EINVAL, "level 0 is the regularised KEO itself (nosh_get_block_csr + nosh_keoreg_get_diags)");
+  export_csr(ctx, L.n, L.nb, L.rowptr.p, L.col.p, L.val.p, rowptr, cols, vals);
+  API_END(ctx)
+}
+
+nosh_status nosh_amg_get_prolongator(nosh_ctx *ctx, int level, int64_t *rowptr, int32_t *cols, double *vals) {
+  API_BEGIN(ctx)
+  AmgLevel &L = amg_level(ctx, level);
+  if (!L.p_rowptr.p) NOSH_THROW(NOSH_EINVAL, "level %d is the coarsest level", level);
+  export_csr(ctx, L.n, L.p_nnz, L.p_rowptr.p, L.p_col.p, L.p_val.p, rowptr, cols, vals);
+  API_END(ctx)
+}
+
+nosh_status nosh_ctx_set_preconditioner(nosh_ctx *ctx, nosh_precond prec) {
+  API_BEGIN(ctx)
+  if (prec != NOSH_PREC_NONE && prec != NOSH_PREC_KEOREG_AMG) NOSH_THROW(NOSH_EINVAL, "unknown preconditioner %d", (int)prec);
+  ctx->precond = prec;
   API_END(ctx)
 }
 
@@ -563,29 +672,39 @@ nosh_status nosh_norm2(nosh_ctx *ctx, const double *x, double *result) {
   API_END(ctx)
 }
 
-static nosh_status krylov_entry(nosh_ctx *ctx, bool is_minres, nosh_operator_id op, const double *b, double *x,
-                                double tol, int maxit, nosh_krylov_result *res, double *hist) {
+static nosh_status krylov_entry(nosh_ctx *ctx, bool is_minres, nosh_operator_id op, int prec, const double *b,
+                                double *x, double tol, int maxit, nosh_krylov_result *res, double *hist) {
   API_BEGIN(ctx)
   require_mesh(ctx);
   ensure_work(ctx);
   const double2 *bd = stage_in(ctx, b, ctx->stage_x, false);
   OutVec o = stage_out(ctx, x, ctx->stage_y);
   if (is_minres)
-    minres_dev(ctx, op, bd, 1.0, o.dev, tol, maxit, res, hist);
+    minres_dev(ctx, op, prec, bd, 1.0, o.dev, tol, maxit, res, hist);
   else
-    cg_dev(ctx, op, bd, 1.0, o.dev, tol, maxit, res, hist);
+    cg_dev(ctx, op, prec, bd, 1.0, o.dev, tol, maxit, res, hist);
   finish_out(ctx, o);
   API_END(ctx)
 }
 
 nosh_status nosh_minres(nosh_ctx *ctx, nosh_operator_id op, const double *b, double *x, double tol, int maxit,
                         nosh_krylov_result *res, double *hist) {
-  return krylov_entry(ctx, true, op, b, x, tol, maxit, res, hist);
+  return krylov_entry(ctx, true, op, NOSH_PREC_NONE, b, x, tol, maxit, res, hist);
 }
 
 nosh_status nosh_cg(nosh_ctx *ctx, nosh_operator_id op, const double *b, double *x, double tol, int maxit,
                     nosh_krylov_result *res, double *hist) {
-  return krylov_entry(ctx, false, op, b, x, tol, maxit, res, hist);
+  return krylov_entry(ctx, false, op, NOSH_PREC_NONE, b, x, tol, maxit, res, hist);
+}
+
+nosh_status nosh_minres_prec(nosh_ctx *ctx, nosh_operator_id op, nosh_precond prec, const double *b, double *x,
+                             double tol, int maxit, nosh_krylov_result *res, double *hist) {
+  return krylov_entry(ctx, true, op, (int)prec, b, x, tol, maxit, res, hist);
+}
+
+nosh_status nosh_cg_prec(nosh_ctx *ctx, nosh_operator_id op, nosh_precond prec, const double *b, double *x,
+                         double tol, int maxit, nosh_krylov_result *res, double *hist) {
+  return krylov_entry(ctx, false, op, (int)prec, b, x, tol, maxit, res, hist);
 }
 
 nosh_status nosh_newton(nosh_ctx *ctx, int np, const char *const *names, const double *values, double *psi,

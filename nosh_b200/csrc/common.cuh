@@ -97,6 +97,7 @@ struct KrylovState {
 };
 
 struct NcclApi;  // comm.cu
+struct Amg;      // amg.h
 
 constexpr int MAX_RANKS = 8;
 
@@ -194,8 +195,18 @@ struct Ctx {
   DBuf<double2> pd0;
   DBuf<double> pd1;
   bool keoreg_ok = false;
+  // ---- preconditioner: AMG V-cycle on the regularised KEO (amg.cu) ----
+  Amg *amg = nullptr;
+  bool amg_valid = false;     // hierarchy matches the reuse policy
+  int amg_degree = 1;         // Chebyshev degree of the pre-/post-smoother
+  int amg_coarse_max = 512;   // nodes at which the hierarchy stops and a dense inverse is used
+  int amg_max_levels = 10;
+  int amg_reuse = 1;          // nosh_amg_reuse: 0 none, 1 full ("reuse: type" = "full", keo_regularized.cpp:300)
+  bool amg_keep_l0 = false;   // keep the level-0 block CSR copy (parity accessors)
+  int64_t keoreg_version = 0, amg_dinv_version = -1;
+  int precond = 0;            // nosh_precond the Newton / continuation drivers use for their linear solves
   // ---- work vectors (2*Nl doubles each) ----
-  DBuf<double2> work[12];
+  DBuf<double2> work[14];
   DBuf<double2> scratch[8];
   DBuf<double2> stage_x, stage_y;   // host staging
   // ---- reductions ----

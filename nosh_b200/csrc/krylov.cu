@@ -19,6 +19,7 @@
 
 #include <cstdlib>
 
+#include "amg.h"
 #include "apply.cuh"
 #include "comm.h"
 #include "reduce.cuh"
@@ -430,6 +431,8 @@ void keoreg_diags_dev(Ctx *ctx, double g, const double2 *psi) {
     KLAUNCH(ctx, k_keoreg_diags, (unsigned)cdiv(ctx->No, 256), 256, g, ctx->cv.p, ctx->thick.p, psi, ctx->No,
             ctx->pd0.p, ctx->pd1.p);
   ctx->keoreg_ok = true;
+  ctx->keoreg_version++;
+  if (ctx->amg_reuse == 0) ctx->amg_valid = false;  // "reuse: type" = "none": new hierarchy per rebuild
 }
 
 void axpy_dev(Ctx *ctx, double a, const double2 *x, double2 *y) {
@@ -458,23 +461,40 @@ void compute_f_dev(Ctx *ctx, double g, double2 *psi, double2 *f) {
   launch_apply(ctx, EPI_F, FUSE_NONE, A);
 }
 
-void minres_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_out, double tol, int maxit,
+// z = M r with the selected preconditioner (M = I is handled by the callers: z aliases r)
+void precond_apply(Ctx *ctx, int prec, const double2 *r, double2 *z) {
+  if (prec == NOSH_PREC_KEOREG_AMG) amg_vcycle(ctx, r, z, ctx->kstate.p);
+}
+
+void minres_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, double2 *x_out, double tol, int maxit,
                 nosh_krylov_result *res, double *hist_host) {
   ensure_work(ctx);
   if (maxit < 0) NOSH_THROW(NOSH_EINVAL, "maxit < 0");
+  if (prec != NOSH_PREC_NONE && prec != NOSH_PREC_KEOREG_AMG) NOSH_THROW(NOSH_EINVAL, "unknown preconditioner %d", prec);
+  const bool pc = prec != NOSH_PREC_NONE;
+  if (pc) amg_ensure(ctx);
   ApplyArgs A = base_args(ctx, nullptr, nullptr, nullptr);
   int epi;
   op_args(ctx, op, A, &epi);
   ctx->hist.ensure((size_t)maxit + 2);
-  double2 *R[2] = {ctx->work[0].p, ctx->work[1].p};
+  // Z: what the operator is applied to (z_k = M r_k; the peer-memory halo push exports these two
+  // buffers).  Without a preconditioner z_k is r_k itself.
+  double2 *Z[2] = {ctx->work[0].p, ctx->work[1].p};
+  double2 *R[2] = {pc ? ctx->work[12].p : Z[0], pc ? ctx->work[13].p : Z[1]};
   double2 *Pv = ctx->work[2].p;
   double2 *W[3] = {ctx->work[3].p, ctx->work[4].p, ctx->work[5].p};
   double2 *X = x_out;
   const unsigned grid = (unsigned)ctx->n_chunks;
   const int64_t No = ctx->No;
-  FinArgs F = fin_args(ctx, FIN_MINRES_INIT, 0, tol, maxit, nullptr);
-  if (grid) KLAUNCH(ctx, k_minres_init, grid, TPB, b, bscale, No, R[0], W[0], W[1], W[2], X, ctx->partials.p, F);
-  if (ctx->nranks > 1 && ctx->p2p.ok) p2p_halo_push(ctx, 0, R[0]);  // r_1 ghosts; ordered by the reduction below
+  FinArgs F = fin_args(ctx, FIN_MINRES_INIT, 0, tol, maxit, nullptr, !pc);
+  FinArgs Fnone = fin_args(ctx, FIN_DOT, 0, tol, maxit, nullptr, false);
+  if (grid) KLAUNCH(ctx, k_minres_init, grid, TPB, b, bscale, No, R[0], W[0], W[1], W[2], X, ctx->partials.p, pc ? Fnone : F);
+  if (pc) {
+    // beta_1^2 = <r_1, M r_1>
+    amg_vcycle(ctx, R[0], Z[0], nullptr);
+    if (grid) KLAUNCH(ctx, k_dot, grid, TPB, R[0], Z[0], No, ctx->partials.p, Fnone);
+  }
+  if (ctx->nranks > 1 && ctx->p2p.ok) p2p_halo_push(ctx, 0, Z[0]);  // z_1 ghosts; ordered by the reduction below
   finalize_launch(ctx, F);
   KrylovState hs;
   int check = 4;
@@ -482,13 +502,14 @@ void minres_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_ou
   // while the interior chunks of A(h) run; C(h-1) also runs on stream2, next to A(h) and the
   // alpha all-reduce, and must only be finished before B(h) overwrites the buffer it reads.
   const bool p2p = ctx->nranks > 1 && ctx->p2p.ok;
-  const bool overlap = ctx->nranks > 1 && !p2p;
+  const bool overlap = ctx->nranks > 1 && !p2p && !pc;
   cudaStream_t S0 = ctx->stream, S1 = ctx->stream2;
   if (overlap) CUDA_CHECK(cudaEventRecord(ctx->e_b, S0));  // r_1 is ready
   int h_last = 0;
   for (int h = 1; h <= maxit; h++) {
     double2 *rcur = R[(h - 1) & 1], *rprev = R[h & 1];
-    A.x = rcur;
+    double2 *zcur = Z[(h - 1) & 1], *zprev = Z[h & 1];
+    A.x = zcur;
     A.y = Pv;
     A.r1 = rprev;
     A.host_iter = h;
@@ -528,19 +549,26 @@ void minres_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_ou
       // A: y = J v - (beta/oldBeta) r_prev, partials <v,y>
       // (one GPU: the last CTA of A / B finishes the reduction and the scalar recurrences itself)
       FinArgs Fa = fin_args(ctx, FIN_MINRES_ALPHA, h, tol, maxit, nullptr);
-      FinArgs Fb = fin_args(ctx, FIN_MINRES_BETA, h, tol, maxit, nullptr);
+      FinArgs Fb = fin_args(ctx, FIN_MINRES_BETA, h, tol, maxit, nullptr, !pc);
+      if (ctx->nranks > 1 && !p2p) halo_exchange(ctx, zcur);  // NCCL fallback of the preconditioned loop
       A.fin = Fa;
       launch_apply(ctx, epi, FUSE_MINRES, A);
       finalize_launch(ctx, Fa);
       // B: r_next = y - (alpha/beta) r_cur  (written over r_prev)
-      if (grid) KLAUNCH(ctx, k_minres_B, grid, TPB, ctx->kstate.p, h, Pv, rcur, rprev, No, ctx->partials.p, Fb);
-      // multi-GPU, peer-memory path: push the boundary entries of r_next into the neighbours'
+      if (grid)
+        KLAUNCH(ctx, k_minres_B, grid, TPB, ctx->kstate.p, h, Pv, rcur, rprev, No, ctx->partials.p, pc ? Fnone : Fb);
+      if (pc) {
+        // z_next = M r_next, beta_next^2 = <r_next, z_next>
+        precond_apply(ctx, prec, rprev, zprev);
+        if (grid) KLAUNCH(ctx, k_dot, grid, TPB, rprev, zprev, No, ctx->partials.p, Fnone);
+      }
+      // multi-GPU, peer-memory path: push the boundary entries of z_next into the neighbours'
       // ghost segments; the beta reduction that follows is also the barrier that orders them
-      if (p2p) p2p_halo_push(ctx, h & 1, rprev);
+      if (p2p) p2p_halo_push(ctx, h & 1, zprev);
       finalize_launch(ctx, Fb);
       // C: w_h, x
       if (grid)
-        KLAUNCH(ctx, k_minres_C, grid, TPB, ctx->kstate.p, h, rcur, W[(h + 1) % 3], W[(h + 2) % 3], W[h % 3], X, No);
+        KLAUNCH(ctx, k_minres_C, grid, TPB, ctx->kstate.p, h, zcur, W[(h + 1) % 3], W[(h + 2) % 3], W[h % 3], X, No);
     }
     h_last = h;
     if (h % check == 0 || h == maxit) {
@@ -570,20 +598,32 @@ void minres_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_ou
   }
 }
 
-void cg_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_out, double tol, int maxit,
+void cg_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, double2 *x_out, double tol, int maxit,
             nosh_krylov_result *res, double *hist_host) {
   ensure_work(ctx);
   if (maxit < 0) NOSH_THROW(NOSH_EINVAL, "maxit < 0");
+  if (prec != NOSH_PREC_NONE && prec != NOSH_PREC_KEOREG_AMG) NOSH_THROW(NOSH_EINVAL, "unknown preconditioner %d", prec);
+  const bool pc = prec != NOSH_PREC_NONE;
+  if (pc) amg_ensure(ctx);
   ApplyArgs A = base_args(ctx, nullptr, nullptr, nullptr);
   int epi;
   op_args(ctx, op, A, &epi);
   ctx->hist.ensure((size_t)maxit + 2);
-  double2 *Rv = ctx->work[0].p, *Pd = ctx->work[1].p, *AP = ctx->work[2].p, *X = x_out;
+  double2 *Rv = ctx->work[0].p, *Pd = ctx->work[1].p, *AP = ctx->work[2].p, *Zv = ctx->work[12].p, *X = x_out;
   const unsigned grid = (unsigned)ctx->n_chunks;
   const int64_t No = ctx->No;
   FinArgs F = fin_args(ctx, FIN_CG_INIT, 0, tol, maxit, nullptr);
+  FinArgs Fnone = fin_args(ctx, FIN_DOT, 0, tol, maxit, nullptr, false);
   if (grid) KLAUNCH(ctx, k_cg_init, grid, TPB, b, bscale, No, Rv, Pd, X, ctx->partials.p, F);
   finalize_launch(ctx, F);
+  if (pc) {
+    // p_0 = z_0 = M r_0, rho_0 = <r_0, z_0>
+    amg_vcycle(ctx, Rv, Zv, nullptr);
+    FinArgs Fr = fin_args(ctx, FIN_PCG_INIT_RHO, 0, tol, maxit, nullptr, false);
+    if (grid) KLAUNCH(ctx, k_dot, grid, TPB, Rv, Zv, No, ctx->partials.p, Fnone);
+    finalize_launch(ctx, Fr);
+    if (No) CUDA_CHECK(cudaMemcpyAsync(Pd, Zv, sizeof(double2) * No, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
   KrylovState hs;
   int check = 4;
   for (int h = 1; h <= maxit; h++) {
@@ -592,13 +632,20 @@ void cg_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_out, d
     A.y = AP;
     A.host_iter = h;
     FinArgs Fa = fin_args(ctx, FIN_CG_PAP, h, tol, maxit, nullptr);
-    FinArgs Fb = fin_args(ctx, FIN_CG_RHO, h, tol, maxit, nullptr);
+    FinArgs Fb = fin_args(ctx, pc ? FIN_PCG_RR : FIN_CG_RHO, h, tol, maxit, nullptr);
     A.fin = Fa;
     launch_apply(ctx, epi, FUSE_CG, A);
     finalize_launch(ctx, Fa);
     if (grid) KLAUNCH(ctx, k_cg_update, grid, TPB, ctx->kstate.p, h, Pd, AP, Rv, X, No, ctx->partials.p, Fb);
     finalize_launch(ctx, Fb);
-    if (grid) KLAUNCH(ctx, k_cg_direction, grid, TPB, ctx->kstate.p, h, Rv, Pd, No);
+    if (pc) {
+      // z = M r, beta = <r, z> / rho  (the finalize is gated on iter == h, i.e. host_iter h + 1)
+      precond_apply(ctx, prec, Rv, Zv);
+      FinArgs Fr = fin_args(ctx, FIN_PCG_RHO, h + 1, tol, maxit, nullptr, false);
+      if (grid) KLAUNCH(ctx, k_dot, grid, TPB, Rv, Zv, No, ctx->partials.p, Fnone);
+      finalize_launch(ctx, Fr);
+    }
+    if (grid) KLAUNCH(ctx, k_cg_direction, grid, TPB, ctx->kstate.p, h, pc ? Zv : Rv, Pd, No);
     if (h % check == 0 || h == maxit) {
       if (poll_done(ctx, &hs)) break;
       if (check < 32) check *= 2;
@@ -652,8 +699,10 @@ void newton_dev(Ctx *ctx, int np, const char *const *names, const double *values
   while (k < nl_maxit && !(fn < nl_tol)) {
     // evalModel(W_op): jacobian_operator::rebuild (KEO refill is a cache hit) + diagonals
     jac_diags_dev(ctx, g, psi);
+    // evalModel(W_prec): keo_regularized::rebuild at the current state (src/model_evaluator_nls.cpp:507-522)
+    if (ctx->precond != NOSH_PREC_NONE) keoreg_diags_dev(ctx, g, psi);
     nosh_krylov_result kr;
-    minres_dev(ctx, NOSH_OP_JACOBIAN, F, -1.0, D, lin_tol, lin_maxit, &kr, nullptr);
+    minres_dev(ctx, NOSH_OP_JACOBIAN, ctx->precond, F, -1.0, D, lin_tol, lin_maxit, &kr, nullptr);
     if (lin_iters) lin_iters[k] = kr.iterations;
     total += kr.iterations;
     axpy_dev(ctx, 1.0, D, psi);
@@ -695,9 +744,10 @@ void continuation_dev(Ctx *ctx, int np, const char *const *names, const double *
       keo_fill(ctx, np, names, vals.data(), false);
       update_potential(ctx, np, names, vals.data());
       jac_diags_dev(ctx, g, psi);
+      if (ctx->precond != NOSH_PREC_NONE) keoreg_diags_dev(ctx, g, psi);
       compute_dfdp_dev(ctx, np, names, vals.data(), pname, psi, dF);
       nosh_krylov_result kr;
-      minres_dev(ctx, NOSH_OP_JACOBIAN, dF, -1.0, T, lin_tol, lin_maxit, &kr, nullptr);
+      minres_dev(ctx, NOSH_OP_JACOBIAN, ctx->precond, dF, -1.0, T, lin_tol, lin_maxit, &kr, nullptr);
       st.predictor_linear_iterations = kr.iterations;
       axpy_dev(ctx, dp, T, psi);
     }

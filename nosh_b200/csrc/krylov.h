@@ -9,9 +9,9 @@ void keoreg_diags_dev(Ctx *ctx, double g, const double2 *psi);
 void axpy_dev(Ctx *ctx, double a, const double2 *x, double2 *y);
 void apply_op_dev(Ctx *ctx, int op, double2 *x, double2 *y);
 void compute_f_dev(Ctx *ctx, double g, double2 *psi, double2 *f);
-void minres_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_out, double tol, int maxit,
+void minres_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, double2 *x_out, double tol, int maxit,
                 nosh_krylov_result *res, double *hist_host);
-void cg_dev(Ctx *ctx, int op, const double2 *b, double bscale, double2 *x_out, double tol, int maxit,
+void cg_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, double2 *x_out, double tol, int maxit,
             nosh_krylov_result *res, double *hist_host);
 void newton_dev(Ctx *ctx, int np, const char *const *names, const double *values, double2 *psi, double nl_tol,
                 int nl_maxit, double lin_tol, int lin_maxit, nosh_newton_result *res, int32_t *lin_iters,

@@ -7,7 +7,8 @@
 
 namespace nosh {
 
-enum { FIN_DOT = 0, FIN_MINRES_INIT, FIN_MINRES_ALPHA, FIN_MINRES_BETA, FIN_CG_INIT, FIN_CG_PAP, FIN_CG_RHO };
+enum { FIN_DOT = 0, FIN_MINRES_INIT, FIN_MINRES_ALPHA, FIN_MINRES_BETA, FIN_CG_INIT, FIN_CG_PAP, FIN_CG_RHO,
+       FIN_PCG_INIT_RHO, FIN_PCG_RR, FIN_PCG_RHO };
 
 struct FinArgs {
   const double *partials;
@@ -155,6 +156,25 @@ static __device__ __forceinline__ void fin_scalars(const FinArgs &F, double tota
       st->pAp = total;
       st->cg_alpha = st->rho / total;
       break;
+    case FIN_PCG_INIT_RHO:  // preconditioned CG: rho_0 = <r_0, M r_0> (r0norm comes from FIN_CG_INIT)
+      st->rho = total;
+      break;
+    case FIN_PCG_RR: {  // ||r_k|| -> convergence test; rho / beta follow in FIN_PCG_RHO
+      st->iter += 1;
+      st->relres = sqrt(total) / st->r0norm;
+      if (F.hist) F.hist[st->iter] = st->relres;
+      if (st->relres <= st->tol) {
+        st->done = 1;
+        st->converged = 1;
+      } else if (st->iter >= st->maxit) {
+        st->done = 1;
+      }
+      break;
+    }
+    case FIN_PCG_RHO:
+      st->cg_beta = total / st->rho;
+      st->rho = total;
+      break;
     case FIN_CG_RHO: {
       st->cg_beta = total / st->rho;
       st->rho = total;
@@ -174,7 +194,8 @@ static __device__ __forceinline__ void fin_scalars(const FinArgs &F, double tota
 
 
 static __device__ __forceinline__ bool fin_is_iterative(int what) {
-  return what == FIN_MINRES_ALPHA || what == FIN_MINRES_BETA || what == FIN_CG_PAP || what == FIN_CG_RHO;
+  return what == FIN_MINRES_ALPHA || what == FIN_MINRES_BETA || what == FIN_CG_PAP || what == FIN_CG_RHO ||
+         what == FIN_PCG_RR || what == FIN_PCG_RHO;
 }
 
 // Called by ALL threads of one CTA (any multiple of 32 threads up to 1024).  sm: 32 doubles of

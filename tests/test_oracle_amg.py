@@ -1,0 +1,72 @@
+"""CPU checks of the preconditioner oracle (oracle/amg.py): the restated smoothed-aggregation V-cycle is a
+symmetric positive definite operator, accelerates MINRES, and its two formulations of the aggregation (the
+sequential greedy sweep and the synchronous rounds the GPU runs) agree.  MueLu itself is not in the reference
+tree -- parity for this row is unpinned (see the header of oracle/amg.py)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle
+from oracle import amg, meshgen
+
+
+def regularised_problem(n, mu=0.1, g=1.0, state="ones"):
+    coords, cells = meshgen.tetgrid(n)
+    psi, A = meshgen.plain_gl_fields(coords)
+    P = oracle.OracleProblem(coords, cells, ("explicit", A))
+    x = psi if state == "ones" else meshgen.random_state(P.N)
+    P.keo_fill(mu)
+    P.jac_rebuild(g, x)
+    N = P.N
+    K = sp.csr_matrix((P.vals.copy(), P.cols, P.rowptr), shape=(2 * N, 2 * N))
+    r = np.arange(N)
+    D = sp.csr_matrix((np.concatenate([P.d0[0::2], P.d0[1::2], P.d1b, P.d1b]),
+                       (np.concatenate([2 * r, 2 * r + 1, 2 * r, 2 * r + 1]),
+                        np.concatenate([2 * r, 2 * r + 1, 2 * r + 1, 2 * r]))), shape=(2 * N, 2 * N))
+    J = (K + D).tocsr()
+    Pm = sp.csr_matrix((P.keoreg_fill(mu, g, x), P.cols, P.rowptr), shape=(2 * N, 2 * N))
+    return P, J, Pm, x
+
+
+@pytest.mark.parametrize("level", [0, 1])
+def test_mis2_rounds_equal_greedy(level):
+    P, J, Pm, _ = regularised_problem(9)
+    G = amg.node_pattern(Pm)
+    a, na = amg.aggregate_mis2(G, level)
+    b, nb = amg.aggregate_mis2_rounds(G, level)
+    assert na == nb and np.array_equal(a, b)
+    assert a.min() == 0 and a.max() == na - 1 and np.unique(a).size == na
+    # roots are pairwise more than two edges apart: no node sees two aggregates' roots
+    sizes = np.bincount(a)
+    assert sizes.min() >= 1 and sizes.mean() > 8
+
+
+def test_vcycle_is_spd_and_accelerates_minres():
+    P, J, Pm, x = regularised_problem(12, state="random")
+    H = amg.Hierarchy(Pm, coarse_max=64)
+    assert len(H.levels) >= 2
+    n2 = Pm.shape[0]
+    rng = np.random.default_rng(0)
+    u, v = rng.standard_normal(n2), rng.standard_normal(n2)
+    Mu, Mv = H.vcycle(u), H.vcycle(v)
+    assert abs(v @ Mu - u @ Mv) <= 1e-12 * abs(v @ Mu)      # symmetric
+    assert u @ Mu > 0 and v @ Mv > 0                         # positive
+    # M approximates the inverse of the regularised KEO
+    assert np.linalg.norm(Pm @ Mu - u) < 0.9 * np.linalg.norm(u)
+    b = -P.compute_f(1.0, x)
+    x0, it0, _ = P.krylov(b, 1e-10, 2000)
+    x1, it1, rr, hist = amg.pminres(lambda t: J @ t, H.vcycle, b, 1e-10, 2000)
+    assert it1 < it0 / 2
+    assert np.linalg.norm(J @ x1 - b) <= 1e-8 * np.linalg.norm(b)
+    # with M = I the Python restatement is the C++ oracle's MINRES
+    x2, it2, _, _ = amg.pminres(lambda t: J @ t, lambda r: r.copy(), b, 1e-10, 2000)
+    assert it2 == it0 and np.abs(x2 - x0).max() <= 1e-9 * np.abs(x0).max()
+
+
+def test_pcg_on_the_regularised_keo():
+    P, J, Pm, x = regularised_problem(10)
+    H = amg.Hierarchy(Pm, coarse_max=64, degree=2)
+    b = np.sin(np.arange(Pm.shape[0]) * 0.37)
+    x1, it1, rr, _ = amg.pcg(lambda t: Pm @ t, H.vcycle, b, 1e-10, 500)
+    assert rr <= 1e-10 and it1 < 40
+    assert np.linalg.norm(Pm @ x1 - b) <= 1e-9 * np.linalg.norm(b)
