@@ -243,7 +243,7 @@ typedef struct {
   int64_t nodes[NOSH_AMG_MAX_LEVELS];     /* block rows per level */
   int64_t blocks[NOSH_AMG_MAX_LEVELS];    /* 2x2 blocks per level (level 0: complex blocks of the owned columns) */
   int64_t p_blocks[NOSH_AMG_MAX_LEVELS];  /* blocks of the prolongator from level l+1 to l */
-  double lambda_max[NOSH_AMG_MAX_LEVELS]; /* estimate of lambda_max(D^-1 A) */
+  double lambda_max[NOSH_AMG_MAX_LEVELS]; /* power-iteration estimate of lambda_max(D^-1 A) (prolongator damping) */
   double setup_seconds;
 } nosh_amg_info_t;
 NOSH_API nosh_status nosh_amg_info(nosh_ctx *ctx, nosh_amg_info_t *info);

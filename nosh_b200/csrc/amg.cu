@@ -13,7 +13,9 @@
 //                 to the oracle's sequential greedy sweep
 //   P           : (I - 4/3 / lambda_max D^-1 A) P0,   A_c = P^T A P   by expand-sort-compress SpGEMM
 //                 (stable radix sort => fixed summation order => run-to-run identical bits)
-//   smoother    : Chebyshev of degree `amg_degree` on D^-1 A, ratio 20, boost 1.1 (degree 1 = damped Jacobi)
+//   smoother    : Chebyshev of degree `amg_degree` on S^-1 A over [1/20, 1], S = absolute row sums (l1-Jacobi
+//                 scaling: lambda_max(S^-1 A) <= 1 is a true bound row by row, so the V-cycle stays positive
+//                 definite on any mesh); degree 1 = damped l1-Jacobi
 //   coarsest    : dense inverse (host Cholesky at set-up), warp-per-row matvec
 // No atomics on floating-point data anywhere; restriction uses an explicit transpose index.
 #include "amg.h"
@@ -31,7 +33,6 @@ namespace {
 constexpr int POWER_ITS = 10;
 constexpr double SA_DAMPING = 4.0 / 3.0;
 constexpr double CHEB_RATIO = 20.0;
-constexpr double CHEB_BOOST = 1.1;
 constexpr int ST_OUT = 0, ST_UND = 1, ST_IN = 2;
 
 inline dim3 grid_for(int64_t n, int tpb = 256) { return dim3((unsigned)cdiv(n > 0 ? n : 1, tpb)); }
@@ -158,20 +159,41 @@ __global__ void k_l0_fill(const int32_t *rowptr, const int32_t *col, const int32
     o++;
   }
 }
-__global__ void k_l0_dinv(const double2 *K, const int32_t *diag_slot, const double2 *pd0, int64_t No, double2 *dinv) {
+// level 0, once per hierarchy: off-diagonal absolute row sums of K (both scalar rows of a complex block
+// row have the same one)
+__global__ void k_l0_offsum(const int32_t *rowptr, const int32_t *col, const B22 *val, int64_t n, double *offsum) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int p = rowptr[i]; p < rowptr[i + 1]; p++)
+    if (col[p] != i) s += fabs(val[p].a) + fabs(val[p].b);
+  offsum[i] = s;
+}
+// level 0, per state: 1 / diagonal and 1 / absolute row sum of the regularised KEO
+__global__ void k_l0_dinv(const double2 *K, const int32_t *diag_slot, const double2 *pd0, const double *pd1,
+                          const double *offsum, int64_t No, double2 *dinv, double2 *sinv) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= No) return;
   const double kd = K[diag_slot[i]].x;
   const double2 d0 = pd0[i];
   dinv[i] = make_double2(1.0 / (kd + d0.x), 1.0 / (kd + d0.y));
+  const double off = offsum[i] + fabs(pd1[i]);
+  sinv[i] = make_double2(1.0 / (off + fabs(kd + d0.x)), 1.0 / (off + fabs(kd + d0.y)));
 }
-__global__ void k_dinv(const int32_t *rowptr, const int32_t *col, const B22 *val, int64_t n, double2 *dinv) {
+__global__ void k_dinv(const int32_t *rowptr, const int32_t *col, const B22 *val, int64_t n, double2 *dinv,
+                       double2 *sinv) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   double2 d = make_double2(1.0, 1.0);
-  for (int p = rowptr[i]; p < rowptr[i + 1]; p++)
-    if (col[p] == i) d = make_double2(1.0 / val[p].a, 1.0 / val[p].d);
+  double s0 = 0.0, s1 = 0.0;
+  for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
+    const B22 v = val[p];
+    if (col[p] == i) d = make_double2(1.0 / v.a, 1.0 / v.d);
+    s0 += fabs(v.a) + fabs(v.b);
+    s1 += fabs(v.c) + fabs(v.d);
+  }
   dinv[i] = d;
+  sinv[i] = make_double2(1.0 / s0, 1.0 / s1);
 }
 
 // ---- MIS-2 aggregation -------------------------------------------------------------------------
@@ -662,7 +684,7 @@ double local_dot(Ctx *ctx, DBuf<double> &scratch, int64_t n, const double2 *x, c
 
 // ---- level operations used by both set-up and the V-cycle ---------------------------------------------------
 void level_apply(Ctx *ctx, AmgLevel &L, int lev, int mode, const double2 *x, double2 *y, const double2 *b, double2 *d,
-                 double c1, double c2, const KrylovState *gate) {
+                 double c1, double c2, const KrylovState *gate, const double2 *scale) {
   if (L.n == 0) return;
   if (lev == 0) {
     ApplyArgs A;
@@ -680,14 +702,14 @@ void level_apply(Ctx *ctx, AmgLevel &L, int lev, int mode, const double2 *x, dou
     A.d1 = ctx->pd1.p;
     A.bvec = b;
     A.dvec = d;
-    A.dinv = L.dinv.p;
+    A.dinv = scale;
     A.c1 = c1;
     A.c2 = c2;
     A.gate = gate;
     launch_apply(ctx, EPI_DIAG, mode == M_APPLY ? FUSE_NONE : mode == M_RESID ? FUSE_RESID : FUSE_CHEB, A);
     return;
   }
-  LevelArgs A{L.n, L.nslices, L.slice_off.p, L.scol.p, L.sval.p, x, y, b, d, L.dinv.p, c1, c2, gate};
+  LevelArgs A{L.n, L.nslices, L.slice_off.p, L.scol.p, L.sval.p, x, y, b, d, scale, c1, c2, gate};
   const unsigned grid = (unsigned)cdiv(L.nslices * 32, 256);
   if (mode == M_APPLY) k_level_apply<M_APPLY><<<grid, 256, 0, ctx->stream>>>(A);
   else if (mode == M_RESID) k_level_apply<M_RESID><<<grid, 256, 0, ctx->stream>>>(A);
@@ -707,12 +729,17 @@ double estimate_lambda(Ctx *ctx, AmgLevel &L, int lev, DBuf<double> &scratch) {
   double lam = 0.0;
   for (int it = 0; it < POWER_ITS; it++) {
     // y = D^-1 A x  ==  Chebyshev step with b = 0, c1 = 0, c2 = -1 (d receives the result)
-    level_apply(ctx, L, lev, M_CHEB, x, junk, zero, y, 0.0, -1.0, nullptr);
+    level_apply(ctx, L, lev, M_CHEB, x, junk, zero, y, 0.0, -1.0, nullptr, L.dinv.p);
     lam = local_dot(ctx, scratch, n, x, y);
     nrm = sqrt(local_dot(ctx, scratch, n, y, y));
     ALAUNCH(ctx, k_scale2, n, n, 1.0 / nrm, y, x);
   }
   return lam;
+}
+
+void l0_refresh_diag(Ctx *ctx, AmgLevel &L) {
+  ALAUNCH(ctx, k_l0_dinv, ctx->No, ctx->Kval.p, ctx->diag_slot.p, ctx->pd0.p, ctx->pd1.p, L.offsum.p, ctx->No,
+          L.dinv.p, L.sinv.p);
 }
 
 void alloc_level_vectors(Ctx *ctx, AmgLevel &L, int lev) {
@@ -861,7 +888,10 @@ void build_hierarchy(Ctx *ctx) {
             No, L->rowptr.p, L->col.p, L->val.p);
   }
   L->dinv.alloc(No > 0 ? No : 1);
-  ALAUNCH(ctx, k_l0_dinv, No, ctx->Kval.p, ctx->diag_slot.p, ctx->pd0.p, No, L->dinv.p);
+  L->sinv.alloc(No > 0 ? No : 1);
+  L->offsum.alloc(No > 0 ? No : 1);
+  ALAUNCH(ctx, k_l0_offsum, No, L->rowptr.p, L->col.p, L->val.p, No, L->offsum.p);
+  l0_refresh_diag(ctx, *L);
   alloc_level_vectors(ctx, *L, 0);
   DBuf<double> s_cur;  // null-space weights of the current level (level 0: all ones => not allocated)
   for (int lev = 0;; lev++) {
@@ -942,7 +972,8 @@ void build_hierarchy(Ctx *ctx) {
       L->val.release();
     }
     C->dinv.alloc(nc);
-    ALAUNCH(ctx, k_dinv, nc, C->rowptr.p, C->col.p, C->val.p, nc, C->dinv.p);
+    C->sinv.alloc(nc);
+    ALAUNCH(ctx, k_dinv, nc, C->rowptr.p, C->col.p, C->val.p, nc, C->dinv.p, C->sinv.p);
     build_sell(ctx, tmp, *C);
     alloc_level_vectors(ctx, *C, lev + 1);
     s_cur.swap(sc);
@@ -956,8 +987,8 @@ void build_hierarchy(Ctx *ctx) {
 
 struct Cheb {
   double theta, delta, sigma;
-  explicit Cheb(double lam) {
-    const double lmax = CHEB_BOOST * lam, lmin = lmax / CHEB_RATIO;
+  Cheb() {  // spectrum of S^-1 A, S = absolute row sums: lambda_max <= 1 is a true bound, so no boost factor
+    const double lmax = 1.0, lmin = lmax / CHEB_RATIO;
     theta = 0.5 * (lmax + lmin);
     delta = 0.5 * (lmax - lmin);
     sigma = theta / delta;
@@ -981,21 +1012,21 @@ double2 *vcycle_level(Ctx *ctx, Amg &H, int lev, const double2 *b, double2 *out,
     return x;
   }
   const int deg = ctx->amg_degree;
-  const Cheb ch(L.lam);
+  const Cheb ch;
   // 2*deg - 1 buffer flips follow the first write: start so that the last one lands in `out`
   double2 *xa = L.x.p, *xb = out ? out : L.x2.p;
   double2 *dvec = deg > 1 ? L.d.p : nullptr;
   // pre-smoothing from x = 0
-  ALAUNCH(ctx, k_cheb_first, n, n, b, L.dinv.p, 1.0 / ch.theta, dvec, xa, gate);
+  ALAUNCH(ctx, k_cheb_first, n, n, b, L.sinv.p, 1.0 / ch.theta, dvec, xa, gate);
   double rho = 1.0 / ch.sigma;
   for (int k = 1; k < deg; k++) {
     const double rho_new = 1.0 / (2.0 * ch.sigma - rho);
-    level_apply(ctx, L, lev, M_CHEB, xa, xb, b, dvec, rho_new * rho, 2.0 * rho_new / ch.delta, gate);
+    level_apply(ctx, L, lev, M_CHEB, xa, xb, b, dvec, rho_new * rho, 2.0 * rho_new / ch.delta, gate, L.sinv.p);
     std::swap(xa, xb);
     rho = rho_new;
   }
   // coarse-grid correction
-  level_apply(ctx, L, lev, M_RESID, xa, L.r.p, b, nullptr, 0.0, 0.0, gate);
+  level_apply(ctx, L, lev, M_RESID, xa, L.r.p, b, nullptr, 0.0, 0.0, gate, nullptr);
   AmgLevel &C = *H.levels[lev + 1];
   k_restrict<8><<<(unsigned)cdiv(C.n * 8, 256), 256, 0, ctx->stream>>>(C.n, L.r_rowptr.p, L.r_fine.p, L.r_pos.p,
                                                                       L.p_val.p, L.r.p, C.b.p, gate);
@@ -1005,11 +1036,11 @@ double2 *vcycle_level(Ctx *ctx, Amg &H, int lev, const double2 *b, double2 *out,
   ALAUNCH(ctx, k_prolong, n, n, L.p_rowptr.p, L.p_col.p, L.p_val.p, xc, xa, gate);
   // post-smoothing
   rho = 1.0 / ch.sigma;
-  level_apply(ctx, L, lev, M_CHEB, xa, xb, b, dvec, 0.0, 1.0 / ch.theta, gate);
+  level_apply(ctx, L, lev, M_CHEB, xa, xb, b, dvec, 0.0, 1.0 / ch.theta, gate, L.sinv.p);
   std::swap(xa, xb);
   for (int k = 1; k < deg; k++) {
     const double rho_new = 1.0 / (2.0 * ch.sigma - rho);
-    level_apply(ctx, L, lev, M_CHEB, xa, xb, b, dvec, rho_new * rho, 2.0 * rho_new / ch.delta, gate);
+    level_apply(ctx, L, lev, M_CHEB, xa, xb, b, dvec, rho_new * rho, 2.0 * rho_new / ch.delta, gate, L.sinv.p);
     std::swap(xa, xb);
     rho = rho_new;
   }
@@ -1033,8 +1064,7 @@ void amg_ensure(Ctx *ctx) {
     if (ctx->amg_dinv_version != ctx->keoreg_version) {
       // "reuse: type" = "full": the hierarchy is kept; only the finest-level matrix (read live from the
       // ctx) and its diagonal follow the new state
-      AmgLevel &L = *ctx->amg->levels[0];
-      ALAUNCH(ctx, k_l0_dinv, ctx->No, ctx->Kval.p, ctx->diag_slot.p, ctx->pd0.p, ctx->No, L.dinv.p);
+      l0_refresh_diag(ctx, *ctx->amg->levels[0]);
       ctx->amg_dinv_version = ctx->keoreg_version;
     }
     return;

@@ -44,7 +44,8 @@ struct Temp {
 
 void sort_pairs_u64(Ctx *ctx, Temp &tmp, DBuf<uint64_t> &keys, DBuf<uint32_t> &vals, int64_t n,
                     int end_bit = 64) {
-  if (n >= (int64_t)2147483647) NOSH_THROW(NOSH_EINVAL, "mesh too large for one GPU (sort of %lld items)", (long long)n);
+  // payloads are 32-bit positions: up to 2^32 - 2 items (64M vertices = 2.3e9 (cell, edge) pairs fit)
+  if (n >= (int64_t)4294967295ll) NOSH_THROW(NOSH_EINVAL, "mesh too large for one GPU (sort of %lld items)", (long long)n);
   DBuf<uint64_t> k2;
   DBuf<uint32_t> v2;
   k2.alloc(n);
@@ -52,9 +53,9 @@ void sort_pairs_u64(Ctx *ctx, Temp &tmp, DBuf<uint64_t> &keys, DBuf<uint32_t> &v
   cub::DoubleBuffer<uint64_t> dk(keys.p, k2.p);
   cub::DoubleBuffer<uint32_t> dv(vals.p, v2.p);
   size_t bytes = 0;
-  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)n, 0, end_bit, ctx->stream));
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, n, 0, end_bit, ctx->stream));
   void *t = tmp.get(bytes);
-  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(t, bytes, dk, dv, (int)n, 0, end_bit, ctx->stream));
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(t, bytes, dk, dv, n, 0, end_bit, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   if (dk.Current() != keys.p) keys.swap(k2);
   if (dv.Current() != vals.p) vals.swap(v2);
@@ -90,9 +91,9 @@ void sort_keys_u32(Ctx *ctx, Temp &tmp, DBuf<uint32_t> &keys, int64_t n) {
 
 void inclusive_scan_i32(Ctx *ctx, Temp &tmp, const int32_t *in, int32_t *out, int64_t n) {
   size_t bytes = 0;
-  CUDA_CHECK(cub::DeviceScan::InclusiveSum(nullptr, bytes, in, out, (int)n, ctx->stream));
+  CUDA_CHECK(cub::DeviceScan::InclusiveSum(nullptr, bytes, in, out, n, ctx->stream));
   void *t = tmp.get(bytes);
-  CUDA_CHECK(cub::DeviceScan::InclusiveSum(t, bytes, in, out, (int)n, ctx->stream));
+  CUDA_CHECK(cub::DeviceScan::InclusiveSum(t, bytes, in, out, n, ctx->stream));
 }
 
 void exclusive_scan_i32(Ctx *ctx, Temp &tmp, const int32_t *in, int32_t *out, int64_t n) {
@@ -268,25 +269,18 @@ __global__ void k_head_flags_u64(const uint64_t *keys, int64_t n, int32_t *head)
 // sorted position i -> edge id (incl[i]-1); writes edges, incidence pointers, cell_edges
 __global__ void k_edges_from_sorted(const uint64_t *keys, const uint32_t *vals, const int32_t *head,
                                     const int32_t *incl, int64_t n, int64_t vb, int64_t ve, int64_t No,
-                                    const uint32_t *ghost, int Ng, int32_t *edges, int32_t *inc_ptr,
-                                    int32_t *cell_edges) {
+                                    const uint32_t *ghost, int Ng, int32_t *edges, uint32_t *inc_ptr) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t k = keys[i];
-  if (k == SENT64) {
-    cell_edges[vals[i]] = -1;
-    return;
-  }
+  if (k == SENT64 || !head[i]) return;
   const int e = incl[i] - 1;
-  cell_edges[vals[i]] = e;
-  if (head[i]) {
-    edges[2 * e] = to_local((uint32_t)(k >> 32), vb, ve, No, ghost, Ng);
-    edges[2 * e + 1] = to_local((uint32_t)(k & 0xFFFFFFFFu), vb, ve, No, ghost, Ng);
-    inc_ptr[e] = (int32_t)i;
-  }
+  edges[2 * e] = to_local((uint32_t)(k >> 32), vb, ve, No, ghost, Ng);
+  edges[2 * e + 1] = to_local((uint32_t)(k & 0xFFFFFFFFu), vb, ve, No, ghost, Ng);
+  inc_ptr[e] = (uint32_t)i;
 }
-__global__ void k_count_nonsent(const uint64_t *keys, int64_t n, int32_t *out) {
-  out[0] = (int32_t)lower_bound_u64(keys, n, SENT64);
+__global__ void k_count_nonsent(const uint64_t *keys, int64_t n, uint32_t *out) {
+  out[0] = (uint32_t)lower_bound_u64(keys, n, SENT64);
 }
 __global__ void k_edge_length(const double *coords, const int32_t *edges, int64_t E, double *len) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -402,13 +396,13 @@ __global__ void k_cell_coeff_tri(const double *coords, const int32_t *cellsL, co
 
 // covolume_e = sum over the edge's cells, in ascending cell order, of coef * length
 // (src/mesh_tetra.cpp:95-99); products and sums individually rounded like the scalar loop.
-__global__ void k_edge_covolume(const double *coef, const uint32_t *inc, const int32_t *inc_ptr,
+__global__ void k_edge_covolume(const double *coef, const uint32_t *inc, const uint32_t *inc_ptr,
                                 const double *len, int64_t E, double *cov) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= E) return;
   const double l = len[e];
   double s = 0.0;
-  for (int p = inc_ptr[e]; p < inc_ptr[e + 1]; p++) s = __dadd_rn(s, __dmul_rn(coef[inc[p]], l));
+  for (uint32_t p = inc_ptr[e]; p < inc_ptr[e + 1]; p++) s = __dadd_rn(s, __dmul_rn(coef[inc[p]], l));
   cov[e] = s;
 }
 
@@ -630,9 +624,9 @@ void build_from_cells(Ctx *ctx, DBuf<int32_t> &cellsG, int64_t ncand, const doub
   LAUNCH(ctx, (k_edge_keys<NVC, NE>), nke, ctx->cells.p, ctx->gid.p, nc, No, ekeys.p, evals.p);
   sort_pairs_u64(ctx, tmp, ekeys, evals, nke);
   int64_t E = 0;
-  DBuf<int32_t> inc_ptr;
+  DBuf<uint32_t> inc_ptr;
   {
-    DBuf<int32_t> head, incl, cell_edges;
+    DBuf<int32_t> head, incl;
     head.alloc(nke);
     incl.alloc(nke);
     LAUNCH(ctx, k_head_flags_u64, nke, ekeys.p, nke, head.p);
@@ -641,9 +635,8 @@ void build_from_cells(Ctx *ctx, DBuf<int32_t> &cellsG, int64_t ncand, const doub
     ctx->E = E;
     ctx->edges.alloc(E * 2);
     inc_ptr.alloc(E + 1);
-    cell_edges.alloc(nke);  // kept only as a by-product check; coefficients use incidence lists
     LAUNCH(ctx, k_edges_from_sorted, nke, ekeys.p, evals.p, head.p, incl.p, nke, vb, ve, No, ghost.p,
-           (int)Ng, ctx->edges.p, inc_ptr.p, cell_edges.p);
+           (int)Ng, ctx->edges.p, inc_ptr.p);
     // end pointer: first sentinel position (== number of non-sentinel keys)
     k_count_nonsent<<<1, 1, 0, ctx->stream>>>(ekeys.p, nke, inc_ptr.p + E);
     ctx->launches++;

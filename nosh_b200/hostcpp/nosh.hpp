@@ -326,7 +326,8 @@ public:
       : mesh_(mesh), thickness_(thickness), mvp_(mvp) {
     bind_fields(*mesh_, thickness_.get(), mvp_.get(), nullptr);
   }
-  // the inverse is a MueLu V-cycle in the reference (out of scope): throws std::runtime_error
+  // one AMG V-cycle on the regularised KEO (src/keo_regularized.cpp:88-165; MueLu in the reference, built on
+  // the device here); unsupported mode/alpha/beta -> std::logic_error (:98-100)
   void apply(const Tpetra::MultiVector<double, int, int> &X, Tpetra::MultiVector<double, int, int> &Y,
              Teuchos::ETransp mode = Teuchos::NO_TRANS, double alpha = 1.0, double beta = 0.0) const override {
     check(mesh_->ctx(), nosh_keoreg_apply(mesh_->ctx(), X.getData(), (int64_t)X.getStride(), Y.getDataNonConst(),

@@ -144,12 +144,21 @@ static void run(const Fixture &fx) {
     REQUIRE_THROWS_AS(jac->apply(s, Js, Teuchos::TRANS, 1.0, 0.0), std::logic_error);
     REQUIRE_THROWS_AS(jac->apply(s, Js, Teuchos::NO_TRANS, 2.0, 0.0), std::logic_error);
     REQUIRE_THROWS_AS(jac->apply(s, Js, Teuchos::NO_TRANS, 1.0, 1.0), std::logic_error);
-    // preconditioner object: matrix rebuild works, the AMG inverse is out of scope
+    // preconditioner object (keo_regularized): rebuild, then apply = one AMG V-cycle.  On these fixtures
+    // the hierarchy is a single level, i.e. the exact inverse: P (M s) == s.
     auto prec = model.create_W_prec();
     auto out2 = model.createOutArgs();
     out2.set_W_prec(prec);
     model.evalModel(in, out2);
-    REQUIRE_THROWS_AS(prec->apply(s, Js), std::runtime_error);
+    Tpetra::Vector<double, int, int> Ms(jac->getRangeMap()), PMs(jac->getRangeMap());
+    prec->apply(s, Ms);
+    std::dynamic_pointer_cast<nosh::keo_regularized>(prec)->apply_matrix(Ms, PMs);
+    double worst_p = 0.0;
+    for (size_t k = 0; k < 2 * N; k++) worst_p = std::fmax(worst_p, std::fabs(PMs[k] - s[k]));
+    REQUIRE_APPROX(1.0 + worst_p, 1.0, 1e-10);
+    // keo_regularized.cpp:98-100: anything but NO_TRANS / 1 / 0 is refused
+    REQUIRE_THROWS_AS(prec->apply(s, Ms, Teuchos::TRANS, 1.0, 0.0), std::logic_error);
+    REQUIRE_THROWS_AS(prec->apply(s, Ms, Teuchos::NO_TRANS, 1.0, 1.0), std::logic_error);
   }
   // ---- test/dfdp.cpp:51-142: dF/dg vs central difference, mu = 0 ----
   {
