@@ -34,6 +34,7 @@ constexpr int POWER_ITS = 10;
 constexpr double SA_DAMPING = 4.0 / 3.0;
 constexpr double CHEB_RATIO = 20.0;
 constexpr int ST_OUT = 0, ST_UND = 1, ST_IN = 2;
+constexpr int64_t SMALL_LEVEL = 65536;  // rows below which a level uses the lanes-per-row kernels
 
 inline dim3 grid_for(int64_t n, int tpb = 256) { return dim3((unsigned)cdiv(n > 0 ? n : 1, tpb)); }
 
@@ -567,6 +568,60 @@ __global__ void __launch_bounds__(256) k_level_apply(const LevelArgs L) {
   L.y[row] = s;
 }
 
+// Small levels (a few thousand rows of ~50 blocks): one thread per row is latency bound, so LPR lanes
+// share a row of the block CSR (consecutive lanes read consecutive 32-byte blocks) and combine with a
+// fixed xor tree.  Same modes as k_level_apply.
+struct LevelCsrArgs {
+  int64_t n;
+  const int32_t *rowptr, *col;
+  const B22 *val;
+  const double2 *x;
+  double2 *y;
+  const double2 *b;
+  double2 *d;
+  const double2 *dinv;
+  double c1, c2;
+  const KrylovState *gate;
+};
+template <int MODE, int LPR>
+__global__ void __launch_bounds__(256) k_level_apply_csr(const LevelCsrArgs L) {
+  if (L.gate && L.gate->done) return;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t row = t / LPR;
+  const int sl = (int)(t % LPR);
+  double2 s = make_double2(0.0, 0.0);
+  if (row < L.n) {
+    const int e = __ldg(L.rowptr + row + 1);
+    for (int p = __ldg(L.rowptr + row) + sl; p < e; p += LPR) {
+      const B22 v = L.val[p];
+      const double2 xv = __ldg(L.x + __ldg(L.col + p));
+      s.x += v.a * xv.x + v.b * xv.y;
+      s.y += v.c * xv.x + v.d * xv.y;
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+    s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+  }
+  if (row >= L.n || sl != 0) return;
+  if (MODE == M_RESID) {
+    const double2 bb = L.b[row];
+    s = make_double2(bb.x - s.x, bb.y - s.y);
+  } else if (MODE == M_CHEB) {
+    const double2 bb = L.b[row], di = L.dinv[row], xi = L.x[row];
+    double2 dd = make_double2(L.c2 * (di.x * (bb.x - s.x)), L.c2 * (di.y * (bb.y - s.y)));
+    if (L.c1 != 0.0) {
+      const double2 dold = L.d[row];
+      dd.x += L.c1 * dold.x;
+      dd.y += L.c1 * dold.y;
+    }
+    if (L.d) L.d[row] = dd;
+    s = make_double2(xi.x + dd.x, xi.y + dd.y);
+  }
+  L.y[row] = s;
+}
+
 // d = c2 D^-1 b,  x = d   (first Chebyshev step from a zero initial guess)
 __global__ void k_cheb_first(int64_t n, const double2 *b, const double2 *dinv, double c2, double2 *d, double2 *x,
                              const KrylovState *gate) {
@@ -707,6 +762,17 @@ void level_apply(Ctx *ctx, AmgLevel &L, int lev, int mode, const double2 *x, dou
     A.c2 = c2;
     A.gate = gate;
     launch_apply(ctx, EPI_DIAG, mode == M_APPLY ? FUSE_NONE : mode == M_RESID ? FUSE_RESID : FUSE_CHEB, A);
+    return;
+  }
+  if (L.n <= SMALL_LEVEL) {
+    constexpr int LPR = 8;
+    LevelCsrArgs A{L.n, L.rowptr.p, L.col.p, L.val.p, x, y, b, d, scale, c1, c2, gate};
+    const unsigned grid = (unsigned)cdiv(L.n * LPR, 256);
+    if (mode == M_APPLY) k_level_apply_csr<M_APPLY, LPR><<<grid, 256, 0, ctx->stream>>>(A);
+    else if (mode == M_RESID) k_level_apply_csr<M_RESID, LPR><<<grid, 256, 0, ctx->stream>>>(A);
+    else k_level_apply_csr<M_CHEB, LPR><<<grid, 256, 0, ctx->stream>>>(A);
+    ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
     return;
   }
   LevelArgs A{L.n, L.nslices, L.slice_off.p, L.scol.p, L.sval.p, x, y, b, d, scale, c1, c2, gate};
@@ -1028,8 +1094,12 @@ double2 *vcycle_level(Ctx *ctx, Amg &H, int lev, const double2 *b, double2 *out,
   // coarse-grid correction
   level_apply(ctx, L, lev, M_RESID, xa, L.r.p, b, nullptr, 0.0, 0.0, gate, nullptr);
   AmgLevel &C = *H.levels[lev + 1];
-  k_restrict<8><<<(unsigned)cdiv(C.n * 8, 256), 256, 0, ctx->stream>>>(C.n, L.r_rowptr.p, L.r_fine.p, L.r_pos.p,
-                                                                      L.p_val.p, L.r.p, C.b.p, gate);
+  if (C.n <= SMALL_LEVEL)  // long rows of P^T, few of them: a full warp per coarse node
+    k_restrict<32><<<(unsigned)cdiv(C.n * 32, 256), 256, 0, ctx->stream>>>(C.n, L.r_rowptr.p, L.r_fine.p, L.r_pos.p,
+                                                                          L.p_val.p, L.r.p, C.b.p, gate);
+  else
+    k_restrict<8><<<(unsigned)cdiv(C.n * 8, 256), 256, 0, ctx->stream>>>(C.n, L.r_rowptr.p, L.r_fine.p, L.r_pos.p,
+                                                                        L.p_val.p, L.r.p, C.b.p, gate);
   ctx->launches++;
   CUDA_CHECK(cudaGetLastError());
   const double2 *xc = vcycle_level(ctx, H, lev + 1, C.b.p, nullptr, gate);

@@ -19,6 +19,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", "--mesh-n", dest="n", type=int, default=100)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--layout", default="sell32")
+ap.add_argument("--precond", default="none", choices=["none", "amg"])
+ap.add_argument("--amg-degree", type=int, default=1)
 a = ap.parse_args()
 
 ctx = nosh_b200.Context(layout={"csr": 0, "sell32": 1}[a.layout])
@@ -35,11 +37,19 @@ x = torch.empty_like(b)
 par = {"g": 1.0, "mu": 1.0, "theta": 0.0}
 
 
+if a.precond == "amg":
+    ctx.amg_set_options(degree=a.amg_degree)
+
+
 def step(k):
     par["mu"] = 1.0 + 1e-9 * k
     ctx.keo_fill(par)
     ctx.jac_rebuild(par, psi)
-    ctx.minres(b, x, tol=0.0, maxit=a.iters)
+    if a.precond == "amg":
+        ctx.keoreg_rebuild(par, psi)
+        ctx.minres(b, x, tol=0.0, maxit=a.iters, prec=nosh_b200.PREC_KEOREG_AMG)
+    else:
+        ctx.minres(b, x, tol=0.0, maxit=a.iters)
 
 
 step(0)

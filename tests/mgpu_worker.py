@@ -97,6 +97,43 @@ def main():
     assert nres.steps == steps and list(glin) == list(lin), (nres.steps, steps, glin, lin)
     assert relerr(psi, xn[sl]) <= 1e-8
 
+    # ---- preconditioned MINRES: every rank applies the AMG V-cycle of ITS diagonal block of the
+    # regularised KEO (no communication inside the preconditioner); the oracle does the same with one
+    # hierarchy per rank's vertex range
+    import scipy.sparse as sp
+    from oracle import amg
+    ctx.amg_set_options(coarse_max=64)
+    ctx.keo_fill(par)
+    ctx.jac_rebuild(par, x[sl].copy())
+    ctx.keoreg_rebuild(par, x[sl].copy())
+    P.keo_fill(par["mu"])
+    P.jac_rebuild(par["g"], x)
+    K = sp.csr_matrix((P.vals.copy(), P.cols, P.rowptr), shape=(2 * N, 2 * N))
+    rr = np.arange(N)
+    Dj = sp.csr_matrix((np.concatenate([P.d0[0::2], P.d0[1::2], P.d1b, P.d1b]),
+                        (np.concatenate([2 * rr, 2 * rr + 1, 2 * rr, 2 * rr + 1]),
+                         np.concatenate([2 * rr, 2 * rr + 1, 2 * rr + 1, 2 * rr]))), shape=(2 * N, 2 * N))
+    J = (K + Dj).tocsr()
+    Pm = sp.csr_matrix((P.keoreg_fill(par["mu"], par["g"], x), P.cols, P.rowptr), shape=(2 * N, 2 * N))
+    blocks = []
+    for r in range(world):
+        b0, e0, _ = nosh_b200.partition_range(N, world, r, group)
+        blocks.append((b0, e0, amg.Hierarchy(Pm[2 * b0:2 * e0, 2 * b0:2 * e0], coarse_max=64, degree=1)))
+
+    def M(v):
+        out = np.empty_like(v)
+        for b0, e0, H in blocks:
+            out[2 * b0:2 * e0] = H.vcycle(v[2 * b0:2 * e0])
+        return out
+
+    zg = ctx.keoreg_apply(y[sl].copy())
+    assert relerr(zg, M(y)[sl]) <= 1e-11
+    xpo, itpo, _, _ = amg.pminres(lambda t: J @ t, M, b, 1e-10, 1000)
+    xpg, pres = ctx.minres(b[sl].copy(), tol=1e-10, maxit=1000, prec=nosh_b200.PREC_KEOREG_AMG)
+    assert pres.iterations == itpo and pres.converged == 1, (pres.iterations, itpo)
+    assert relerr(xpg, xpo[sl]) <= 1e-8
+    assert itpo < ito / 2
+
     # ---- partition independence: bit-identical to one GPU -----------------------------------
     single = nosh_b200.Context(device=local, group_vertices=group)
     single.mesh_tetgrid(n, n, n + 3)
