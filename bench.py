@@ -276,6 +276,7 @@ def run_b200(args):
             detail["amg"] = {"levels": int(ai.levels), "degree": int(ai.degree),
                              "nodes": [int(ai.nodes[l]) for l in range(ai.levels)],
                              "blocks": [int(ai.blocks[l]) for l in range(ai.levels)],
+                             "prolongator_blocks": [int(ai.p_blocks[l]) for l in range(ai.levels - 1)],
                              "lambda_max": [float(ai.lambda_max[l]) for l in range(ai.levels - 1)],
                              "setup_seconds": float(ai.setup_seconds),
                              "note": "hierarchy built in the first (warm-up) solve and reused "
@@ -421,6 +422,7 @@ def run_solver_workload(args, ctx, mi, world, rank, local, barrier, real_stdout,
             detail["amg"] = {"levels": int(ai.levels), "degree": int(ai.degree),
                              "nodes": [int(ai.nodes[l]) for l in range(ai.levels)],
                              "blocks": [int(ai.blocks[l]) for l in range(ai.levels)],
+                             "prolongator_blocks": [int(ai.p_blocks[l]) for l in range(ai.levels - 1)],
                              "lambda_max": [float(ai.lambda_max[l]) for l in range(ai.levels - 1)],
                              "setup_seconds": float(ai.setup_seconds),
                              "note": "hierarchy built in the first (warm-up) solve and reused "

@@ -22,6 +22,7 @@
 
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cub/cub.cuh>
 
 #include "apply.cuh"
@@ -931,6 +932,20 @@ void build_coarse_inverse(Ctx *ctx, Amg &H) {
 
 void build_hierarchy(Ctx *ctx) {
   const auto t0 = std::chrono::steady_clock::now();
+  // NOSH_B200_AMG_TIMING=1: phase times of the set-up on stderr
+  static const bool timing = [] {
+    const char *e = getenv("NOSH_B200_AMG_TIMING");
+    return e && atoi(e) != 0;
+  }();
+  auto tlast = t0;
+  auto tick = [&](const char *what, int lev) {
+    if (!timing) return;
+    cudaStreamSynchronize(ctx->stream);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[amg setup] level %d %-22s %8.1f ms\n", lev, what,
+            1e3 * std::chrono::duration<double>(now - tlast).count());
+    tlast = now;
+  };
   amg_free(ctx);
   Amg *H = new Amg();
   ctx->amg = H;
@@ -959,6 +974,7 @@ void build_hierarchy(Ctx *ctx) {
   ALAUNCH(ctx, k_l0_offsum, No, L->rowptr.p, L->col.p, L->val.p, No, L->offsum.p);
   l0_refresh_diag(ctx, *L);
   alloc_level_vectors(ctx, *L, 0);
+  tick("level-0 block CSR", 0);
   DBuf<double> s_cur;  // null-space weights of the current level (level 0: all ones => not allocated)
   for (int lev = 0;; lev++) {
     L = H->levels[lev];
@@ -967,8 +983,10 @@ void build_hierarchy(Ctx *ctx) {
     const int64_t nc = aggregate(ctx, tmp, *L, lev, L->rowptr.p, L->col.p);
     if (nc >= n) break;
     L->nc = nc;
+    tick("aggregation", lev);
     L->lam = estimate_lambda(ctx, *L, lev, scratch);
     L->omega = SA_DAMPING / L->lam;
+    tick("power iteration", lev);
     // tentative prolongator weights
     DBuf<double> sc;
     sc.alloc(nc);
@@ -1000,6 +1018,7 @@ void build_hierarchy(Ctx *ctx) {
       spgemm(ctx, tmp, Csr{n, L->rowptr.p, L->col.p, L->val.p}, P0.view(), P);
     }
     ALAUNCH(ctx, k_smooth_p, n, n, P.rowptr.p, P.col.p, P.val.p, L->agg.p, L->p0.p, L->dinv.p, L->omega);
+    tick("P = (I - w D^-1 A) P0", lev);
     // A_c = P^T (A P)
     AmgLevel *C = new AmgLevel();
     H->levels.push_back(C);
@@ -1007,7 +1026,9 @@ void build_hierarchy(Ctx *ctx) {
     {
       CsrOut AP, Ac;
       spgemm(ctx, tmp, Csr{n, L->rowptr.p, L->col.p, L->val.p}, P.view(), AP);
+      tick("A P", lev);
       spgemm_atb(ctx, tmp, P.view(), AP.view(), nc, Ac);
+      tick("P^T (A P)", lev);
       C->nb = Ac.nnz;
       C->rowptr.swap(Ac.rowptr);
       C->col.swap(Ac.col);
@@ -1044,8 +1065,10 @@ void build_hierarchy(Ctx *ctx) {
     alloc_level_vectors(ctx, *C, lev + 1);
     s_cur.swap(sc);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    tick("transpose, SELL, vectors", lev);
   }
   build_coarse_inverse(ctx, *H);
+  tick("dense coarse inverse", (int)H->levels.size() - 1);
   ctx->amg_valid = true;
   ctx->amg_dinv_version = ctx->keoreg_version;
   H->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
