@@ -282,6 +282,14 @@ NOSH_API nosh_status nosh_minres_prec(nosh_ctx *ctx, nosh_operator_id op, nosh_p
 NOSH_API nosh_status nosh_cg_prec(nosh_ctx *ctx, nosh_operator_id op, nosh_precond prec, const double *b,
                                   double *x, double tol, int maxit, nosh_krylov_result *res,
                                   double *hist);
+/* Restarted GMRES(restart): the solver examples/conf.xml:104 selects ("Pseudo Block GMRES", tolerance
+ * 1e-10, 1000 iterations; Belos' default restart length "Num Blocks" = 300).  Two-pass iterated
+ * classical Gram-Schmidt (Belos' default "ICGS"), x0 = 0, stop on the implicit relative residual
+ * |g_{j+1}| / ||b|| <= tol; prec is applied from the RIGHT (x = M y), so residuals are true residuals.
+ * Needs (restart+1) extra vectors of device memory.  restart in [1, 500]. */
+NOSH_API nosh_status nosh_gmres(nosh_ctx *ctx, nosh_operator_id op, nosh_precond prec, const double *b,
+                                double *x, double tol, int maxit, int restart, nosh_krylov_result *res,
+                                double *hist);
 /* preconditioner the Newton / continuation drivers give their linear solves (default NONE);
  * with KEOREG_AMG every Newton step also does keo_regularized::rebuild at the current state,
  * the evalModel(W_prec) of src/model_evaluator_nls.cpp:507-522 */
@@ -333,6 +341,47 @@ NOSH_API nosh_status nosh_continuation(nosh_ctx *ctx, int np, const char *const 
                                        const double *values, const char *pname, double dp, int nsteps,
                                        double *psi, double nl_tol, int nl_maxit, double lin_tol,
                                        int lin_maxit, nosh_continuation_step *steps);
+
+/* Pseudo-arclength continuation: the LOCA configuration nosh-cont actually uses
+ * (examples/conf.xml:35-75: "Continuation Method" = "Arc Length", "Predictor" = "Tangent", adaptive
+ * step size with aggressiveness 2, failed steps halved).  LOCA is third party (not in the reference
+ * tree, unpinned); the algorithm is the bordering form restated in oracle/continuation.py:
+ * constraint <xdot, x - x0>/len + pdot (p - p0) = ds with LOCA's scaled dot product (Euclidean / vector
+ * length, parameter scaling 1), Newton on the bordered system by two MINRES solves with the same
+ * Jacobian (J a = -F, J b = -dF/dp), tangent J t = -dF/dp after every accepted step.
+ * steps: max_steps+1 records (step 0 = the solution at the initial parameter value);
+ * *n_records = number written.  Follows the branch through turning points, where the natural
+ * continuation of nosh_continuation fails. */
+typedef struct {
+  double initial_step_size; /* signed: the direction of the first step in the parameter */
+  double min_step_size, max_step_size;
+  double aggressiveness;
+  int32_t max_steps;
+  int32_t nl_maxit;
+  double nl_tol;   /* on sqrt(||F||^2 + g^2) */
+  double lin_tol;
+  int32_t lin_maxit;
+  int32_t reserved;
+  double min_value, max_value; /* stop once the parameter leaves [min_value, max_value] */
+} nosh_arclength_options;
+typedef struct {
+  int32_t step;
+  int32_t converged;
+  int32_t newton_steps;
+  int32_t linear_iterations;           /* MINRES iterations of the corrector (two solves per Newton step) */
+  int32_t predictor_linear_iterations; /* MINRES iterations of the tangent solve this step started from */
+  int32_t reserved;
+  double param;
+  double gibbs_energy;
+  double norm;
+  double fnorm;
+  double step_size;  /* arc length of this step */
+  double dparam_ds;  /* parameter component of the unit tangent at the new point */
+} nosh_arclength_step;
+NOSH_API nosh_status nosh_continuation_arclength(nosh_ctx *ctx, int np, const char *const *names,
+                                                 const double *values, const char *pname,
+                                                 const nosh_arclength_options *opt, double *psi,
+                                                 nosh_arclength_step *steps, int32_t *n_records);
 
 /* ---- measurement helpers: device-resident scratch vectors so that benchmarks can
  * time kernels with inputs already in HBM.  slot in [0,8). Returns a device pointer to

@@ -45,6 +45,21 @@ class AmgInfo(C.Structure):
                 ("lambda_max", C.c_double * AMG_MAX_LEVELS), ("setup_seconds", C.c_double)]
 
 
+class ArclengthOptions(C.Structure):
+    _fields_ = [("initial_step_size", C.c_double), ("min_step_size", C.c_double), ("max_step_size", C.c_double),
+                ("aggressiveness", C.c_double), ("max_steps", C.c_int32), ("nl_maxit", C.c_int32),
+                ("nl_tol", C.c_double), ("lin_tol", C.c_double), ("lin_maxit", C.c_int32),
+                ("reserved", C.c_int32), ("min_value", C.c_double), ("max_value", C.c_double)]
+
+
+class ArclengthStep(C.Structure):
+    _fields_ = [("step", C.c_int32), ("converged", C.c_int32), ("newton_steps", C.c_int32),
+                ("linear_iterations", C.c_int32), ("predictor_linear_iterations", C.c_int32),
+                ("reserved", C.c_int32), ("param", C.c_double), ("gibbs_energy", C.c_double),
+                ("norm", C.c_double), ("fnorm", C.c_double), ("step_size", C.c_double),
+                ("dparam_ds", C.c_double)]
+
+
 class NewtonResult(C.Structure):
     _fields_ = [("steps", C.c_int32), ("converged", C.c_int32),
                 ("total_linear_iterations", C.c_int32), ("fnorm", C.c_double)]
@@ -132,6 +147,7 @@ def lib():
         "nosh_cg": (C.c_int, [vp, C.c_int, vp, vp, dbl, C.c_int, C.POINTER(KrylovResult), vp]),
         "nosh_minres_prec": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, dbl, C.c_int, C.POINTER(KrylovResult), vp]),
         "nosh_cg_prec": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, dbl, C.c_int, C.POINTER(KrylovResult), vp]),
+        "nosh_gmres": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, dbl, C.c_int, C.c_int, C.POINTER(KrylovResult), vp]),
         "nosh_ctx_set_preconditioner": (C.c_int, [vp, C.c_int]),
         "nosh_newton": (C.c_int, [vp, C.c_int, cpp, vp, vp, dbl, C.c_int, dbl, C.c_int,
                                   C.POINTER(NewtonResult), vp, vp]),
@@ -139,6 +155,8 @@ def lib():
         "nosh_gibbs_energy": (C.c_int, [vp, vp, C.POINTER(dbl)]),
         "nosh_continuation": (C.c_int, [vp, C.c_int, cpp, vp, C.c_char_p, dbl, C.c_int, vp, dbl, C.c_int, dbl,
                                         C.c_int, vp]),
+        "nosh_continuation_arclength": (C.c_int, [vp, C.c_int, cpp, vp, C.c_char_p, C.POINTER(ArclengthOptions), vp,
+                                                  vp, C.POINTER(C.c_int32)]),
         "nosh_scratch_vector": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
         "nosh_launch_count": (i64, [vp]),
         "nosh_timer_start": (C.c_int, [vp]),

@@ -17,7 +17,7 @@ import numpy as np
 from . import _lib
 from ._lib import (AMG_REUSE_FULL, AMG_REUSE_NONE, LAYOUT_CSR, LAYOUT_SELL32, MAT_DKEO, MAT_KEO,  # noqa: F401
                    NO_TRANS, OP_JACOBIAN, OP_KEO, OP_KEOREG, PREC_KEOREG_AMG, PREC_NONE, AmgInfo,
-                   ContinuationStep, KrylovResult, MeshInfo, NewtonResult)
+                   ArclengthOptions, ArclengthStep, ContinuationStep, KrylovResult, MeshInfo, NewtonResult)
 
 
 class NoshError(RuntimeError):
@@ -372,6 +372,17 @@ class Context:
     def cg(self, b, x=None, op=OP_JACOBIAN, tol=1e-10, maxit=1000, history=False, prec=PREC_NONE):
         return self._krylov(self.L.nosh_cg, self.L.nosh_cg_prec, op, prec, b, x, tol, maxit, history)
 
+    def gmres(self, b, x=None, op=OP_JACOBIAN, tol=1e-10, maxit=1000, restart=300, history=False,
+              prec=PREC_NONE):
+        x = self._out_like(b) if x is None else x
+        res = KrylovResult()
+        hist = np.full(maxit + 1, np.nan) if history else None
+        self._ck(self.L.nosh_gmres(self.h, op, int(prec), _ptr(b), _ptr(x), float(tol), int(maxit), int(restart),
+                                   C.byref(res), _ptr(hist)))
+        if history:
+            return x, res, hist[:res.iterations + 1]
+        return x, res
+
     def newton(self, params, psi, nl_tol=1e-8, nl_maxit=20, lin_tol=1e-10, lin_maxit=1000):
         """psi is updated in place.  Returns (result, lin_iters, fnorms)."""
         n, names, vals = _params(params)
@@ -402,6 +413,21 @@ class Context:
                                           int(nsteps), _ptr(psi), float(nl_tol), int(nl_maxit),
                                           float(lin_tol), int(lin_maxit), steps))
         return [s for s in steps if s.step >= 0]
+
+    def continuation_arclength(self, params, pname, psi, initial_step_size=1e-3, min_step_size=1e-7,
+                               max_step_size=1e-2, aggressiveness=2.0, max_steps=10, nl_tol=1e-8, nl_maxit=20,
+                               lin_tol=1e-10, lin_maxit=1000, min_value=-100.0, max_value=100.0):
+        """Pseudo-arclength continuation (defaults: the LOCA settings of examples/conf.xml:35-75); psi is
+        updated in place.  Returns the step records."""
+        n, names, vals = _params(params)
+        opt = ArclengthOptions(float(initial_step_size), float(min_step_size), float(max_step_size),
+                               float(aggressiveness), int(max_steps), int(nl_maxit), float(nl_tol),
+                               float(lin_tol), int(lin_maxit), 0, float(min_value), float(max_value))
+        steps = (ArclengthStep * (max_steps + 1))()
+        nrec = C.c_int32(0)
+        self._ck(self.L.nosh_continuation_arclength(self.h, n, names, _ptr(vals), pname.encode(), C.byref(opt),
+                                                    _ptr(psi), steps, C.byref(nrec)))
+        return [steps[i] for i in range(nrec.value)]
 
     @staticmethod
     def write_continuation_csv(path, steps, pname):

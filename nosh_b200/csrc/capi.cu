@@ -707,6 +707,18 @@ nosh_status nosh_cg_prec(nosh_ctx *ctx, nosh_operator_id op, nosh_precond prec, 
   return krylov_entry(ctx, false, op, (int)prec, b, x, tol, maxit, res, hist);
 }
 
+nosh_status nosh_gmres(nosh_ctx *ctx, nosh_operator_id op, nosh_precond prec, const double *b, double *x, double tol,
+                       int maxit, int restart, nosh_krylov_result *res, double *hist) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  ensure_work(ctx);
+  const double2 *bd = stage_in(ctx, b, ctx->stage_x, false);
+  OutVec o = stage_out(ctx, x, ctx->stage_y);
+  gmres_dev(ctx, op, (int)prec, bd, 1.0, o.dev, tol, maxit, restart, res, hist);
+  finish_out(ctx, o);
+  API_END(ctx)
+}
+
 nosh_status nosh_newton(nosh_ctx *ctx, int np, const char *const *names, const double *values, double *psi,
                         double nl_tol, int nl_maxit, double lin_tol, int lin_maxit, nosh_newton_result *res,
                         int32_t *lin_iters, double *fnorms) {
@@ -760,6 +772,26 @@ nosh_status nosh_continuation(nosh_ctx *ctx, int np, const char *const *names, c
   CUDA_CHECK(cudaMemcpyAsync(x, psi, sizeof(double2) * ctx->No, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                              ctx->stream));
   continuation_dev(ctx, np, names, values, pname, dp, nsteps, x, nl_tol, nl_maxit, lin_tol, lin_maxit, steps);
+  CUDA_CHECK(cudaMemcpyAsync(psi, x, sizeof(double2) * ctx->No, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                             ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+nosh_status nosh_continuation_arclength(nosh_ctx *ctx, int np, const char *const *names, const double *values,
+                                        const char *pname, const nosh_arclength_options *opt, double *psi,
+                                        nosh_arclength_step *steps, int32_t *n_records) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  ensure_work(ctx);
+  if (!psi || !pname || !opt) NOSH_THROW(NOSH_EINVAL, "NULL argument");
+  const bool dev = is_device_ptr(psi);
+  double2 *x = ctx->work[8].p;
+  CUDA_CHECK(cudaMemcpyAsync(x, psi, sizeof(double2) * ctx->No, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                             ctx->stream));
+  int n = 0;
+  arclength_dev(ctx, np, names, values, pname, opt, x, steps, &n);
+  if (n_records) *n_records = n;
   CUDA_CHECK(cudaMemcpyAsync(psi, x, sizeof(double2) * ctx->No, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                              ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

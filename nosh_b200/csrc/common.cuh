@@ -209,6 +209,7 @@ struct Ctx {
   DBuf<double2> work[14];
   DBuf<double2> scratch[8];
   DBuf<double2> stage_x, stage_y;   // host staging
+  DBuf<double2> gmres_basis;        // (restart+1) x Nl Arnoldi vectors, allocated by the first nosh_gmres
   // ---- reductions ----
   DBuf<double> partials;            // 2 x n_chunks
   DBuf<double> group_sums;          // 2 x MAX_GROUPS (global group index)

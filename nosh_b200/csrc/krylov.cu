@@ -231,6 +231,14 @@ __global__ void k_axpy(double a, const double2 *x, double2 *y, int64_t n) {
     y[i] = yy;
   }
 }
+// z = a x + b y   (z may alias x or y)
+__global__ void k_lincomb(double a, const double2 *x, double b, const double2 *y, double2 *z, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double2 xx = x[i], yy = y[i];
+    z[i] = make_double2(a * xx.x + b * yy.x, a * xx.y + b * yy.y);
+  }
+}
 // jacobian_operator::rebuild_diags_ (src/jacobian_operator.cpp:184-197)
 __global__ void k_jac_diags(double g, const double *cv, const double *thick, const double *V,
                             const double2 *psi, int64_t No, double2 *d0, double *d1) {
@@ -771,6 +779,160 @@ void continuation_dev(Ctx *ctx, int np, const char *const *names, const double *
       break;
     }
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Pseudo-arclength continuation: the LOCA configuration of the reference's nosh-cont
+// (examples/conf.xml:35-75: "Continuation Method" = "Arc Length", "Predictor" = "Tangent", "Step Size"
+// "Method" = "Adaptive", aggressiveness 2).  LOCA is not in the reference tree: what is restated
+// (oracle/continuation.py) is the textbook bordering form it implements:
+//   unknowns (x, p), constraint  g = <xdot, x - x0>/len + pdot (p - p0) - ds = 0   (LOCA's scaled dot
+//   product: Euclidean / vector length, parameter scaling theta = 1)
+//   Newton on the bordered system by two solves with the same Jacobian:  J a = -F,  J b = -dF/dp,
+//   dp = -(g + <xdot,a>/len) / (pdot + <xdot,b>/len),  x += a + dp b,  p += dp
+//   tangent after every accepted step:  J t = -dF/dp,  (xdot, pdot) = +-(t, 1)/sqrt(<t,t>/len + 1), sign
+//   such that the direction is kept
+//   step size: ds *= 1 + aggr ((nl_maxit - its)/(nl_maxit - 1))^2 after success, ds /= 2 after failure.
+// ---------------------------------------------------------------------------------------------------------
+void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *values, const char *pname,
+                   const nosh_arclength_options *opt, double2 *psi, nosh_arclength_step *out, int *nsteps_out) {
+  ensure_work(ctx);
+  int ip = -1;
+  for (int i = 0; i < np; i++)
+    if (names[i] && strcmp(names[i], pname) == 0) ip = i;
+  if (ip < 0) NOSH_THROW(NOSH_EKEY, "continuation parameter \"%s\" missing", pname);
+  if (!(opt->initial_step_size != 0.0) || !(opt->min_step_size > 0.0) || !(opt->max_step_size >= opt->min_step_size) ||
+      opt->max_steps < 0 || opt->nl_maxit < 2)
+    NOSH_THROW(NOSH_EINVAL, "bad arc-length options");
+  std::vector<double> vals(values, values + np);
+  const int64_t No = ctx->No, Nl = ctx->Nl > 0 ? ctx->Nl : 1;
+  const double len = 2.0 * (double)ctx->n_global;  // Tpetra vector length of the complex_map
+  const double volume = weighted_sum_dev(ctx, 0, nullptr, nullptr);
+  DBuf<double2> X0, XD, Av, Bv, Fp, Dx;
+  for (DBuf<double2> *v : {&X0, &XD, &Av, &Bv, &Fp, &Dx}) {
+    v->alloc(Nl);
+    CUDA_CHECK(cudaMemsetAsync(v->p, 0, sizeof(double2) * Nl, ctx->stream));
+  }
+  double2 *F = ctx->work[6].p;
+  const unsigned g1 = (unsigned)cdiv(No > 0 ? No : 1, 256);
+  auto lincomb = [&](double a, const double2 *x, double b, const double2 *y, double2 *z) {
+    if (No) KLAUNCH(ctx, k_lincomb, g1, 256, a, x, b, y, z, No);
+  };
+  auto prepare = [&](const double2 *x) {  // K(p), V(p), Jacobian (+ preconditioner) diagonals at x
+    const double g = param_at(np, names, vals.data(), "g");
+    keo_fill(ctx, np, names, vals.data(), false);
+    update_potential(ctx, np, names, vals.data());
+    jac_diags_dev(ctx, g, x);
+    if (ctx->precond != NOSH_PREC_NONE) keoreg_diags_dev(ctx, g, x);
+    return g;
+  };
+  auto record = [&](int k, int conv, int nsteps, int lin, int pred, double fn, double ds, double pdot) {
+    nosh_arclength_step st;
+    memset(&st, 0, sizeof(st));
+    st.step = k;
+    st.converged = conv;
+    st.newton_steps = nsteps;
+    st.linear_iterations = lin;
+    st.predictor_linear_iterations = pred;
+    st.param = vals[ip];
+    st.fnorm = fn;
+    st.step_size = ds;
+    st.dparam_ds = pdot;
+    st.gibbs_energy = weighted_sum_dev(ctx, 2, psi, psi) / volume;
+    st.norm = sqrt(weighted_sum_dev(ctx, 1, psi, psi) / volume);
+    if (out) out[k] = st;
+  };
+  // tangent at (psi, p): J t = -dF/dp; returns MINRES iterations, writes (XD, pdot) with the sign that
+  // keeps <(XD,pdot)_new, (XD,pdot)_old> > 0 (first call: pdot has the sign of ds)
+  auto tangent = [&](double &pdot, bool first, double sign0) {
+    prepare(psi);
+    compute_dfdp_dev(ctx, np, names, vals.data(), pname, psi, Fp.p);
+    nosh_krylov_result kr;
+    minres_dev(ctx, NOSH_OP_JACOBIAN, ctx->precond, Fp.p, -1.0, Bv.p, opt->lin_tol, opt->lin_maxit, &kr, nullptr);
+    const double tt = dot_dev(ctx, Bv.p, Bv.p) / len;
+    double pd = 1.0 / sqrt(tt + 1.0);
+    if (first) {
+      if (sign0 < 0.0) pd = -pd;
+    } else {
+      const double along = dot_dev(ctx, Bv.p, XD.p) / len * pd + pd * pdot;
+      if (along < 0.0) pd = -pd;
+    }
+    lincomb(pd, Bv.p, 0.0, Bv.p, XD.p);
+    pdot = pd;
+    return kr.iterations;
+  };
+
+  int done = 0;
+  // step 0: solution at the initial parameter value
+  nosh_newton_result nr;
+  newton_dev(ctx, np, names, vals.data(), psi, opt->nl_tol, opt->nl_maxit, opt->lin_tol, opt->lin_maxit, &nr, nullptr,
+             nullptr);
+  record(0, nr.converged, nr.steps, nr.total_linear_iterations, 0, nr.fnorm, 0.0, 0.0);
+  done = 1;
+  if (nr.converged && opt->max_steps > 0) {
+    double ds = opt->initial_step_size, pdot = 0.0;
+    int pred_its = tangent(pdot, true, ds);
+    ds = fabs(ds);
+    double p0 = vals[ip];
+    if (No) CUDA_CHECK(cudaMemcpyAsync(X0.p, psi, sizeof(double2) * No, cudaMemcpyDeviceToDevice, ctx->stream));
+    for (int k = 1; k <= opt->max_steps;) {
+      // predictor
+      lincomb(1.0, X0.p, ds, XD.p, psi);
+      vals[ip] = p0 + ds * pdot;
+      // corrector: Newton on the bordered system
+      int its = 0, lin = 0;
+      double nrm = 0.0;
+      bool ok = false;
+      for (;;) {
+        const double g = prepare(psi);
+        compute_f_dev(ctx, g, psi, F);
+        lincomb(1.0, psi, -1.0, X0.p, Dx.p);
+        const double gc = dot_dev(ctx, XD.p, Dx.p) / len + pdot * (vals[ip] - p0) - ds;
+        nrm = sqrt(dot_dev(ctx, F, F) + gc * gc);
+        if (nrm < opt->nl_tol) {
+          ok = true;
+          break;
+        }
+        if (its >= opt->nl_maxit || !(nrm == nrm)) break;
+        compute_dfdp_dev(ctx, np, names, vals.data(), pname, psi, Fp.p);
+        nosh_krylov_result ka, kb;
+        minres_dev(ctx, NOSH_OP_JACOBIAN, ctx->precond, F, -1.0, Av.p, opt->lin_tol, opt->lin_maxit, &ka, nullptr);
+        minres_dev(ctx, NOSH_OP_JACOBIAN, ctx->precond, Fp.p, -1.0, Bv.p, opt->lin_tol, opt->lin_maxit, &kb, nullptr);
+        lin += ka.iterations + kb.iterations;
+        const double xa = dot_dev(ctx, XD.p, Av.p) / len, xb = dot_dev(ctx, XD.p, Bv.p) / len;
+        const double dp = -(gc + xa) / (pdot + xb);
+        axpy_dev(ctx, 1.0, Av.p, psi);
+        axpy_dev(ctx, dp, Bv.p, psi);
+        vals[ip] += dp;
+        its++;
+      }
+      if (!ok) {
+        // failed step: halve and retry from the last solution (LOCA: "Failed Step Reduction Factor" 0.5)
+        ds *= 0.5;
+        if (ds < opt->min_step_size) {
+          if (No) CUDA_CHECK(cudaMemcpyAsync(psi, X0.p, sizeof(double2) * No, cudaMemcpyDeviceToDevice, ctx->stream));
+          vals[ip] = p0;
+          break;
+        }
+        continue;
+      }
+      // accepted
+      const double ds_used = ds;
+      p0 = vals[ip];
+      if (No) CUDA_CHECK(cudaMemcpyAsync(X0.p, psi, sizeof(double2) * No, cudaMemcpyDeviceToDevice, ctx->stream));
+      const int pred_prev = pred_its;
+      pred_its = tangent(pdot, false, 0.0);
+      record(k, 1, its, lin, pred_prev, nrm, ds_used, pdot);
+      done = k + 1;
+      const double fac = (double)(opt->nl_maxit - its) / (double)(opt->nl_maxit - 1);
+      ds *= 1.0 + opt->aggressiveness * fac * fac;
+      if (ds > opt->max_step_size) ds = opt->max_step_size;
+      if (vals[ip] > opt->max_value || vals[ip] < opt->min_value) break;
+      k++;
+    }
+  }
+  if (nsteps_out) *nsteps_out = done;
 }
 
 }  // namespace nosh

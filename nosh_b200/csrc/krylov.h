@@ -22,4 +22,8 @@ void compute_dfdp_dev(Ctx *ctx, int np, const char *const *names, const double *
 void continuation_dev(Ctx *ctx, int np, const char *const *names, const double *values, const char *pname,
                       double dp, int nsteps, double2 *psi, double nl_tol, int nl_maxit, double lin_tol,
                       int lin_maxit, nosh_continuation_step *out);
+void gmres_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, double2 *x_out, double tol, int maxit,
+               int restart, nosh_krylov_result *res, double *hist_host);
+void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *values, const char *pname,
+                   const nosh_arclength_options *opt, double2 *psi, nosh_arclength_step *out, int *nsteps_out);
 }  // namespace nosh

@@ -6,3 +6,5 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 """
 from .oracle import OracleProblem, build_library, lib, num_threads  # noqa: F401
 from . import meshgen  # noqa: F401
+from . import continuation  # noqa: F401
+from . import gmres  # noqa: F401

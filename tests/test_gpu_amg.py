@@ -247,3 +247,28 @@ def test_reuse_none_rebuilds(nb, orc):
     H2 = amg.Hierarchy(sp.csr_matrix((P.keoreg_fill(params["mu"], params["g"], x2), P.cols, P.rowptr),
                                      shape=Pm.shape), coarse_max=40, degree=1)
     assert relerr(y_none, H2.vcycle(b)) <= TOL
+
+
+@pytest.mark.parametrize("restart,prec", [(300, False), (20, False), (40, True)])
+def test_gmres_iteration_counts(nb, orc, restart, prec):
+    """Restarted GMRES (the solver examples/conf.xml:104 selects) against oracle/gmres.py: identical
+    iteration counts and residual histories, plain, restarted and right-preconditioned with the V-cycle."""
+    from oracle import gmres as og
+    ctx, P, Pm, H, x, params = setup_pair(nb, orc, n=12, state="random", coarse_max=64)
+    J = oracle_jacobian(P)
+    b = -P.compute_f(params["g"], x)
+    M = H.vcycle if prec else None
+    xr, itr, rr, hist_r = og.gmres(lambda t: J @ t, M, b, 1e-10, 1000, restart=restart)
+    xg, res, hist_g = ctx.gmres(b, tol=1e-10, maxit=1000, restart=restart, history=True,
+                                prec=nb.PREC_KEOREG_AMG if prec else nb.PREC_NONE)
+    assert res.converged == 1 and res.iterations == itr
+    assert np.allclose(hist_g, hist_r, rtol=1e-5, atol=1e-16)
+    assert relerr(xg, xr) <= 1e-8
+    assert np.linalg.norm(J @ xg - b) <= 2e-10 * np.linalg.norm(b)
+    if not prec and restart == 300:
+        # symmetric operator: full GMRES and MINRES minimise the same residual norm
+        _, rm, hist_m = ctx.minres(b, tol=1e-10, maxit=1000, history=True)
+        assert res.iterations <= rm.iterations <= res.iterations + 10   # MINRES loses orthogonality late
+        assert np.allclose(hist_m[:60], hist_g[:60], rtol=1e-5, atol=0)
+    with pytest.raises(ValueError):
+        ctx.gmres(b, restart=0)

@@ -445,3 +445,34 @@ def test_medium_mesh_parity(nb, orc):
     cv = ctx.control_volumes()
     assert cv.sum() == pytest.approx(1000.0, rel=1e-12) and cv.min() > 0
     ctx.close()
+
+
+def test_arclength_continuation(nb, orc):
+    """Pseudo-arclength continuation (LOCA "Arc Length" + tangent predictor + adaptive step size, the
+    settings of examples/conf.xml:35-75) against the restatement in oracle/continuation.py: same step
+    records, through a turning point of the branch (dparam_ds changes sign)."""
+    coords, cells = orc.meshgen.tetgrid(9)
+    ctx, P, psi = make_pair(nb, orc, coords, cells, 1, group=512)
+    kw = dict(initial_step_size=0.05, min_step_size=1e-7, max_step_size=0.1, aggressiveness=2.0, max_steps=6)
+    xo, recs = orc.continuation.arclength(P, 1.0, 0.0, psi, kw["initial_step_size"], kw["min_step_size"],
+                                          kw["max_step_size"], kw["aggressiveness"], kw["max_steps"])
+    xg = psi.copy()
+    steps = ctx.continuation_arclength({"g": 1.0, "mu": 0.0}, "mu", xg, **kw)
+    assert len(steps) == len(recs) == 7
+    for s, r in zip(steps, recs):
+        assert s.step == r["step"] and s.converged == 1
+        assert s.param == pytest.approx(r["param"], rel=1e-7, abs=1e-12)
+        assert s.newton_steps == r["newton_steps"]
+        assert s.step_size == pytest.approx(r["step_size"], rel=1e-12)
+        assert s.dparam_ds == pytest.approx(r["dparam_ds"], rel=1e-6, abs=1e-9)
+        assert s.gibbs_energy == pytest.approx(r["gibbs_energy"], rel=1e-7)
+        assert s.norm == pytest.approx(r["norm"], rel=1e-7)
+        # rounding-dominated last corrector solves: band (see test_continuation_and_energy)
+        assert abs(s.linear_iterations - r["linear_iterations"]) <= 0.25 * max(1, r["linear_iterations"])
+    assert min(r["dparam_ds"] for r in recs[1:]) < 0 < max(r["dparam_ds"] for r in recs[1:])   # turning point passed
+    assert relerr(xg, xo) <= 1e-5
+    with pytest.raises(KeyError):
+        ctx.continuation_arclength({"g": 1.0, "mu": 0.0}, "nu", xg, **kw)
+    with pytest.raises(ValueError):
+        ctx.continuation_arclength({"g": 1.0, "mu": 0.0}, "mu", xg, initial_step_size=0.0)
+    ctx.close()

@@ -70,3 +70,22 @@ def test_pcg_on_the_regularised_keo():
     x1, it1, rr, _ = amg.pcg(lambda t: Pm @ t, H.vcycle, b, 1e-10, 500)
     assert rr <= 1e-10 and it1 < 40
     assert np.linalg.norm(Pm @ x1 - b) <= 1e-9 * np.linalg.norm(b)
+
+
+def test_gmres_restatement():
+    """oracle/gmres.py: on a symmetric matrix full GMRES and MINRES minimise the same residual, so their
+    residual histories agree; restarted and right-preconditioned variants converge to the same solution."""
+    from oracle import gmres as og
+    P, J, Pm, x = regularised_problem(8, state="random")
+    b = -P.compute_f(1.0, x)
+    xm, itm, _, hm = amg.pminres(lambda t: J @ t, lambda r: r.copy(), b, 1e-10, 2000)
+    xg, itg, rr, hg = og.gmres(lambda t: J @ t, None, b, 1e-10, 2000, restart=2000)
+    # (MINRES' short recurrences lose orthogonality late in the run: a few more iterations at the end)
+    assert itg <= itm <= itg + 10
+    assert np.allclose(hg[:60], hm[:60], rtol=1e-6, atol=0)
+    assert np.abs(xg - xm).max() <= 1e-8 * np.abs(xm).max()
+    xr, itr, rr, _ = og.gmres(lambda t: J @ t, None, b, 1e-10, 5000, restart=25)
+    assert itr > itg and np.linalg.norm(J @ xr - b) <= 1.0001e-10 * np.linalg.norm(b) * 10
+    H = amg.Hierarchy(Pm, coarse_max=64, degree=1)
+    xp, itp, rr, _ = og.gmres(lambda t: J @ t, H.vcycle, b, 1e-10, 500, restart=50)
+    assert itp < itg / 2 and np.linalg.norm(J @ xp - b) <= 1.0001e-10 * np.linalg.norm(b)
