@@ -383,6 +383,36 @@ NOSH_API nosh_status nosh_continuation_arclength(nosh_ctx *ctx, int np, const ch
                                                  const nosh_arclength_options *opt, double *psi,
                                                  nosh_arclength_step *steps, int32_t *n_records);
 
+/* ---- mesh files and vertex ordering ("next" row f3; host-only, no GPU needed) -------------------
+ * nosh::read (src/mesh_reader.cpp:19-162) + the vertex tags the drivers take from the file --
+ * mesh::get_complex_vector("psi"), get_vector("V"), get_multi_vector("A") (src/mesh.cpp:249-446) -- and
+ * mesh::write for the outNNNN state dumps (src/mesh.cpp:249-263, src/continuation_data_saver.hpp:24-50).
+ * The reference goes through MOAB (.h5m / Exodus); MOAB, HDF5 and netCDF are not available here, so the
+ * supported format is the legacy VTK unstructured grid, ASCII or BINARY (what `meshio-convert in.e out.vtk`
+ * writes; MOAB reads it too).  Triangles / tetrahedra only, the highest-dimensional kind present.
+ * .h5m / .e / .exo paths return NOSH_EUNSUPPORTED.  Errors: nosh_meshfile_last_error(). */
+typedef struct nosh_meshfile nosh_meshfile;
+NOSH_API const char *nosh_meshfile_last_error(void);
+NOSH_API nosh_status nosh_meshfile_read(const char *path, nosh_meshfile **out);
+NOSH_API void nosh_meshfile_free(nosh_meshfile *m);
+NOSH_API nosh_status nosh_meshfile_info(const nosh_meshfile *m, int32_t *dim, int64_t *n_vertices,
+                                        int64_t *n_cells, int32_t *n_fields);
+NOSH_API nosh_status nosh_meshfile_get(const nosh_meshfile *m, double *coords /* n x 3 */,
+                                       int32_t *cells /* n_cells x (dim+1) */);
+NOSH_API nosh_status nosh_meshfile_field_name(const nosh_meshfile *m, int32_t index, const char **name,
+                                              int32_t *ncomp);
+/* vertex tag by name (NOSH_EKEY if absent); values may be NULL to query ncomp */
+NOSH_API nosh_status nosh_meshfile_get_field(const nosh_meshfile *m, const char *name, int32_t *ncomp,
+                                             double *values /* n x ncomp */);
+NOSH_API nosh_status nosh_meshfile_write(const char *path, int32_t dim, int64_t n_vertices,
+                                         const double *coords, int64_t n_cells, const int32_t *cells,
+                                         int32_t n_fields, const char *const *names, const int32_t *ncomps,
+                                         const double *const *values, int32_t binary);
+/* Spatially local vertex numbering for the contiguous-range partition (the stand-in for the `mbpart`
+ * step of test/data/CMakeLists.txt:36-52): perm[i] = old id of the vertex that gets new id i along a
+ * Morton curve through the bounding box. */
+NOSH_API nosh_status nosh_morton_order(int64_t n_vertices, const double *coords /* n x 3 */, int64_t *perm);
+
 /* ---- measurement helpers: device-resident scratch vectors so that benchmarks can
  * time kernels with inputs already in HBM.  slot in [0,8). Returns a device pointer to
  * 2*(n_owned+n_ghost) doubles owned by the ctx. */

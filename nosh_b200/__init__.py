@@ -5,7 +5,8 @@ The product is the C-ABI shared library ``libnosh_b200.so`` (include/nosh_b200.h
 ``nosh_b200/hostcpp`` the C++ mirror of the reference's classes.  No CPU fallback exists.
 """
 from . import _lib  # noqa: F401
-from .api import Context, NoshError, partition_range  # noqa: F401
+from .api import (Context, NoshError, morton_order, partition_range, read_mesh, renumber,  # noqa: F401
+                  write_mesh)
 from ._lib import (LAYOUT_CSR, LAYOUT_SELL32, MAT_DKEO, MAT_KEO, NO_TRANS, TRANS, CONJ_TRANS,  # noqa: F401
                    OP_JACOBIAN, OP_KEO, OP_KEOREG, PREC_NONE, PREC_KEOREG_AMG, AMG_REUSE_NONE, AMG_REUSE_FULL,
                    build)

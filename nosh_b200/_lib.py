@@ -157,6 +157,15 @@ def lib():
                                         C.c_int, vp]),
         "nosh_continuation_arclength": (C.c_int, [vp, C.c_int, cpp, vp, C.c_char_p, C.POINTER(ArclengthOptions), vp,
                                                   vp, C.POINTER(C.c_int32)]),
+        "nosh_meshfile_last_error": (C.c_char_p, []),
+        "nosh_meshfile_read": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+        "nosh_meshfile_free": (None, [vp]),
+        "nosh_meshfile_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
+        "nosh_meshfile_get": (C.c_int, [vp, vp, vp]),
+        "nosh_meshfile_field_name": (C.c_int, [vp, i32, C.POINTER(C.c_char_p), C.POINTER(i32)]),
+        "nosh_meshfile_get_field": (C.c_int, [vp, C.c_char_p, C.POINTER(i32), vp]),
+        "nosh_meshfile_write": (C.c_int, [C.c_char_p, i32, i64, vp, i64, vp, i32, cpp, vp, vp, i32]),
+        "nosh_morton_order": (C.c_int, [i64, vp, vp]),
         "nosh_scratch_vector": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
         "nosh_launch_count": (i64, [vp]),
         "nosh_timer_start": (C.c_int, [vp]),

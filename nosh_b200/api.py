@@ -52,6 +52,72 @@ def partition_range(n_global, nranks, rank, group_vertices=65536):
     return b.value, e.value, g.value
 
 
+def _io_check(rc):
+    if rc == 0:
+        return
+    msg = (_lib.lib().nosh_meshfile_last_error() or b"").decode()
+    if rc == _lib.NOSH_EKEY:
+        raise KeyError(msg)
+    if rc == _lib.NOSH_EINVAL:
+        raise ValueError(msg)
+    raise NoshError("status %d: %s" % (rc, msg))
+
+
+def read_mesh(path):
+    """nosh::read + the vertex tags (host only): returns (coords (N,3), cells (C,dim+1) int32, fields dict).
+    Legacy VTK unstructured grids, ASCII or BINARY; complex states come back as (N,2) arrays."""
+    L = _lib.lib()
+    h = C.c_void_p()
+    _io_check(L.nosh_meshfile_read(str(path).encode(), C.byref(h)))
+    try:
+        dim, nv, nc, nf = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int32()
+        _io_check(L.nosh_meshfile_info(h, C.byref(dim), C.byref(nv), C.byref(nc), C.byref(nf)))
+        coords = np.empty((nv.value, 3))
+        cells = np.empty((nc.value, dim.value + 1), np.int32)
+        _io_check(L.nosh_meshfile_get(h, _ptr(coords), _ptr(cells)))
+        fields = {}
+        for i in range(nf.value):
+            name, ncomp = C.c_char_p(), C.c_int32()
+            _io_check(L.nosh_meshfile_field_name(h, i, C.byref(name), C.byref(ncomp)))
+            v = np.empty((nv.value, ncomp.value))
+            _io_check(L.nosh_meshfile_get_field(h, name.value, None, _ptr(v)))
+            fields[name.value.decode()] = v[:, 0].copy() if ncomp.value == 1 else v
+        return coords, cells, fields
+    finally:
+        L.nosh_meshfile_free(h)
+
+
+def write_mesh(path, coords, cells, fields=None, binary=False):
+    """mesh::write (the outNNNN dumps): legacy VTK with the given vertex tags.  A state vector in the
+    interleaved (re,im) layout is passed as psi.reshape(-1, 2)."""
+    coords = np.ascontiguousarray(coords, np.float64)
+    cells = np.ascontiguousarray(cells, np.int32)
+    fields = fields or {}
+    names = (C.c_char_p * max(1, len(fields)))(*[k.encode() for k in fields])
+    arrs = [np.ascontiguousarray(np.asarray(v, np.float64).reshape(coords.shape[0], -1)) for v in fields.values()]
+    ncomps = np.array([a.shape[1] for a in arrs] or [0], np.int32)
+    ptrs = (C.c_void_p * max(1, len(arrs)))(*[a.ctypes.data for a in arrs])
+    _io_check(_lib.lib().nosh_meshfile_write(str(path).encode(), cells.shape[1] - 1, coords.shape[0], _ptr(coords),
+                                             cells.shape[0], _ptr(cells), len(arrs), names, _ptr(ncomps), ptrs,
+                                             1 if binary else 0))
+
+
+def morton_order(coords):
+    """perm with perm[i] = old id of the vertex that gets new id i (spatially local numbering)."""
+    coords = np.ascontiguousarray(coords, np.float64)
+    perm = np.empty(coords.shape[0], np.int64)
+    _io_check(_lib.lib().nosh_morton_order(coords.shape[0], _ptr(coords), _ptr(perm)))
+    return perm
+
+
+def renumber(coords, cells, perm, fields=None):
+    """apply a vertex permutation (new <- old = perm) to a mesh and its vertex fields"""
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    out_fields = {k: np.asarray(v)[perm] for k, v in (fields or {}).items()}
+    return coords[perm], inv[cells].astype(np.int32), out_fields
+
+
 class Context:
     """One nosh_ctx: one process, one GPU."""
 
