@@ -46,8 +46,43 @@ inline dim3 grid_for(int64_t n, int tpb = 256) { return dim3((unsigned)cdiv(n > 
     CUDA_CHECK(cudaGetLastError());                              \
   } while (0)
 
+// Set-up temporaries come from the device's stream-ordered memory pool: the expand-sort-compress products
+// allocate and free tens of GB in many pieces, and cudaMalloc / cudaFree map and unmap every one of them
+// (measured: the same set-up took 0.4 ... 7.6 s depending on the allocator's mood).  With the pool's
+// release threshold raised for the duration of the set-up, freed blocks are reused without unmapping;
+// the pool is trimmed again when the hierarchy is complete.  Persistent level data stays in cudaMalloc'ed
+// DBufs.
+thread_local cudaStream_t g_tstream = nullptr;
+template <typename T>
+struct TBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  TBuf() = default;
+  TBuf(const TBuf &) = delete;
+  TBuf &operator=(const TBuf &) = delete;
+  ~TBuf() { release(); }
+  void release() {
+    if (p) cudaFreeAsync(p, g_tstream);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    release();
+    if (count == 0) count = 1;
+    CUDA_CHECK(cudaMallocAsync(&p, count * sizeof(T), g_tstream));
+    n = count;
+  }
+  void ensure(size_t count) {
+    if (count > n) alloc(count);
+  }
+  void swap(TBuf &o) {
+    std::swap(p, o.p);
+    std::swap(n, o.n);
+  }
+};
+
 struct Temp {
-  DBuf<char> buf;
+  TBuf<char> buf;
   void *get(size_t bytes) {
     buf.ensure(bytes);
     return buf.p;
@@ -66,11 +101,11 @@ void check_count(int64_t n, const char *what) {
   if (n >= (int64_t)2147483647) NOSH_THROW(NOSH_EINVAL, "AMG set-up: %s needs %lld items (>= 2^31)", what, (long long)n);
 }
 
-void sort_pairs_u64(Ctx *ctx, Temp &tmp, DBuf<uint64_t> &keys, DBuf<uint32_t> &vals, int64_t n) {
+void sort_pairs_u64(Ctx *ctx, Temp &tmp, TBuf<uint64_t> &keys, TBuf<uint32_t> &vals, int64_t n) {
   check_count(n, "sort");
   if (n == 0) return;
-  DBuf<uint64_t> k2;
-  DBuf<uint32_t> v2;
+  TBuf<uint64_t> k2;
+  TBuf<uint32_t> v2;
   k2.alloc(n);
   v2.alloc(n);
   cub::DoubleBuffer<uint64_t> dk(keys.p, k2.p);
@@ -388,16 +423,16 @@ struct CsrOut {
 
 // expand (already counted) -> sort -> compress
 template <typename ExpandFn>
-void esc_finish(Ctx *ctx, Temp &tmp, DBuf<int64_t> &cnt, int64_t nrows_in, int64_t nrows_out, ExpandFn expand,
+void esc_finish(Ctx *ctx, Temp &tmp, TBuf<int64_t> &cnt, int64_t nrows_in, int64_t nrows_out, ExpandFn expand,
                 CsrOut &C) {
-  DBuf<int64_t> off;
+  TBuf<int64_t> off;
   off.alloc(nrows_in + 1);
   exclusive_scan_i64(ctx, tmp, cnt.p, off.p, nrows_in + 1);
   const int64_t total = fetch(ctx, off.p + nrows_in);
   check_count(total, "a sparse product");
-  DBuf<uint64_t> keys;
-  DBuf<uint32_t> idx;
-  DBuf<B22> vals;
+  TBuf<uint64_t> keys;
+  TBuf<uint32_t> idx;
+  TBuf<B22> vals;
   keys.alloc(total);
   idx.alloc(total);
   vals.alloc(total);
@@ -405,14 +440,14 @@ void esc_finish(Ctx *ctx, Temp &tmp, DBuf<int64_t> &cnt, int64_t nrows_in, int64
   off.release();
   cnt.release();
   sort_pairs_u64(ctx, tmp, keys, idx, total);
-  DBuf<int32_t> head, excl;
+  TBuf<int32_t> head, excl;
   head.alloc(total + 1);
   excl.alloc(total + 1);
   ALAUNCH(ctx, k_head_flags, total + 1, keys.p, total, head.p);
   exclusive_scan_i32(ctx, tmp, head.p, excl.p, total + 1);
   const int64_t nuniq = fetch(ctx, excl.p + total);
-  DBuf<uint64_t> ukeys;
-  DBuf<int32_t> start;
+  TBuf<uint64_t> ukeys;
+  TBuf<int32_t> start;
   ukeys.alloc(nuniq);
   start.alloc(nuniq + 1);
   ALAUNCH(ctx, k_unique_starts, total + 1, keys.p, head.p, excl.p, total, nuniq, ukeys.p, start.p);
@@ -427,7 +462,7 @@ void esc_finish(Ctx *ctx, Temp &tmp, DBuf<int64_t> &cnt, int64_t nrows_in, int64
 }
 
 void spgemm(Ctx *ctx, Temp &tmp, const Csr &A, const Csr &B, CsrOut &C) {
-  DBuf<int64_t> cnt;
+  TBuf<int64_t> cnt;
   cnt.alloc(A.n + 1);
   ALAUNCH(ctx, k_mm_count, A.n + 1, A, B, cnt.p);
   esc_finish(ctx, tmp, cnt, A.n, A.n,
@@ -437,7 +472,7 @@ void spgemm(Ctx *ctx, Temp &tmp, const Csr &A, const Csr &B, CsrOut &C) {
              C);
 }
 void spgemm_atb(Ctx *ctx, Temp &tmp, const Csr &A, const Csr &B, int64_t ncols_a, CsrOut &C) {
-  DBuf<int64_t> cnt;
+  TBuf<int64_t> cnt;
   cnt.alloc(A.n + 1);
   ALAUNCH(ctx, k_atb_count, A.n + 1, A, B, cnt.p);
   esc_finish(ctx, tmp, cnt, A.n, ncols_a,
@@ -820,7 +855,7 @@ void alloc_level_vectors(Ctx *ctx, AmgLevel &L, int lev) {
 void build_sell(Ctx *ctx, Temp &tmp, AmgLevel &L) {
   const int64_t ns = cdiv(L.n, 32);
   L.nslices = ns;
-  DBuf<int32_t> w32;
+  TBuf<int32_t> w32;
   w32.alloc(ns + 1);
   ALAUNCH(ctx, k_slice_width, ns + 1, L.rowptr.p, L.n, ns, w32.p);
   L.slice_off.alloc(ns + 1);
@@ -834,8 +869,8 @@ void build_sell(Ctx *ctx, Temp &tmp, AmgLevel &L) {
 // MIS-2 aggregation of the block graph (rowptr, col) of `n` nodes; fills L.agg, returns #aggregates
 int64_t aggregate(Ctx *ctx, Temp &tmp, AmgLevel &L, int lev, const int32_t *rowptr, const int32_t *col) {
   const int64_t n = L.n;
-  DBuf<int32_t> state, counter, flag, rootnum, agg2;
-  DBuf<uint64_t> T0, T1, T2;
+  TBuf<int32_t> state, counter, flag, rootnum, agg2;
+  TBuf<uint64_t> T0, T1, T2;
   state.alloc(n);
   counter.alloc(1);
   T0.alloc(n);
@@ -865,11 +900,15 @@ int64_t aggregate(Ctx *ctx, Temp &tmp, AmgLevel &L, int lev, const int32_t *rowp
 
 // dense SPD inverse on the host (Cholesky); returns false if a pivot is not positive
 bool dense_spd_inverse(std::vector<double> &a, int64_t n) {
+  // a pivot below this is rounding noise of a singular matrix (e.g. the pure Laplacian for g = mu = 0)
+  double amax = 0.0;
+  for (int64_t j = 0; j < n; j++) amax = std::max(amax, std::fabs(a[j * n + j]));
+  const double tiny = 1e-13 * amax * (double)(n > 0 ? n : 1);
   // A = L L^T (lower, in place)
   for (int64_t j = 0; j < n; j++) {
     double d = a[j * n + j];
     for (int64_t k = 0; k < j; k++) d -= a[j * n + k] * a[j * n + k];
-    if (!(d > 0.0)) return false;
+    if (!(d > tiny)) return false;
     d = std::sqrt(d);
     a[j * n + j] = d;
     for (int64_t i = j + 1; i < n; i++) {
@@ -923,7 +962,8 @@ void build_coarse_inverse(Ctx *ctx, Amg &H) {
     for (int64_t j = 0; j < i; j++) a[i * n2 + j] = a[j * n2 + i] = 0.5 * (a[i * n2 + j] + a[j * n2 + i]);
   if (!dense_spd_inverse(a, n2))
     NOSH_THROW(NOSH_ESTATE,
-               "AMG: the regularised KEO is not positive definite on the coarsest level (g <= 0 and mu == 0?)");
+               "AMG: the regularised KEO is not positive definite (to rounding) on the coarsest level "
+               "(g <= 0 and mu == 0?)");
   H.n_coarse2 = n2;
   H.coarse_inv.alloc((size_t)n2 * n2);
   CUDA_CHECK(cudaMemcpyAsync(H.coarse_inv.p, a.data(), sizeof(double) * n2 * n2, cudaMemcpyHostToDevice, ctx->stream));
@@ -949,6 +989,22 @@ void build_hierarchy(Ctx *ctx) {
   amg_free(ctx);
   Amg *H = new Amg();
   ctx->amg = H;
+  // stream-ordered pool for the temporaries (see TBuf): keep freed blocks mapped until the set-up is done
+  g_tstream = ctx->stream;
+  cudaMemPool_t pool = nullptr;
+  CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+  uint64_t keep_all = UINT64_MAX, keep_none = 0;
+  CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
+  struct PoolGuard {
+    cudaMemPool_t pool;
+    cudaStream_t stream;
+    uint64_t *zero;
+    ~PoolGuard() {
+      cudaStreamSynchronize(stream);
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, zero);
+      cudaMemPoolTrimTo(pool, 0);
+    }
+  } pool_guard{pool, ctx->stream, &keep_none};
   Temp tmp;
   DBuf<double> scratch;
   const int64_t No = ctx->No;
@@ -957,7 +1013,7 @@ void build_hierarchy(Ctx *ctx) {
   H->levels.push_back(L);
   L->n = No;
   {
-    DBuf<int32_t> cnt;
+    TBuf<int32_t> cnt;
     cnt.alloc(No + 1);
     ALAUNCH(ctx, k_l0_count, No + 1, ctx->rowptr.p, ctx->csr_col.p, No, cnt.p);
     L->rowptr.alloc(No + 1);
@@ -991,9 +1047,9 @@ void build_hierarchy(Ctx *ctx) {
     DBuf<double> sc;
     sc.alloc(nc);
     {
-      DBuf<uint64_t> mkeys;
-      DBuf<uint32_t> mvals;
-      DBuf<int32_t> mrow;
+      TBuf<uint64_t> mkeys;
+      TBuf<uint32_t> mvals;
+      TBuf<int32_t> mrow;
       mkeys.alloc(n);
       mvals.alloc(n);
       mrow.alloc(nc + 1);
@@ -1040,8 +1096,8 @@ void build_hierarchy(Ctx *ctx) {
     L->p_col.swap(P.col);
     L->p_val.swap(P.val);
     {
-      DBuf<uint64_t> tkeys;
-      DBuf<uint32_t> tvals;
+      TBuf<uint64_t> tkeys;
+      TBuf<uint32_t> tvals;
       tkeys.alloc(L->p_nnz);
       tvals.alloc(L->p_nnz);
       ALAUNCH(ctx, k_transpose_keys, n, n, L->p_rowptr.p, L->p_col.p, tkeys.p, tvals.p);

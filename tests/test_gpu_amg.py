@@ -272,3 +272,58 @@ def test_gmres_iteration_counts(nb, orc, restart, prec):
         assert np.allclose(hist_m[:60], hist_g[:60], rtol=1e-5, atol=0)
     with pytest.raises(ValueError):
         ctx.gmres(b, restart=0)
+
+
+def test_amg_on_a_triangle_mesh_with_varying_thickness(nb, orc):
+    """2D (config 1's family): triangle grid, non-constant thickness, scrambled vertex numbering."""
+    from oracle import amg
+    coords, cells = orc.meshgen.trigrid(41, 31, lo=(-5.0, -3.0), hi=(5.0, 3.0))
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(coords.shape[0])
+    coords, cells, _ = nb.renumber(coords, cells, perm)
+    N = coords.shape[0]
+    thickness = 1.0 + 0.3 * np.sin(coords[:, 0])
+    psi, A = orc.meshgen.plain_gl_fields(coords)
+    x = orc.meshgen.random_state(N, 11)
+    params = {"g": 2.0, "mu": 0.05}
+    ctx = nb.Context()
+    ctx.mesh_set(coords, cells)
+    ctx.set_thickness(thickness, 1.0)
+    ctx.set_potential_constant(-1.0)
+    ctx.set_mvp_explicit(A)
+    ctx.amg_set_options(coarse_max=30, degree=2)
+    ctx.keoreg_rebuild(params, x)
+    P = orc.OracleProblem(coords, cells, ("explicit", A), thickness=thickness)
+    Pm = sp.csr_matrix((P.keoreg_fill(params["mu"], params["g"], x), P.cols, P.rowptr), shape=(2 * N, 2 * N))
+    H = amg.Hierarchy(Pm, coarse_max=30, degree=2)
+    b = rng.standard_normal(2 * N)
+    y = ctx.keoreg_apply(b)
+    assert ctx.amg_info().levels == len(H.levels) >= 3
+    assert relerr(y, H.vcycle(b)) <= TOL
+    xr, itr, _, _ = amg.pcg(lambda t: Pm @ t, H.vcycle, b, 1e-10, 200)
+    xg, res = ctx.cg(b, op=nb.OP_KEOREG, tol=1e-10, maxit=200, prec=nb.PREC_KEOREG_AMG)
+    assert res.iterations == itr and res.converged == 1 and relerr(xg, xr) <= 1e-8
+
+
+def test_singular_preconditioner_matrix_is_reported(nb, orc):
+    """g = 0 and mu = 0: the regularised KEO is the pure (singular) Laplacian -> no Cholesky factor on the
+    coarsest level; the call fails with a status instead of returning garbage."""
+    coords, cells = orc.meshgen.tetgrid(6)
+    psi, A = orc.meshgen.plain_gl_fields(coords)
+    ctx = nb.Context()
+    ctx.mesh_set(coords, cells)
+    ctx.set_thickness(None, 1.0)
+    ctx.set_potential_constant(-1.0)
+    ctx.set_mvp_explicit(A)
+    ctx.keoreg_rebuild({"g": 0.0, "mu": 0.0}, psi)
+    with pytest.raises(RuntimeError, match="positive definite"):
+        ctx.keoreg_apply(np.ones(2 * coords.shape[0]))
+    # CSR layout: the V-cycle is built on the SELL-32 kernels only
+    ctx2 = nb.Context(layout=nb.LAYOUT_CSR)
+    ctx2.mesh_set(coords, cells)
+    ctx2.set_thickness(None, 1.0)
+    ctx2.set_potential_constant(-1.0)
+    ctx2.set_mvp_explicit(A)
+    ctx2.keoreg_rebuild({"g": 1.0, "mu": 0.1}, psi)
+    with pytest.raises(RuntimeError, match="SELL-32"):
+        ctx2.keoreg_apply(np.ones(2 * coords.shape[0]))
