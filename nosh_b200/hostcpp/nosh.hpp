@@ -298,6 +298,7 @@ public:
       : mesh_(mesh), scalar_potential_(scalar_potential), thickness_(thickness), keo_(keo) {
     bind_fields(*mesh_, thickness_.get(), nullptr, scalar_potential_.get());
   }
+  nosh_ctx *ctx() const { return mesh_->ctx(); }
   void apply(const Tpetra::MultiVector<double, int, int> &X, Tpetra::MultiVector<double, int, int> &Y,
              Teuchos::ETransp mode = Teuchos::NO_TRANS, double alpha = 1.0, double beta = 0.0) const override {
     // unsupported mode/alpha/beta -> NOSH_EINVAL -> std::logic_error, as jacobian_operator.cpp:48-59
@@ -326,6 +327,7 @@ public:
       : mesh_(mesh), thickness_(thickness), mvp_(mvp) {
     bind_fields(*mesh_, thickness_.get(), mvp_.get(), nullptr);
   }
+  nosh_ctx *ctx() const { return mesh_->ctx(); }
   // one AMG V-cycle on the regularised KEO (src/keo_regularized.cpp:88-165; MueLu in the reference, built on
   // the device here); unsupported mode/alpha/beta -> std::logic_error (:98-100)
   void apply(const Tpetra::MultiVector<double, int, int> &X, Tpetra::MultiVector<double, int, int> &Y,
@@ -353,6 +355,64 @@ private:
 };
 
 // ---------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// What nls::get_W_factory hands to NOX/LOCA: a Stratimikos "Belos" linear-solve strategy
+// (src/model_evaluator_nls.cpp:269-299: "Pseudo Block CG", no preconditioner; the alternatives it keeps
+// commented out -- "MINRES", "Pseudo Block GMRES" -- are what examples/conf.xml:103-136 configures).
+// Stratimikos/Belos are not installed; this is the image of that parameter list over the device solvers.
+// ---------------------------------------------------------------------------------------------
+struct linear_solve_status {
+  int iterations = 0;
+  bool converged = false;
+  double achieved_tol = 0.0;
+};
+class belos_solve_strategy {
+public:
+  std::string solver_type = "Pseudo Block CG";  // model_evaluator_nls.cpp:282
+  std::string preconditioner_type = "None";     // :291
+  double convergence_tolerance = 1e-8;          // Belos default; conf.xml sets 1e-10
+  int maximum_iterations = 1000;                // Belos default
+  int num_blocks = 300;                         // GMRES restart length, Belos default
+  // solve op x = b; op: the jacobian_operator / keo / keo_regularized of `mesh`, prec: a rebuilt
+  // keo_regularized (create_W_prec) or null
+  linear_solve_status solve(const Tpetra::Operator<double, int, int> &op, const Tpetra::Vector<double, int, int> &b,
+                            Tpetra::Vector<double, int, int> &x,
+                            const std::shared_ptr<Tpetra::Operator<double, int, int>> &prec = nullptr) const {
+    nosh_ctx *c = nullptr;
+    nosh_operator_id id;
+    if (auto j = dynamic_cast<const nosh::jacobian_operator *>(&op)) {
+      c = j->ctx();
+      id = NOSH_OP_JACOBIAN;
+    } else if (auto k = dynamic_cast<const nosh::keo_regularized *>(&op)) {
+      c = k->ctx();
+      id = NOSH_OP_KEOREG;
+    } else {
+      throw std::logic_error("belos_solve_strategy: unknown operator type");
+    }
+    const bool use_prec = prec && preconditioner_type != "None";
+    if (use_prec && !std::dynamic_pointer_cast<nosh::keo_regularized>(prec))
+      throw std::logic_error("belos_solve_strategy: the preconditioner must be a nosh::keo_regularized");
+    const nosh_precond pc = use_prec ? NOSH_PREC_KEOREG_AMG : NOSH_PREC_NONE;
+    nosh_krylov_result r;
+    if (solver_type == "Pseudo Block CG")
+      check(c, nosh_cg_prec(c, id, pc, b.getData(), x.getDataNonConst(), convergence_tolerance, maximum_iterations, &r,
+                            nullptr));
+    else if (solver_type == "MINRES")
+      check(c, nosh_minres_prec(c, id, pc, b.getData(), x.getDataNonConst(), convergence_tolerance, maximum_iterations,
+                                &r, nullptr));
+    else if (solver_type == "Pseudo Block GMRES")
+      check(c, nosh_gmres(c, id, pc, b.getData(), x.getDataNonConst(), convergence_tolerance, maximum_iterations,
+                          num_blocks, &r, nullptr));
+    else
+      throw std::logic_error("belos_solve_strategy: unknown \"Solver Type\" " + solver_type);
+    linear_solve_status st;
+    st.iterations = r.iterations;
+    st.converged = r.converged != 0;
+    st.achieved_tol = r.relres;
+    return st;
+  }
+};
+
 namespace model_evaluator {
 
 // the members of Thyra::ModelEvaluatorBase::InArgs / OutArgs that nls supports
@@ -418,6 +478,10 @@ public:
   }
   std::shared_ptr<Tpetra::Operator<double, int, int>> create_W_prec() const {
     return std::make_shared<nosh::keo_regularized>(mesh_, thickness_, mvp_);  // :301-314
+  }
+  // :269-299 (live settings: "Pseudo Block CG", "Preconditioner Type" = "None")
+  std::shared_ptr<nosh::belos_solve_strategy> get_W_factory() const {
+    return std::make_shared<nosh::belos_solve_strategy>();
   }
   const std::shared_ptr<const nosh::mesh> mesh() const { return mesh_; }
 

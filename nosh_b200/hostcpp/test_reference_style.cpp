@@ -159,6 +159,34 @@ static void run(const Fixture &fx) {
     // keo_regularized.cpp:98-100: anything but NO_TRANS / 1 / 0 is refused
     REQUIRE_THROWS_AS(prec->apply(s, Ms, Teuchos::TRANS, 1.0, 0.0), std::logic_error);
     REQUIRE_THROWS_AS(prec->apply(s, Ms, Teuchos::NO_TRANS, 1.0, 1.0), std::logic_error);
+    // one Newton correction the way NOX drives it: F, W_op, W_prec from evalModel, then the linear-solve
+    // strategy of get_W_factory (model_evaluator_nls.cpp:269-299) on J d = -F
+    auto lows = model.get_W_factory();
+    REQUIRE_APPROX((double)(lows->solver_type == "Pseudo Block CG" && lows->preconditioner_type == "None"), 1.0, 0.0);
+    auto fvec = std::make_shared<Tpetra::Vector<double, int, int>>(mesh->complex_map());
+    auto out3 = model.createOutArgs();
+    out3.set_f(fvec);
+    model.evalModel(in, out3);
+    Tpetra::Vector<double, int, int> rhs(jac->getRangeMap()), d(jac->getDomainMap()), Jd(jac->getRangeMap());
+    for (size_t k = 0; k < 2 * N; k++) rhs[k] = -(*fvec)[k];
+    for (const char *type : {"MINRES", "Pseudo Block GMRES"}) {
+      for (const char *pt : {"None", "keo_regularized"}) {
+        lows->solver_type = type;
+        lows->preconditioner_type = pt;
+        lows->convergence_tolerance = 1e-12;
+        const auto st = lows->solve(*jac, rhs, d, prec);
+        REQUIRE_APPROX((double)st.converged, 1.0, 0.0);
+        jac->apply(d, Jd);
+        double worst_r = 0.0, scale = 0.0;
+        for (size_t k = 0; k < 2 * N; k++) {
+          worst_r = std::fmax(worst_r, std::fabs(Jd[k] - rhs[k]));
+          scale = std::fmax(scale, std::fabs(rhs[k]));
+        }
+        REQUIRE_APPROX(1.0 + worst_r / scale, 1.0, 1e-9);
+      }
+    }
+    lows->solver_type = "no such solver";
+    REQUIRE_THROWS_AS(lows->solve(*jac, rhs, d, prec), std::logic_error);
   }
   // ---- test/dfdp.cpp:51-142: dF/dg vs central difference, mu = 0 ----
   {
