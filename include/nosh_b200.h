@@ -80,6 +80,10 @@ typedef enum { NOSH_PREC_NONE = 0, NOSH_PREC_KEOREG_AMG = 1 } nosh_precond;
  * current matrix */
 typedef enum { NOSH_AMG_REUSE_NONE = 0, NOSH_AMG_REUSE_FULL = 1 } nosh_amg_reuse;
 
+/* Krylov solver of the Newton / continuation drivers: the "Solver Type" values of the reference's Belos
+ * parameter lists (src/model_evaluator_nls.cpp:280-282, examples/conf.xml:103-105) */
+typedef enum { NOSH_SOLVER_MINRES = 0, NOSH_SOLVER_CG = 1, NOSH_SOLVER_GMRES = 2 } nosh_linear_solver;
+
 /* ---- lifecycle ------------------------------------------------------------- */
 NOSH_API const char *nosh_version(void);
 /* stream: a cudaStream_t (as void*) all work is enqueued on, or NULL for a
@@ -294,6 +298,9 @@ NOSH_API nosh_status nosh_gmres(nosh_ctx *ctx, nosh_operator_id op, nosh_precond
  * with KEOREG_AMG every Newton step also does keo_regularized::rebuild at the current state,
  * the evalModel(W_prec) of src/model_evaluator_nls.cpp:507-522 */
 NOSH_API nosh_status nosh_ctx_set_preconditioner(nosh_ctx *ctx, nosh_precond prec);
+/* Krylov solver of the Newton / continuation drivers (default MINRES; the reference's live default is
+ * "Pseudo Block CG", its conf.xml selects "Pseudo Block GMRES"); gmres_restart <= 0 keeps the setting */
+NOSH_API nosh_status nosh_ctx_set_linear_solver(nosh_ctx *ctx, nosh_linear_solver solver, int gmres_restart);
 
 /* ---- Newton.  NOX "Line Search Based"/"Full Step" with a NormF test as configured in
  * examples/conf.xml:76-191, driving evalModel(f), evalModel(W_op) and the MINRES solve

@@ -18,6 +18,7 @@ LAYOUT_CSR, LAYOUT_SELL32 = 0, 1
 MAT_KEO, MAT_DKEO = 0, 1
 OP_JACOBIAN, OP_KEO, OP_KEOREG = 0, 1, 2
 PREC_NONE, PREC_KEOREG_AMG = 0, 1
+SOLVER_MINRES, SOLVER_CG, SOLVER_GMRES = 0, 1, 2
 AMG_REUSE_NONE, AMG_REUSE_FULL = 0, 1
 AMG_MAX_LEVELS = 16
 
@@ -148,6 +149,7 @@ def lib():
         "nosh_minres_prec": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, dbl, C.c_int, C.POINTER(KrylovResult), vp]),
         "nosh_cg_prec": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, dbl, C.c_int, C.POINTER(KrylovResult), vp]),
         "nosh_gmres": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, dbl, C.c_int, C.c_int, C.POINTER(KrylovResult), vp]),
+        "nosh_ctx_set_linear_solver": (C.c_int, [vp, C.c_int, C.c_int]),
         "nosh_ctx_set_preconditioner": (C.c_int, [vp, C.c_int]),
         "nosh_newton": (C.c_int, [vp, C.c_int, cpp, vp, vp, dbl, C.c_int, dbl, C.c_int,
                                   C.POINTER(NewtonResult), vp, vp]),

@@ -404,6 +404,10 @@ class Context:
         return self._amg_csr(self.L.nosh_amg_get_prolongator, level, info.nodes[level],
                              info.p_blocks[level])
 
+    def set_linear_solver(self, solver, gmres_restart=0):
+        """Krylov solver of newton / continuation / continuation_arclength (SOLVER_MINRES, _CG, _GMRES)."""
+        self._ck(self.L.nosh_ctx_set_linear_solver(self.h, int(solver), int(gmres_restart)))
+
     def set_preconditioner(self, prec):
         self._ck(self.L.nosh_ctx_set_preconditioner(self.h, int(prec)))
 

@@ -646,6 +646,16 @@ nosh_status nosh_amg_get_prolongator(nosh_ctx *ctx, int level, int64_t *rowptr, 
   API_END(ctx)
 }
 
+nosh_status nosh_ctx_set_linear_solver(nosh_ctx *ctx, nosh_linear_solver solver, int gmres_restart) {
+  API_BEGIN(ctx)
+  if (solver != NOSH_SOLVER_MINRES && solver != NOSH_SOLVER_CG && solver != NOSH_SOLVER_GMRES)
+    NOSH_THROW(NOSH_EINVAL, "unknown linear solver %d", (int)solver);
+  if (gmres_restart > 500) NOSH_THROW(NOSH_EINVAL, "restart length must be in [1, 500]");
+  ctx->lin_solver = solver;
+  if (gmres_restart > 0) ctx->gmres_restart = gmres_restart;
+  API_END(ctx)
+}
+
 nosh_status nosh_ctx_set_preconditioner(nosh_ctx *ctx, nosh_precond prec) {
   API_BEGIN(ctx)
   if (prec != NOSH_PREC_NONE && prec != NOSH_PREC_KEOREG_AMG) NOSH_THROW(NOSH_EINVAL, "unknown preconditioner %d", (int)prec);

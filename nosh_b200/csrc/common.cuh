@@ -204,6 +204,8 @@ struct Ctx {
   int amg_reuse = 1;          // nosh_amg_reuse: 0 none, 1 full ("reuse: type" = "full", keo_regularized.cpp:300)
   bool amg_keep_l0 = false;   // keep the level-0 block CSR copy (parity accessors)
   int64_t keoreg_version = 0, amg_dinv_version = -1;
+  int lin_solver = 0;         // nosh_linear_solver of the Newton / continuation drivers (default MINRES)
+  int gmres_restart = 300;    // Belos "Num Blocks" default
   int precond = 0;            // nosh_precond the Newton / continuation drivers use for their linear solves
   // ---- work vectors (2*Nl doubles each) ----
   DBuf<double2> work[14];

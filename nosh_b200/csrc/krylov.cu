@@ -672,6 +672,24 @@ void cg_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, double2
   }
 }
 
+// the linear solve of the Newton / continuation drivers: J x = bscale * b with the ctx's solver choice
+void jacobian_solve(Ctx *ctx, const double2 *b, double bscale, double2 *x, double tol, int maxit,
+                    nosh_krylov_result *kr) {
+  switch (ctx->lin_solver) {
+    case NOSH_SOLVER_MINRES:
+      minres_dev(ctx, NOSH_OP_JACOBIAN, ctx->precond, b, bscale, x, tol, maxit, kr, nullptr);
+      break;
+    case NOSH_SOLVER_CG:
+      cg_dev(ctx, NOSH_OP_JACOBIAN, ctx->precond, b, bscale, x, tol, maxit, kr, nullptr);
+      break;
+    case NOSH_SOLVER_GMRES:
+      gmres_dev(ctx, NOSH_OP_JACOBIAN, ctx->precond, b, bscale, x, tol, maxit, ctx->gmres_restart, kr, nullptr);
+      break;
+    default:
+      NOSH_THROW(NOSH_EINVAL, "unknown linear solver %d", ctx->lin_solver);
+  }
+}
+
 // dF/dp = (dK/dp) psi + { c t |psi|^2 psi  (p == "g")  |  c t dV/dp psi }   (nls::computeDFDP_)
 void compute_dfdp_dev(Ctx *ctx, int np, const char *const *names, const double *values, const char *pname,
                       double2 *psi, double2 *out) {
@@ -710,7 +728,7 @@ void newton_dev(Ctx *ctx, int np, const char *const *names, const double *values
     // evalModel(W_prec): keo_regularized::rebuild at the current state (src/model_evaluator_nls.cpp:507-522)
     if (ctx->precond != NOSH_PREC_NONE) keoreg_diags_dev(ctx, g, psi);
     nosh_krylov_result kr;
-    minres_dev(ctx, NOSH_OP_JACOBIAN, ctx->precond, F, -1.0, D, lin_tol, lin_maxit, &kr, nullptr);
+    jacobian_solve(ctx, F, -1.0, D, lin_tol, lin_maxit, &kr);
     if (lin_iters) lin_iters[k] = kr.iterations;
     total += kr.iterations;
     axpy_dev(ctx, 1.0, D, psi);
@@ -755,7 +773,7 @@ void continuation_dev(Ctx *ctx, int np, const char *const *names, const double *
       if (ctx->precond != NOSH_PREC_NONE) keoreg_diags_dev(ctx, g, psi);
       compute_dfdp_dev(ctx, np, names, vals.data(), pname, psi, dF);
       nosh_krylov_result kr;
-      minres_dev(ctx, NOSH_OP_JACOBIAN, ctx->precond, dF, -1.0, T, lin_tol, lin_maxit, &kr, nullptr);
+      jacobian_solve(ctx, dF, -1.0, T, lin_tol, lin_maxit, &kr);
       st.predictor_linear_iterations = kr.iterations;
       axpy_dev(ctx, dp, T, psi);
     }
@@ -849,7 +867,7 @@ void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *val
     prepare(psi);
     compute_dfdp_dev(ctx, np, names, vals.data(), pname, psi, Fp.p);
     nosh_krylov_result kr;
-    minres_dev(ctx, NOSH_OP_JACOBIAN, ctx->precond, Fp.p, -1.0, Bv.p, opt->lin_tol, opt->lin_maxit, &kr, nullptr);
+    jacobian_solve(ctx, Fp.p, -1.0, Bv.p, opt->lin_tol, opt->lin_maxit, &kr);
     const double tt = dot_dev(ctx, Bv.p, Bv.p) / len;
     double pd = 1.0 / sqrt(tt + 1.0);
     if (first) {
@@ -897,8 +915,8 @@ void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *val
         if (its >= opt->nl_maxit || !(nrm == nrm)) break;
         compute_dfdp_dev(ctx, np, names, vals.data(), pname, psi, Fp.p);
         nosh_krylov_result ka, kb;
-        minres_dev(ctx, NOSH_OP_JACOBIAN, ctx->precond, F, -1.0, Av.p, opt->lin_tol, opt->lin_maxit, &ka, nullptr);
-        minres_dev(ctx, NOSH_OP_JACOBIAN, ctx->precond, Fp.p, -1.0, Bv.p, opt->lin_tol, opt->lin_maxit, &kb, nullptr);
+        jacobian_solve(ctx, F, -1.0, Av.p, opt->lin_tol, opt->lin_maxit, &ka);
+        jacobian_solve(ctx, Fp.p, -1.0, Bv.p, opt->lin_tol, opt->lin_maxit, &kb);
         lin += ka.iterations + kb.iterations;
         const double xa = dot_dev(ctx, XD.p, Av.p) / len, xb = dot_dev(ctx, XD.p, Bv.p) / len;
         const double dp = -(gc + xa) / (pdot + xb);

@@ -327,3 +327,35 @@ def test_singular_preconditioner_matrix_is_reported(nb, orc):
     ctx2.keoreg_rebuild({"g": 1.0, "mu": 0.1}, psi)
     with pytest.raises(RuntimeError, match="SELL-32"):
         ctx2.keoreg_apply(np.ones(2 * coords.shape[0]))
+
+
+def test_newton_solver_choice(nb, orc):
+    """The Newton driver with each Belos "Solver Type" of the reference's parameter lists (MINRES, the live
+    default "Pseudo Block CG", conf.xml's "Pseudo Block GMRES"), with and without the preconditioner: same
+    solution; GMRES never needs more iterations than MINRES (same Krylov space, full orthogonalisation)."""
+    coords, cells = orc.meshgen.tetgrid(12)
+    psi, A = orc.meshgen.plain_gl_fields(coords)
+    params = {"g": 1.0, "mu": 0.1}
+    ctx = nb.Context()
+    ctx.mesh_set(coords, cells)
+    ctx.set_thickness(None, 1.0)
+    ctx.set_potential_constant(-1.0)
+    ctx.set_mvp_explicit(A)
+    ctx.amg_set_options(coarse_max=64)
+    sols, its = {}, {}
+    for prec in (nb.PREC_NONE, nb.PREC_KEOREG_AMG):
+        ctx.set_preconditioner(prec)
+        for name, solver in (("minres", nb.SOLVER_MINRES), ("gmres", nb.SOLVER_GMRES), ("cg", nb.SOLVER_CG)):
+            ctx.set_linear_solver(solver, 300)
+            x = psi.copy()
+            res, lin, fn = ctx.newton(params, x, nl_tol=1e-8, nl_maxit=20, lin_tol=1e-10, lin_maxit=3000)
+            assert res.converged == 1, (name, prec, fn)
+            sols[(name, prec)], its[(name, prec)] = x, lin
+    ref = sols[("minres", nb.PREC_NONE)]
+    for k, x in sols.items():
+        assert relerr(x, ref) <= 1e-6, k
+    for prec in (nb.PREC_NONE, nb.PREC_KEOREG_AMG):
+        assert its[("gmres", prec)][0] <= its[("minres", prec)][0]
+    assert its[("gmres", nb.PREC_KEOREG_AMG)].sum() < its[("gmres", nb.PREC_NONE)].sum() / 2
+    with pytest.raises(ValueError):
+        ctx.set_linear_solver(7)
