@@ -424,6 +424,9 @@ NOSH_API nosh_status nosh_morton_order(int64_t n_vertices, const double *coords 
  * time kernels with inputs already in HBM.  slot in [0,8). Returns a device pointer to
  * 2*(n_owned+n_ghost) doubles owned by the ctx. */
 NOSH_API nosh_status nosh_scratch_vector(nosh_ctx *ctx, int slot, double **dev_ptr);
+/* tuning knobs for measurements (profiles/apply_variants.py): key "apply_variant" = which compiled variant
+ * of the SELL-32 apply kernel the MINRES loop uses (0 = default).  Results do not depend on it. */
+NOSH_API nosh_status nosh_ctx_set_tuning(nosh_ctx *ctx, const char *key, int value);
 /* number of kernels this library has launched on ctx so far */
 NOSH_API int64_t nosh_launch_count(const nosh_ctx *ctx);
 /* CUDA-event timing on the ctx stream */

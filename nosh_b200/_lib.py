@@ -169,6 +169,7 @@ def lib():
         "nosh_meshfile_write": (C.c_int, [C.c_char_p, i32, i64, vp, i64, vp, i32, cpp, vp, vp, i32]),
         "nosh_morton_order": (C.c_int, [i64, vp, vp]),
         "nosh_scratch_vector": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+        "nosh_ctx_set_tuning": (C.c_int, [vp, C.c_char_p, C.c_int]),
         "nosh_launch_count": (i64, [vp]),
         "nosh_timer_start": (C.c_int, [vp]),
         "nosh_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),

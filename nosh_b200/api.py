@@ -513,6 +513,9 @@ class Context:
         self._ck(self.L.nosh_scratch_vector(self.h, int(slot), C.byref(p)))
         return p.value
 
+    def set_tuning(self, key, value):
+        self._ck(self.L.nosh_ctx_set_tuning(self.h, key.encode(), int(value)))
+
     def launch_count(self):
         return int(self.L.nosh_launch_count(self.h))
 

@@ -62,8 +62,12 @@ __device__ __forceinline__ bool krylov_skip(const ApplyArgs &A) {
 // -------------------------------------------------------------------------------------------
 // SELL-32, one thread per row, one CTA per CHUNK (=512) rows = 16 slices.
 // -------------------------------------------------------------------------------------------
-template <int EPI, int FUSE, int U>
-__global__ void __launch_bounds__(CHUNK, 2) k_apply_sell(const ApplyArgs A) {
+// U: independent (column, value) pairs in flight per thread; MINB: CTAs per SM the register budget is
+// sized for (2 -> 64 registers, 1 -> up to 128); PF: load the next batch's columns before the current
+// batch's gathers are consumed (software pipelining of the col -> x dependency).  The variants exist
+// for measurement (profiles/apply_variants.py); launch2 picks the one that measured best.
+template <int EPI, int FUSE, int U, int MINB, bool PF>
+__global__ void __launch_bounds__(CHUNK, MINB) k_apply_sell(const ApplyArgs A) {
   if (krylov_skip<FUSE>(A)) return;
   if (A.gate && A.gate->done) return;
   __shared__ double red[32];
@@ -76,23 +80,53 @@ __global__ void __launch_bounds__(CHUNK, 2) k_apply_sell(const ApplyArgs A) {
   if (slice < A.nslices) {
     int p = __ldg(A.slice_off + slice) + lane;
     const int pend = __ldg(A.slice_off + slice + 1);
-    // U independent (column, value) loads, then U gathers, then the FMAs
-    for (; p + 32 * (U - 1) < pend; p += 32 * U) {
+    if (PF) {
       int c[U];
-      double2 v[U], xv[U];
+      bool have = p + 32 * (U - 1) < pend;
+      if (have) {
 #pragma unroll
-      for (int u = 0; u < U; u++) c[u] = ld_stream_i32(A.col + p + 32 * u);
+        for (int u = 0; u < U; u++) c[u] = ld_stream_i32(A.col + p + 32 * u);
+      }
+      while (have) {
+        double2 v[U], xv[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) v[u] = ld_stream2(A.val + p + 32 * u);
+        for (int u = 0; u < U; u++) v[u] = ld_stream2(A.val + p + 32 * u);
 #pragma unroll
-      for (int u = 0; u < U; u++) xv[u] = __ldg(A.x + c[u]);
+        for (int u = 0; u < U; u++) xv[u] = __ldg(A.x + c[u]);
+        p += 32 * U;
+        have = p + 32 * (U - 1) < pend;
+        if (have) {
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (FUSE == FUSE_MINRES) {
-          xv[u].x *= scale;
-          xv[u].y *= scale;
+          for (int u = 0; u < U; u++) c[u] = ld_stream_i32(A.col + p + 32 * u);
         }
-        cfma(acc, v[u], xv[u]);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if (FUSE == FUSE_MINRES) {
+            xv[u].x *= scale;
+            xv[u].y *= scale;
+          }
+          cfma(acc, v[u], xv[u]);
+        }
+      }
+    } else {
+      // U independent (column, value) loads, then U gathers, then the FMAs
+      for (; p + 32 * (U - 1) < pend; p += 32 * U) {
+        int c[U];
+        double2 v[U], xv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) c[u] = ld_stream_i32(A.col + p + 32 * u);
+#pragma unroll
+        for (int u = 0; u < U; u++) v[u] = ld_stream2(A.val + p + 32 * u);
+#pragma unroll
+        for (int u = 0; u < U; u++) xv[u] = __ldg(A.x + c[u]);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if (FUSE == FUSE_MINRES) {
+            xv[u].x *= scale;
+            xv[u].y *= scale;
+          }
+          cfma(acc, v[u], xv[u]);
+        }
       }
     }
     for (; p < pend; p += 32) {
@@ -221,9 +255,21 @@ template <int EPI, int FUSE>
 void launch2(Ctx *ctx, const ApplyArgs &A) {
   const unsigned grid = A.chunk_list ? (unsigned)A.n_list : (unsigned)cdiv(A.No, CHUNK);
   if (grid == 0) return;
-  if (ctx->layout == NOSH_LAYOUT_SELL32)
-    k_apply_sell<EPI, FUSE, 4><<<grid, CHUNK, 0, ctx->stream>>>(A);
-  else
+  if (ctx->layout == NOSH_LAYOUT_SELL32) {
+    // measurement variants exist for the two kernels of the MINRES loop only (compile time)
+    constexpr bool tunable = EPI == EPI_DIAG && (FUSE == FUSE_NONE || FUSE == FUSE_MINRES);
+    const int v = tunable ? ctx->apply_variant : 0;
+    switch (v) {
+      case 1: k_apply_sell<EPI, FUSE, tunable ? 8 : 4, 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      case 2: k_apply_sell<EPI, FUSE, 4, 2, tunable><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      case 3: k_apply_sell<EPI, FUSE, tunable ? 8 : 4, tunable ? 1 : 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      case 4: k_apply_sell<EPI, FUSE, tunable ? 8 : 4, tunable ? 1 : 2, tunable><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      case 5: k_apply_sell<EPI, FUSE, tunable ? 6 : 4, 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      case 6: k_apply_sell<EPI, FUSE, tunable ? 2 : 4, 2, tunable><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      case 7: k_apply_sell<EPI, FUSE, tunable ? 12 : 4, tunable ? 1 : 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      default: k_apply_sell<EPI, FUSE, 4, 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+    }
+  } else
     k_apply_csr<EPI, FUSE, 8><<<grid, CHUNK, 0, ctx->stream>>>(A);
   ctx->launches++;
   CUDA_CHECK(cudaGetLastError());

@@ -821,6 +821,18 @@ nosh_status nosh_scratch_vector(nosh_ctx *ctx, int slot, double **dev_ptr) {
   API_END(ctx)
 }
 
+nosh_status nosh_ctx_set_tuning(nosh_ctx *ctx, const char *key, int value) {
+  API_BEGIN(ctx)
+  if (!key) NOSH_THROW(NOSH_EINVAL, "NULL key");
+  if (strcmp(key, "apply_variant") == 0) {
+    if (value < 0 || value > 7) NOSH_THROW(NOSH_EINVAL, "apply_variant must be in [0, 7]");
+    ctx->apply_variant = value;
+  } else {
+    NOSH_THROW(NOSH_EKEY, "unknown tuning key \"%s\"", key);
+  }
+  API_END(ctx)
+}
+
 int64_t nosh_launch_count(const nosh_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 nosh_status nosh_timer_start(nosh_ctx *ctx) {

@@ -141,6 +141,7 @@ struct Ctx {
 
   // options
   int layout = NOSH_LAYOUT_SELL32;
+  int apply_variant = 0;            // measurement knob: which k_apply_sell variant the MINRES loop uses (apply.cu)
   int64_t group_vertices = 65536;
 
   // ---- mesh ----
