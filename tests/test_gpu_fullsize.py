@@ -1,0 +1,215 @@
+"""Full-size checks (BASELINE.json configs[1..2] sizes: tetgrid n=200 = 8.0M vertices) through properties that
+do not need the oracle -- it would take hours at this size: volume conservation, Hermitian K, the null
+vector at mu = 0, the reference tests' quadratic-form identity (test/keo.cpp:134-135), dK/dmu and J against
+central differences (the check test/dfdp.cpp makes for dF/dg), linearity, MINRES' implicit residual against
+the true one, and the V-cycle's symmetry / definiteness -- and against tests/golden/fullsize_n200.json, known-answer
+hashes (norms and quadratic forms, the style of the reference's own tests) that the CPU oracle produced for
+exactly this mesh (tests/golden/make_fullsize_golden.py; minutes of CPU time, so not run on the GPU box).
+Vectors live on the device (torch) and are used in place by the C ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N_AXIS = int(os.environ.get("NOSH_FULLSIZE_N", "200"))
+
+
+class Ordered:
+    """The ctx enqueues on its own stream and device-pointer calls return without waiting; torch works on
+    its current stream.  This proxy orders the two (a caller would pass torch's stream to nosh_ctx_create or
+    call nosh_ctx_synchronize): wait for torch before a call, for the ctx after it."""
+
+    def __init__(self, ctx, torch):
+        self._ctx, self._torch = ctx, torch
+
+    def __getattr__(self, name):
+        fn = getattr(self._ctx, name)
+        if not callable(fn):
+            return fn
+
+        def call(*a, **kw):
+            self._torch.cuda.synchronize()
+            r = fn(*a, **kw)
+            self._ctx.synchronize()
+            return r
+        return call
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import torch
+    import nosh_b200
+    ctx = Ordered(nosh_b200.Context(), torch)
+    mi = ctx.mesh_tetgrid(N_AXIS)
+    ctx.set_thickness(None, 1.0)
+    ctx.set_potential_constant(-1.0)
+    ctx.set_mvp_constcurl((0.0, 0.0, 1.0))
+    No = int(mi.n_owned)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    rnd = lambda: torch.randn(2 * No, generator=g, device="cuda", dtype=torch.float64)  # noqa: E731
+    yield ctx, mi, No, rnd, torch, nosh_b200
+    ctx._ctx.close()
+
+
+def test_volume_and_sizes(setup):
+    ctx, mi, No, rnd, torch, nb = setup
+    assert mi.n_global == N_AXIS ** 3 == No
+    assert mi.n_cells == 6 * (N_AXIS - 1) ** 3
+    cv = ctx.control_volumes()
+    assert cv.min() > 0
+    # |[-5,5]^3| = 1000 (test/mesh.cpp's ||c||_1).  The reference's signed-covolume construction
+    # (src/mesh_tetra.cpp:273-331) is exact for well-shaped cells only: on the 8M-vertex jittered mesh the
+    # oracle itself sums to 1000.00000057 (golden below), on <= 1M vertices to exactly 1000.
+    assert cv.sum() == pytest.approx(1000.0, rel=1e-8)
+
+
+def test_against_full_size_oracle_hashes(setup):
+    """the oracle's known answers for this very mesh (generated offline, see the module docstring)"""
+    ctx, mi, No, rnd, torch, nb = setup
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize_n%d.json" % N_AXIS)
+    if not os.path.exists(path):
+        pytest.skip("no golden file for n = %d" % N_AXIS)
+    G = json.load(open(path))
+    from oracle import meshgen
+    assert mi.n_owned == G["num_nodes"] and mi.n_edges == G["num_edges"]
+    cv = ctx.control_volumes()
+    assert np.abs(cv).sum() == pytest.approx(G["cv_norm1"], rel=1e-13)
+    assert np.linalg.norm(cv) == pytest.approx(G["cv_norm2"], rel=1e-13)
+    assert np.abs(cv).max() == pytest.approx(G["cv_norminf"], rel=1e-13)
+    assert cv.min() == pytest.approx(G["cv_min"], rel=1e-10)
+    al = ctx.alpha_cache()
+    assert al.sum() == pytest.approx(G["alpha_sum"], rel=1e-11)
+    assert np.linalg.norm(al) == pytest.approx(G["alpha_norm2"], rel=1e-12)
+    par = {"g": G["g"], "mu": G["mu"], "theta": G["theta"]}
+    dev = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+    one = torch.ones(2 * No, device="cuda", dtype=torch.float64)
+    er = torch.zeros_like(one)
+    er[0::2] = 1.0
+    ei = one - er
+    x = dev(meshgen.random_state(No, 42))
+    out = torch.empty_like(one)
+    ctx.keo_fill(par)
+    # quadratic forms with heavy cancellation (K 1 is almost 0): absolute scale = |x^T K x| of a generic x
+    ctx.keo_apply(x, out)
+    xkx = torch.dot(x, out).item()
+    assert xkx == pytest.approx(G["keo_xKx"], rel=1e-12)
+    assert torch.linalg.vector_norm(out).item() == pytest.approx(G["keo_Kx_norm2"], rel=1e-12)
+    ctx.keo_apply(one, out)
+    assert torch.dot(one, out).item() == pytest.approx(G["keo_1K1"], rel=1e-7, abs=1e-13 * abs(xkx))
+    ctx.keo_apply(er, out)
+    assert torch.dot(er, out).item() == pytest.approx(G["keo_erKer"], rel=1e-7, abs=1e-13 * abs(xkx))
+    f = torch.empty_like(one)
+    ctx.compute_f(par, er, f)
+    assert f.abs().sum().item() == pytest.approx(G["F_norm1"], rel=1e-10)
+    assert torch.linalg.vector_norm(f).item() == pytest.approx(G["F_norm2"], rel=1e-10)
+    assert f.abs().max().item() == pytest.approx(G["F_norminf"], rel=1e-10)
+    ctx.compute_f(par, x, f)
+    assert torch.linalg.vector_norm(f).item() == pytest.approx(G["F_random_state_norm2"], rel=1e-12)
+    ctx.jac_rebuild(par, x)
+    for name, s in (("one", one), ("er", er), ("ei", ei), ("x", x)):
+        ctx.jac_apply(s, out)
+        assert torch.dot(s, out).item() == pytest.approx(G["jac_%s" % name], rel=1e-10), name
+    ctx.compute_dfdp(par, "mu", x, out)
+    assert torch.linalg.vector_norm(out).item() == pytest.approx(G["dfdmu_norm2"], rel=1e-12)
+
+
+def test_keo_structure(setup):
+    ctx, mi, No, rnd, torch, nb = setup
+    one = torch.zeros(2 * No, device="cuda", dtype=torch.float64)
+    one[0::2] = 1.0
+    er = one.clone()
+    x, y = rnd(), rnd()
+    out, out2 = torch.empty_like(x), torch.empty_like(x)
+    # mu = 0: constants are in the null space of K (src/parameter_matrix_keo.cpp:119-126 with a = 0)
+    ctx.keo_fill({"mu": 0.0, "theta": 0.0})
+    ctx.keo_apply(one, out)
+    ctx.keo_apply(x, out2)
+    assert out.abs().max().item() <= 1e-11 * out2.abs().max().item()
+    # mu = 1: Hermitian (real form symmetric), and 1^T K 1 = 2 e_r^T K e_r (test/keo.cpp:134-135: one is
+    # (1,1,...) over BOTH components there; here `full` is that vector)
+    ctx.keo_fill({"mu": 1.0, "theta": 0.0})
+    kx, ky = torch.empty_like(x), torch.empty_like(x)
+    ctx.keo_apply(x, kx)
+    ctx.keo_apply(y, ky)
+    a, b = torch.dot(y, kx).item(), torch.dot(x, ky).item()
+    assert abs(a - b) <= 1e-12 * abs(a)
+    full = torch.ones(2 * No, device="cuda", dtype=torch.float64)
+    ctx.keo_apply(full, out)
+    ctx.keo_apply(er, out2)
+    q_full, q_er = torch.dot(full, out).item(), torch.dot(er, out2).item()
+    assert q_full == pytest.approx(2.0 * q_er, rel=1e-9)
+    assert torch.dot(x, kx).item() > 0                            # positive (semi-)definite
+
+
+def test_derivatives_against_central_differences(setup):
+    ctx, mi, No, rnd, torch, nb = setup
+    par = {"g": 1.0, "mu": 0.7, "theta": 0.0}
+    psi, d = rnd(), rnd()
+    # dF/dg with a constantCurl field: get_d_edge_projection_dp knows "mu" and "theta" only and throws for
+    # anything else (src/vector_field_constant_curl.cpp:135-139)
+    with pytest.raises(ValueError, match="Illegal parameter"):
+        ctx.compute_dfdp(par, "g", psi)
+    # dF/dmu (computeDFDP_) vs (F(p+e) - F(p-e)) / 2e, e = 1e-6
+    for name in ("mu",):
+        e = 1e-6
+        fp, fm, df = torch.empty_like(psi), torch.empty_like(psi), torch.empty_like(psi)
+        ctx.compute_f(dict(par, **{name: par[name] + e}), psi, fp)
+        ctx.compute_f(dict(par, **{name: par[name] - e}), psi, fm)
+        ctx.compute_dfdp(par, name, psi, df)
+        fd = (fp - fm) / (2 * e)
+        assert (fd - df).abs().max().item() <= 1e-7 * df.abs().max().item(), name
+    # J(psi) d vs (F(psi + e d) - F(psi - e d)) / 2e
+    e = 1e-6
+    fp, fm, jd = torch.empty_like(psi), torch.empty_like(psi), torch.empty_like(psi)
+    ctx.compute_f(par, psi + e * d, fp)
+    ctx.compute_f(par, psi - e * d, fm)
+    ctx.jac_rebuild(par, psi)
+    ctx.jac_apply(d, jd)
+    fd = (fp - fm) / (2 * e)
+    assert (fd - jd).abs().max().item() <= 1e-7 * jd.abs().max().item()
+    # real-linear and symmetric
+    x, y = rnd(), rnd()
+    jx, jy, jxy = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    ctx.jac_apply(x, jx)
+    ctx.jac_apply(y, jy)
+    ctx.jac_apply(2.0 * x - 3.0 * y, jxy)
+    assert (jxy - (2.0 * jx - 3.0 * jy)).abs().max().item() <= 1e-12 * jxy.abs().max().item()
+    a, b = torch.dot(y, jx).item(), torch.dot(x, jy).item()
+    assert abs(a - b) <= 1e-12 * abs(a)
+    # the reductions agree with torch's (different summation trees)
+    assert ctx.dot(x, y) == pytest.approx(torch.dot(x, y).item(), rel=1e-10)
+
+
+def test_minres_residuals_and_preconditioner(setup):
+    ctx, mi, No, rnd, torch, nb = setup
+    par = {"g": 1.0, "mu": 0.1, "theta": 0.0}
+    psi = torch.zeros(2 * No, device="cuda", dtype=torch.float64)
+    psi[0::2] = 1.0
+    b = rnd()
+    ctx.jac_rebuild(par, psi)
+    x, jx = torch.empty_like(b), torch.empty_like(b)
+    # implicit residual of MINRES == true residual (no preconditioner: 2-norm)
+    x, res, hist = ctx.minres(b, x, tol=0.0, maxit=60, history=True)
+    assert res.iterations == 60 and np.all(np.diff(hist) <= 1e-14)          # monotone
+    ctx.jac_apply(x, jx)
+    true = (torch.linalg.vector_norm(b - jx) / torch.linalg.vector_norm(b)).item()
+    assert true == pytest.approx(hist[-1], rel=1e-6)
+    # V-cycle: symmetric, positive; preconditioned MINRES reaches a true residual of 1e-8
+    ctx.keoreg_rebuild(par, psi)
+    u, v = rnd(), rnd()
+    mu_, mv = torch.empty_like(u), torch.empty_like(u)
+    ctx.keoreg_apply(u, mu_)
+    ctx.keoreg_apply(v, mv)
+    a, c = torch.dot(v, mu_).item(), torch.dot(u, mv).item()
+    assert abs(a - c) <= 1e-11 * abs(a)
+    assert torch.dot(u, mu_).item() > 0 and torch.dot(v, mv).item() > 0
+    info = ctx.amg_info()
+    assert info.levels >= 3 and info.nodes[1] < No / 15
+    x, res = ctx.minres(b, x, tol=1e-10, maxit=500, prec=nb.PREC_KEOREG_AMG)
+    assert res.converged == 1 and res.iterations < 200
+    ctx.jac_apply(x, jx)
+    assert (torch.linalg.vector_norm(b - jx) / torch.linalg.vector_norm(b)).item() <= 1e-8
