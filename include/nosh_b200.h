@@ -19,6 +19,10 @@
  *  - Vector arguments may be HOST or DEVICE pointers (detected with
  *    cudaPointerGetAttributes).  Host vectors are staged through the ctx's
  *    device buffers (H2D / D2H inside the call); device vectors are used in place.
+ *    Calls whose vectors are all on the device only ENQUEUE work on the ctx's stream and may return
+ *    before it has run: order them against other streams by creating the ctx on your own stream
+ *    (nosh_ctx_create) or with nosh_ctx_synchronize.  Calls with host vectors return when the
+ *    result is in host memory.
  *  - Per-vertex field arrays given at set-up are HOST arrays in LOCAL numbering:
  *    owned vertices first, then ghosts (nosh_mesh_local_gids).  On one GPU
  *    local == global.
