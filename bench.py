@@ -62,6 +62,9 @@ def parse():
                     help="newton / continuation workloads: preconditioner of the MINRES solves (amg = one V-cycle "
                          "on the regularised KEO, keo_regularized::apply)")
     ap.add_argument("--amg-degree", type=int, default=1)
+    ap.add_argument("--no-newton", action="store_true",
+                    help="default workload: skip the extra keys that report one full Newton-MINRES solve of the "
+                         "same mesh (BASELINE.json configs[2]) with and without the AMG preconditioner")
     return ap.parse_args()
 
 
@@ -271,16 +274,6 @@ def run_b200(args):
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        if args.precond == "amg":
-            ai = ctx.amg_info()
-            detail["amg"] = {"levels": int(ai.levels), "degree": int(ai.degree),
-                             "nodes": [int(ai.nodes[l]) for l in range(ai.levels)],
-                             "blocks": [int(ai.blocks[l]) for l in range(ai.levels)],
-                             "prolongator_blocks": [int(ai.p_blocks[l]) for l in range(ai.levels - 1)],
-                             "lambda_max": [float(ai.lambda_max[l]) for l in range(ai.levels - 1)],
-                             "setup_seconds": float(ai.setup_seconds),
-                             "note": "hierarchy built in the first (warm-up) solve and reused "
-                                     "(reuse: type = full, src/keo_regularized.cpp:300)"}
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -327,6 +320,39 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_apply, ms_fill = float(t[0]), float(t[1])
 
+    # ---- configs[2] on the same mesh, outside the timed step: one full Newton-MINRES solve without and
+    # with the AMG V-cycle preconditioner (keo_regularized::apply), CUDA events, max over ranks ----
+    newton = None
+    if not args.no_newton:
+        newton = {"params": {"g": 1.0, "mu": 0.1, "theta": 0.0}, "psi0": "1", "nl_tol": 1e-8, "lin_tol": 1e-10}
+        psi0 = torch.zeros(2 * No, device="cuda", dtype=torch.float64)
+        psi0[0::2] = 1.0
+        for label, prec, runs in (("amg", nosh_b200.PREC_KEOREG_AMG, 2), ("none", nosh_b200.PREC_NONE, 1)):
+            ctx.set_preconditioner(prec)
+            for k in range(runs):          # amg: the first run builds the hierarchy (reuse = full afterwards)
+                psi = psi0.clone()
+                barrier()
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                res, lin, fn = ctx.newton(newton["params"], psi, 1e-8, 20, 1e-10, args.lin_maxit)
+                e1.record()
+                barrier()
+                ms = e0.elapsed_time(e1)
+                if world > 1:
+                    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms = float(t.item())
+            newton[label] = {"solve_seconds": ms * 1e-3, "newton_steps": int(res.steps), "converged": int(res.converged),
+                             "minres_iterations_per_step": [int(v) for v in lin], "fnorm": float(fn[-1])}
+            if label == "amg":
+                ai = ctx.amg_info()
+                newton[label].update({"hierarchy_setup_seconds": float(ai.setup_seconds),
+                                      "level_nodes": [int(ai.nodes[l]) for l in range(ai.levels)],
+                                      "preconditioner": "one V-cycle of smoothed-aggregation AMG on the regularised "
+                                                        "KEO, per rank (block-Jacobi over ranks)"})
+        ctx.set_preconditioner(nosh_b200.PREC_NONE)
+
     nb = int(mi.n_blocks)
     bytes_apply = nb * 20 + (No + 1) * 8 + No * (16 + 16 + 24)   # SURVEY.md 8(d), per launch per GPU
     peak, peak_src = measured_peak()
@@ -364,6 +390,8 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if newton:
+            out["newton_solve"] = newton
         if not args.no_cpu_baseline and world == 1:
             import oracle
             th = oracle.num_threads()

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -114,7 +115,7 @@ extern "C" {
 
 const char *nosh_meshfile_last_error(void) { return g_err.c_str(); }
 
-nosh_status nosh_meshfile_read(const char *path, nosh_meshfile **out) {
+static nosh_status meshfile_read_impl(const char *path, nosh_meshfile **out) {
   if (!path || !out) return fail(NOSH_EINVAL, "NULL argument");
   *out = nullptr;
   const std::string p(path);
@@ -134,7 +135,8 @@ nosh_status nosh_meshfile_read(const char *path, nosh_meshfile **out) {
   else if (fmt != "ASCII") return fail(NOSH_EINVAL, p + ": bad format line");
   if (Reader::upper(R.token()) != "DATASET" || Reader::upper(R.token()) != "UNSTRUCTURED_GRID")
     return fail(NOSH_EINVAL, p + ": only DATASET UNSTRUCTURED_GRID is supported");
-  auto M = new nosh_meshfile();
+  std::unique_ptr<nosh_meshfile> holder(new nosh_meshfile());  // freed on every exit path, exceptions included
+  nosh_meshfile *M = holder.get();
   std::vector<int64_t> conn;  // raw CELLS stream
   std::vector<int64_t> offsets;
   bool new_layout = false;
@@ -233,13 +235,13 @@ nosh_status nosh_meshfile_read(const char *path, nosh_meshfile **out) {
       std::vector<double> v;
       if (!R.read_array(std::string(R.binary ? "unsigned_char" : "float"), 4 * n, v)) goto bad;
     } else {
-      delete M;
+      holder.reset();
       return fail(NOSH_EINVAL, p + ": unsupported VTK section " + kw);
     }
   }
   {
     if (types.size() != ncells) {
-      delete M;
+      holder.reset();
       return fail(NOSH_EINVAL, p + ": CELL_TYPES does not match CELLS");
     }
     // keep the highest-dimensional simplex type present (tetrahedra, else triangles)
@@ -268,17 +270,17 @@ nosh_status nosh_meshfile_read(const char *path, nosh_meshfile **out) {
       }
     }
     if (M->cells.empty()) {
-      delete M;
+      holder.reset();
       return fail(NOSH_EMESH, p + ": no triangles or tetrahedra");
     }
-    *out = M;
+    *out = holder.release();
     return NOSH_OK;
   }
 bad2:
-  delete M;
+  holder.reset();
   return fail(NOSH_EINVAL, p + ": inconsistent cell connectivity");
 bad:
-  delete M;
+  holder.reset();
   return fail(NOSH_EINVAL, p + ": truncated or malformed data array");
 }
 
@@ -319,9 +321,10 @@ nosh_status nosh_meshfile_get_field(const nosh_meshfile *m, const char *name, in
   return NOSH_OK;
 }
 
-nosh_status nosh_meshfile_write(const char *path, int32_t dim, int64_t n_vertices, const double *coords,
-                                int64_t n_cells, const int32_t *cells, int32_t n_fields, const char *const *names,
-                                const int32_t *ncomps, const double *const *values, int32_t binary) {
+static nosh_status meshfile_write_impl(const char *path, int32_t dim, int64_t n_vertices, const double *coords,
+                                      int64_t n_cells, const int32_t *cells, int32_t n_fields,
+                                      const char *const *names, const int32_t *ncomps, const double *const *values,
+                                      int32_t binary) {
   if (!path || !coords || !cells || (dim != 2 && dim != 3) || n_vertices <= 0 || n_cells <= 0 ||
       (n_fields > 0 && (!names || !ncomps || !values)))
     return fail(NOSH_EINVAL, "bad argument");
@@ -381,7 +384,7 @@ nosh_status nosh_meshfile_write(const char *path, int32_t dim, int64_t n_vertice
   return NOSH_OK;
 }
 
-nosh_status nosh_morton_order(int64_t n_vertices, const double *coords, int64_t *perm) {
+static nosh_status morton_order_impl(int64_t n_vertices, const double *coords, int64_t *perm) {
   if (n_vertices <= 0 || !coords || !perm) return fail(NOSH_EINVAL, "bad argument");
   double lo[3], hi[3];
   for (int d = 0; d < 3; d++) lo[d] = hi[d] = coords[d];
@@ -415,6 +418,25 @@ nosh_status nosh_morton_order(int64_t n_vertices, const double *coords, int64_t 
   std::sort(keys.begin(), keys.end());
   for (int64_t i = 0; i < n_vertices; i++) perm[i] = keys[(size_t)i].second;  // new position i <- old vertex perm[i]
   return NOSH_OK;
+}
+
+// nothing may throw across the C boundary (std::bad_alloc on a huge file, stream failures)
+#define GUARDED(call)                                   \
+  try {                                                 \
+    return call;                                        \
+  } catch (const std::exception &e) {                   \
+    return fail(NOSH_EINVAL, std::string(e.what()));    \
+  } catch (...) {                                       \
+    return fail(NOSH_EINVAL, "unknown failure");        \
+  }
+nosh_status nosh_meshfile_read(const char *path, nosh_meshfile **out) { GUARDED(meshfile_read_impl(path, out)) }
+nosh_status nosh_meshfile_write(const char *path, int32_t dim, int64_t n_vertices, const double *coords,
+                                int64_t n_cells, const int32_t *cells, int32_t n_fields, const char *const *names,
+                                const int32_t *ncomps, const double *const *values, int32_t binary) {
+  GUARDED(meshfile_write_impl(path, dim, n_vertices, coords, n_cells, cells, n_fields, names, ncomps, values, binary))
+}
+nosh_status nosh_morton_order(int64_t n_vertices, const double *coords, int64_t *perm) {
+  GUARDED(morton_order_impl(n_vertices, coords, perm))
 }
 
 }  // extern "C"
