@@ -166,12 +166,21 @@ def cpu_step(n, threads, steps, warmup):
     return {"N": N, "sec_per_step": t, "gdofs": 2.0 * N * ITERS / t / 1e9, "iters_per_s": ITERS / t}
 
 
+def host_threads():
+    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    would silently turn the CPU arm into a single-thread run; the oracle's parallel regions take an
+    explicit thread count, so ask the scheduler instead of OpenMP's default."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle
-    threads = oracle.num_threads()
+    threads = host_threads()
     steps = max(1, min(args.steps, 3))
     warm = max(1, min(args.warmup, 1))
     r = cpu_step(args.cpu_n, threads, steps, warm)
@@ -393,8 +402,7 @@ def run_b200(args):
         if newton:
             out["newton_solve"] = newton
         if not args.no_cpu_baseline and world == 1:
-            import oracle
-            th = oracle.num_threads()
+            th = host_threads()
             r = cpu_step(args.cpu_n, th, 1, 1)
             out["cpu_baseline"] = {
                 "value": r["gdofs"], "unit": "GDOF/s", "cores": th, "kind": "port",
