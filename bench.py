@@ -52,9 +52,10 @@ def parse():
                     help="sample mesh of the CPU baseline (100 -> 1.0M vertices = BASELINE.json configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--apply-reps", type=int, default=50)
-    ap.add_argument("--workload", default="minres200", choices=["minres200", "newton", "continuation"],
+    ap.add_argument("--workload", default="minres200", choices=["minres200", "newton", "continuation", "arclength"],
                     help="minres200: the default step (configs[1]); newton: one full Newton-MINRES solve per "
-                         "step (configs[2]); continuation: a mu sweep with tangent predictor (configs[3])")
+                         "step (configs[2]); continuation: a mu sweep with tangent predictor (configs[3]); "
+                         "arclength: the same sweep with LOCA's arc-length stepper (examples/conf.xml:35-75)")
     ap.add_argument("--strong", action="store_true",
                     help="keep the mesh at n^3 for any number of GPUs (configs[4]) instead of growing it")
     ap.add_argument("--lin-maxit", type=int, default=20000)
@@ -441,6 +442,17 @@ def run_solver_workload(args, ctx, mi, world, rank, local, barrier, real_stdout,
             its = int(res.total_linear_iterations)
             detail = {"newton_steps": int(res.steps), "converged": int(res.converged),
                       "minres_iterations_per_step": [int(v) for v in lin], "fnorms": [float(v) for v in fn]}
+        elif args.workload == "arclength":
+            steps = ctx.continuation_arclength({"g": 1.0, "mu": 0.0, "theta": 0.0}, "mu", psi,
+                                               initial_step_size=0.05, min_step_size=1e-7, max_step_size=0.2,
+                                               aggressiveness=2.0, max_steps=4, nl_tol=1e-8, nl_maxit=20,
+                                               lin_tol=1e-10, lin_maxit=args.lin_maxit)
+            its = sum(s.linear_iterations + s.predictor_linear_iterations for s in steps)
+            detail = {"arclength": [{"step": s.step, "mu": s.param, "step_size": s.step_size,
+                                     "dmu_ds": s.dparam_ds, "gibbs_energy": s.gibbs_energy, "norm": s.norm,
+                                     "newton_steps": s.newton_steps, "minres": s.linear_iterations,
+                                     "tangent_minres": s.predictor_linear_iterations,
+                                     "converged": s.converged} for s in steps]}
         else:
             steps = ctx.continuation({"g": 1.0, "mu": 0.0, "theta": 0.0}, "mu", 0.05, 4, psi, 1e-8, 20, 1e-10,
                                      args.lin_maxit)
