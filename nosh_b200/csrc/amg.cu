@@ -196,14 +196,23 @@ __global__ void k_l0_fill(const int32_t *rowptr, const int32_t *col, const int32
     o++;
   }
 }
-// level 0, once per hierarchy: off-diagonal absolute row sums of K (both scalar rows of a complex block
-// row have the same one)
-__global__ void k_l0_offsum(const int32_t *rowptr, const int32_t *col, const B22 *val, int64_t n, double *offsum) {
+// level 0, per state: off-diagonal absolute row sums of the owned block of K, straight from the SELL-32
+// storage (both scalar rows of a complex block row have the same one).  They depend on mu through
+// |cos a| + |sin a|, so they are refreshed with the diagonal whenever the matrix changes -- a hierarchy
+// kept across a continuation run must not smooth with stale bounds.
+__global__ void k_l0_offsum(const int32_t *slice_off, const int32_t *col, const double2 *K, int64_t No,
+                            double *offsum) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= No) return;
+  const int base = slice_off[i >> 5], end = slice_off[(i >> 5) + 1];
   double s = 0.0;
-  for (int p = rowptr[i]; p < rowptr[i + 1]; p++)
-    if (col[p] != i) s += fabs(val[p].a) + fabs(val[p].b);
+  for (int p = base + (int)(i & 31); p < end; p += 32) {
+    const int c = col[p];
+    if (c != i && c < No) {
+      const double2 k = K[p];
+      s += fabs(k.x) + fabs(k.y);
+    }
+  }
   offsum[i] = s;
 }
 // level 0, per state: 1 / diagonal and 1 / absolute row sum of the regularised KEO
@@ -840,6 +849,7 @@ double estimate_lambda(Ctx *ctx, AmgLevel &L, int lev, DBuf<double> &scratch) {
 }
 
 void l0_refresh_diag(Ctx *ctx, AmgLevel &L) {
+  ALAUNCH(ctx, k_l0_offsum, ctx->No, ctx->slice_off.p, ctx->col.p, ctx->Kval.p, ctx->No, L.offsum.p);
   ALAUNCH(ctx, k_l0_dinv, ctx->No, ctx->Kval.p, ctx->diag_slot.p, ctx->pd0.p, ctx->pd1.p, L.offsum.p, ctx->No,
           L.dinv.p, L.sinv.p);
 }
@@ -1027,7 +1037,6 @@ void build_hierarchy(Ctx *ctx) {
   L->dinv.alloc(No > 0 ? No : 1);
   L->sinv.alloc(No > 0 ? No : 1);
   L->offsum.alloc(No > 0 ? No : 1);
-  ALAUNCH(ctx, k_l0_offsum, No, L->rowptr.p, L->col.p, L->val.p, No, L->offsum.p);
   l0_refresh_diag(ctx, *L);
   alloc_level_vectors(ctx, *L, 0);
   tick("level-0 block CSR", 0);

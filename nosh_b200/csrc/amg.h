@@ -23,7 +23,7 @@ struct AmgLevel {
   DBuf<double2> dinv;  // 1 / point diagonal (prolongator smoothing, power iteration)
   DBuf<double2> sinv;  // 1 / absolute row sum: the l1-Jacobi scaling of the smoother, lambda_max(S^-1 A) <= 1
   double lam = 0.0;    // lambda_max(D^-1 A): power-iteration estimate (prolongator damping)
-  DBuf<double> offsum;  // level 0: sum_{j != i} (|Re K_ij| + |Im K_ij|), state independent
+  DBuf<double> offsum;  // level 0: sum_{j != i} (|Re K_ij| + |Im K_ij|) over the owned columns, per state
   double omega = 0.0;  // prolongator damping actually used
   // transfer operators to the next (coarser) level
   int64_t nc = 0;

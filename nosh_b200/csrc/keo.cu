@@ -270,6 +270,7 @@ void keo_fill(Ctx *ctx, int np, const char *const *names, const double *values, 
   ctx->keo_filled = true;
   ctx->keo_mu = mu;
   ctx->keo_theta = theta;
+  ctx->keoreg_version++;  // the regularised KEO shares these values: a kept AMG hierarchy refreshes its finest level
 }
 
 static int dmode_of(Ctx *ctx, const char *dname) {

@@ -239,6 +239,18 @@ def test_reuse_none_rebuilds(nb, orc):
                                 shape=Pm.shape))
     assert relerr(y_full, H.vcycle(b)) <= TOL
     assert relerr(y_full, y0) > 1e-6
+    # ... and a new mu as in a continuation run: K itself changes, the kept hierarchy must refresh the
+    # finest level's diagonal AND its l1 row sums (|cos a| + |sin a| depends on mu)
+    params3 = dict(params, mu=2.5)
+    ctx.keoreg_rebuild(params3, x2)
+    y_mu = ctx.keoreg_apply(b)
+    H.update_fine(sp.csr_matrix((P.keoreg_fill(params3["mu"], params3["g"], x2), P.cols, P.rowptr),
+                                shape=Pm.shape))
+    assert relerr(y_mu, H.vcycle(b)) <= TOL
+    assert relerr(y_mu, y_full) > 1e-6
+    ctx.keoreg_rebuild(params, x2)
+    H.update_fine(sp.csr_matrix((P.keoreg_fill(params["mu"], params["g"], x2), P.cols, P.rowptr),
+                                shape=Pm.shape))
     # reuse = none: a fresh hierarchy for the new matrix
     from oracle import amg
     ctx.amg_set_options(reuse=nb.AMG_REUSE_NONE)
