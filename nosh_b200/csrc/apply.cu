@@ -1,6 +1,8 @@
 // apply.cu -- see apply.cuh
 #include "apply.cuh"
 
+#include "kmath.cuh"
+
 namespace nosh {
 
 namespace {
@@ -8,10 +10,7 @@ namespace {
 template <int EPI>
 __device__ __forceinline__ double2 epilogue(double2 acc, double2 xi, int64_t i, const ApplyArgs &A) {
   if (EPI == EPI_DIAG) {
-    const double2 d0 = ld_stream2(A.d0 + i);
-    const double d1 = __ldg(A.d1 + i);
-    acc.x += d0.x * xi.x + d1 * xi.y;
-    acc.y += d1 * xi.x + d0.y * xi.y;
+    acc = diag_epilogue(acc, ld_stream2(A.d0 + i), __ldg(A.d1 + i), xi);
   } else if (EPI == EPI_F) {
     const double al = A.cv[i] * A.thick[i] * (A.V[i] + A.g * (xi.x * xi.x + xi.y * xi.y));
     acc.x += al * xi.x;
@@ -26,12 +25,6 @@ __device__ __forceinline__ double2 epilogue(double2 acc, double2 xi, int64_t i, 
     acc.y += al * xi.y;
   }
   return acc;
-}
-
-// complex multiply-accumulate  acc += v * x
-__device__ __forceinline__ void cfma(double2 &acc, double2 v, double2 x) {
-  acc.x += v.x * x.x - v.y * x.y;
-  acc.y += v.x * x.y + v.y * x.x;
 }
 
 // AMG smoother tails on the finest level (amg.cu): yi = A x on entry
@@ -102,8 +95,7 @@ __global__ void __launch_bounds__(CHUNK, MINB) k_apply_sell(const ApplyArgs A) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
           if (FUSE == FUSE_MINRES) {
-            xv[u].x *= scale;
-            xv[u].y *= scale;
+            xv[u] = scaled(xv[u], scale);
           }
           cfma(acc, v[u], xv[u]);
         }
@@ -122,8 +114,7 @@ __global__ void __launch_bounds__(CHUNK, MINB) k_apply_sell(const ApplyArgs A) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
           if (FUSE == FUSE_MINRES) {
-            xv[u].x *= scale;
-            xv[u].y *= scale;
+            xv[u] = scaled(xv[u], scale);
           }
           cfma(acc, v[u], xv[u]);
         }
@@ -134,8 +125,7 @@ __global__ void __launch_bounds__(CHUNK, MINB) k_apply_sell(const ApplyArgs A) {
       const double2 v = ld_stream2(A.val + p);
       double2 xv = __ldg(A.x + c);
       if (FUSE == FUSE_MINRES) {
-        xv.x *= scale;
-        xv.y *= scale;
+        xv = scaled(xv, scale);
       }
       cfma(acc, v, xv);
     }
@@ -144,8 +134,7 @@ __global__ void __launch_bounds__(CHUNK, MINB) k_apply_sell(const ApplyArgs A) {
   if (row < A.No) {
     double2 xi = __ldg(A.x + row);
     if (FUSE == FUSE_MINRES) {
-      xi.x *= scale;
-      xi.y *= scale;
+      xi = scaled(xi, scale);
     }
     double2 yi = epilogue<EPI>(acc, xi, row, A);
     if (FUSE == FUSE_AXPBY) {
@@ -159,13 +148,11 @@ __global__ void __launch_bounds__(CHUNK, MINB) k_apply_sell(const ApplyArgs A) {
     } else if (FUSE == FUSE_MINRES) {
       const double f = A.st->f_r1;
       if (f != 0.0) {
-        const double2 r1 = ld_stream2(A.r1 + row);
-        yi.x -= f * r1.x;
-        yi.y -= f * r1.y;
+        yi = sub_scaled(yi, f, ld_stream2(A.r1 + row));
       }
-      contrib = xi.x * yi.x + xi.y * yi.y;
+      contrib = cdot(xi, yi);
     } else if (FUSE == FUSE_CG) {
-      contrib = xi.x * yi.x + xi.y * yi.y;
+      contrib = cdot(xi, yi);
     } else if (FUSE == FUSE_RESID || FUSE == FUSE_CHEB) {
       yi = smoother_tail<FUSE>(yi, xi, row, A);
     }
@@ -202,8 +189,7 @@ __global__ void __launch_bounds__(CHUNK, 2) k_apply_csr(const ApplyArgs A) {
         const double2 v = ld_stream2(A.val + p);
         double2 xv = __ldg(A.x + c);
         if (FUSE == FUSE_MINRES) {
-          xv.x *= scale;
-          xv.y *= scale;
+          xv = scaled(xv, scale);
         }
         cfma(acc, v, xv);
       }
@@ -216,8 +202,7 @@ __global__ void __launch_bounds__(CHUNK, 2) k_apply_csr(const ApplyArgs A) {
     if (sl == 0 && row < A.No) {
       double2 xi = __ldg(A.x + row);
       if (FUSE == FUSE_MINRES) {
-        xi.x *= scale;
-        xi.y *= scale;
+        xi = scaled(xi, scale);
       }
       double2 yi = epilogue<EPI>(acc, xi, row, A);
       if (FUSE == FUSE_AXPBY) {
@@ -231,13 +216,11 @@ __global__ void __launch_bounds__(CHUNK, 2) k_apply_csr(const ApplyArgs A) {
       } else if (FUSE == FUSE_MINRES) {
         const double f = A.st->f_r1;
         if (f != 0.0) {
-          const double2 r1 = ld_stream2(A.r1 + row);
-          yi.x -= f * r1.x;
-          yi.y -= f * r1.y;
+          yi = sub_scaled(yi, f, ld_stream2(A.r1 + row));
         }
-        contrib += xi.x * yi.x + xi.y * yi.y;
+        contrib += cdot(xi, yi);
       } else if (FUSE == FUSE_CG) {
-        contrib += xi.x * yi.x + xi.y * yi.y;
+        contrib += cdot(xi, yi);
       } else if (FUSE == FUSE_RESID || FUSE == FUSE_CHEB) {
         yi = smoother_tail<FUSE>(yi, xi, row, A);
       }

@@ -144,6 +144,7 @@ nosh_status nosh_ctx_create(int device, void *stream, nosh_ctx **out) {
     const long long g = atoll(e);
     if (g >= CHUNK && g % CHUNK == 0) ctx->group_vertices = g;
   }
+  if (const char *e = getenv("NOSH_B200_PERSISTENT_MINRES")) ctx->persistent_minres = atoi(e) != 0;
   *out = ctx;
   return NOSH_OK;
 }
@@ -827,6 +828,8 @@ nosh_status nosh_ctx_set_tuning(nosh_ctx *ctx, const char *key, int value) {
   if (strcmp(key, "apply_variant") == 0) {
     if (value < 0 || value > 7) NOSH_THROW(NOSH_EINVAL, "apply_variant must be in [0, 7]");
     ctx->apply_variant = value;
+  } else if (strcmp(key, "persistent_minres") == 0) {
+    ctx->persistent_minres = value != 0;
   } else {
     NOSH_THROW(NOSH_EKEY, "unknown tuning key \"%s\"", key);
   }

@@ -17,6 +17,8 @@
 // any number of GPUs.
 #include "krylov.h"
 
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "amg.h"
@@ -24,6 +26,7 @@
 #include "comm.h"
 #include "reduce.cuh"
 #include "keo.h"
+#include "kmath.cuh"
 
 namespace nosh {
 
@@ -37,7 +40,6 @@ namespace {
   } while (0)
 
 // ---- chunked vector kernels: one CTA (256 threads) per CHUNK = 512 vertices ------------------
-__device__ __forceinline__ double cdot(double2 a, double2 b) { return a.x * b.x + a.y * b.y; }
 
 __global__ void __launch_bounds__(TPB) k_dot(const double2 *x, const double2 *y, int64_t No, double *partials,
         const FinArgs fin) {
@@ -117,12 +119,12 @@ __global__ void __launch_bounds__(TPB) k_minres_B(const KrylovState *st, int hos
   if (i1 < No) { p1 = ld_stream2(p + i1); q1 = ld_stream2(r2 + i1); }
   double c = 0.0;
   if (i0 < No) {
-    const double2 r = make_double2(p0.x - f * q0.x, p0.y - f * q0.y);
+    const double2 r = sub_scaled(p0, f, q0);
     rnew[i0] = r;
     c = cdot(r, r);
   }
   if (i1 < No) {
-    const double2 r = make_double2(p1.x - f * q1.x, p1.y - f * q1.y);
+    const double2 r = sub_scaled(p1, f, q1);
     rnew[i1] = r;
     c += cdot(r, r);
   }
@@ -141,14 +143,9 @@ __global__ void __launch_bounds__(TPB) k_minres_C(const KrylovState *st, int hos
     const int64_t i = (int64_t)blockIdx.x * CHUNK + threadIdx.x + h * TPB;
     if (i < No) {
       const double2 r = ld_stream2(rcur + i), a = ld_stream2(w1 + i), b = ld_stream2(w2 + i);
-      double2 xx = x[i];
-      double2 w;
-      w.x = ((r.x * ib - oe * a.x) - de * b.x) * ig;
-      w.y = ((r.y * ib - oe * a.y) - de * b.y) * ig;
+      const double2 w = minres_w(r, a, b, ib, oe, de, ig);
       wnew[i] = w;
-      xx.x += ph * w.x;
-      xx.y += ph * w.y;
-      x[i] = xx;
+      x[i] = axpy2(ph, w, x[i]);
     }
   }
 }
@@ -274,6 +271,185 @@ __global__ void __launch_bounds__(1024) k_finalize(const FinArgs F) {
   if (fin_is_iterative(F.what) && (F.st->done || F.st->iter != F.host_iter - 1)) return;
   __shared__ double sm[32];
   finalize_levels<true>(F, sm);
+}
+
+// -------------------------------------------------------------------------------------------------------
+// Persistent MINRES (one GPU, no preconditioner, SELL-32): the whole iteration loop in ONE cooperative
+// launch.  CTA c owns the chunks c, c + grid, ... in every phase, so the element-wise phases (B, C) need no
+// grid-wide ordering; grid.sync() separates the SpMV gather from the writes of r and the two reductions:
+//     A | sync | group sums | sync | alpha (every CTA, redundantly) . B | sync | group sums | sync | beta . C
+// Same chunk partials, same tree, same scalar recurrences as the multi-launch path => bit-identical
+// iterates; what is saved are 5 launches + 2 one-CTA finalize kernels per iteration.
+// -------------------------------------------------------------------------------------------------------
+struct PersistArgs {
+  ApplyArgs A;  // matrix and diagonal pointers only
+  double2 *R0, *R1, *Pv, *W0, *W1, *W2, *X;
+  KrylovState *st;
+  double *partials, *gsums, *hist;
+  int64_t n_chunks, n_groups;
+  int cpg, maxit;
+};
+
+__device__ __forceinline__ void persist_level2(const PersistArgs &P) {
+  const int l = threadIdx.x & 31;
+  const int64_t gw = (int64_t)blockIdx.x * (CHUNK / 32) + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * (CHUNK / 32);
+  const int per = (P.cpg + 31) / 32;
+  for (int64_t g = gw; g < P.n_groups; g += nw) {
+    const int64_t base = g * P.cpg;
+    double s = 0.0;
+    for (int t = 0; t < per; t++) {
+      const int k = l * per + t;
+      if (k < P.cpg && base + k < P.n_chunks) s += __ldcg(P.partials + base + k);
+    }
+    s = warp_sum(s);
+    if (l == 0) P.gsums[g] = s;
+  }
+}
+// every CTA: total of the group sums (the level-3 tree of finalize_levels); valid in thread 0
+__device__ __forceinline__ double persist_level3(const PersistArgs &P, double *sm) {
+  const int nw = CHUNK / 32, w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  for (int seg = w; seg < 32; seg += nw) {
+    const int i = 32 * seg + l;
+    double v = i < P.n_groups ? __ldcg(P.gsums + i) : 0.0;
+    v = warp_sum(v);
+    if (l == 0) sm[seg] = v;
+  }
+  __syncthreads();
+  double t = 0.0;
+  if (w == 0) {
+    t = sm[l];
+    t = warp_sum(t);
+  }
+  __syncthreads();
+  return t;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent(const PersistArgs P) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ KrylovState s_st;
+  __shared__ double red[32], sm[32];
+  __shared__ double pair[CHUNK];
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) s_st = *P.st;
+  __syncthreads();
+  FinArgs F;
+  F.st = &s_st;
+  F.hist = blockIdx.x == 0 ? P.hist : nullptr;
+  F.out = nullptr;
+  F.tol = s_st.tol;
+  F.maxit = s_st.maxit;
+  for (int h = 1; h <= P.maxit; h++) {
+    if (s_st.done) break;  // identical in every CTA
+    double2 *rcur = (h & 1) ? P.R0 : P.R1, *rprev = (h & 1) ? P.R1 : P.R0;
+    double2 *w1 = h % 3 == 0 ? P.W1 : (h % 3 == 1 ? P.W2 : P.W0);   // W[(h + 1) % 3]
+    double2 *w2 = h % 3 == 0 ? P.W2 : (h % 3 == 1 ? P.W0 : P.W1);   // W[(h + 2) % 3]
+    double2 *wn = h % 3 == 0 ? P.W0 : (h % 3 == 1 ? P.W1 : P.W2);   // W[h % 3]
+    // ---- A: y = J (r_h / beta_h) - (beta_h / beta_{h-1}) r_{h-1}, chunk partials of <v, y> ----
+    {
+      const double scale = s_st.inv_beta, f = s_st.f_r1;
+      for (int64_t chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
+        const int64_t row = chunk * CHUNK + tid;
+        const int64_t slice = row >> 5;
+        double2 acc = make_double2(0.0, 0.0);
+        if (slice < P.A.nslices) {
+          int p = __ldg(P.A.slice_off + slice) + lane;
+          const int pend = __ldg(P.A.slice_off + slice + 1);
+          for (; p + 96 < pend; p += 128) {
+            int c[4];
+            double2 v[4], xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) c[u] = ld_stream_i32(P.A.col + p + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = ld_stream2(P.A.val + p + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) xv[u] = rcur[c[u]];  // written in this launch: coherent loads
+#pragma unroll
+            for (int u = 0; u < 4; u++) cfma(acc, v[u], scaled(xv[u], scale));
+          }
+          for (; p < pend; p += 32) {
+            const int c = ld_stream_i32(P.A.col + p);
+            const double2 v = ld_stream2(P.A.val + p);
+            cfma(acc, v, scaled(rcur[c], scale));
+          }
+        }
+        double contrib = 0.0;
+        if (row < P.A.No) {
+          const double2 xi = scaled(rcur[row], scale);
+          double2 yi = acc;
+          if (EPI == EPI_DIAG) yi = diag_epilogue(acc, ld_stream2(P.A.d0 + row), __ldg(P.A.d1 + row), xi);
+          if (f != 0.0) yi = sub_scaled(yi, f, rprev[row]);
+          contrib = cdot(xi, yi);
+          P.Pv[row] = yi;
+        }
+        const double s = block_sum<CHUNK / 32>(contrib, red);
+        if (tid == 0) P.partials[chunk] = s;
+      }
+    }
+    grid.sync();
+    persist_level2(P);
+    grid.sync();
+    {
+      const double total = persist_level3(P, sm);
+      if (tid == 0) {
+        F.what = FIN_MINRES_ALPHA;
+        fin_scalars(F, total);
+      }
+      __syncthreads();
+    }
+    // ---- B: r_{h+1} = y - (alpha_h / beta_h) r_h (over r_{h-1}), chunk partials of <r_{h+1}, r_{h+1}> ----
+    {
+      const double f = s_st.f_r2;
+      for (int64_t chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
+        const int64_t i = chunk * CHUNK + tid;
+        double c = 0.0;
+        if (i < P.A.No) {
+          const double2 r = sub_scaled(P.Pv[i], f, rcur[i]);
+          rprev[i] = r;
+          c = cdot(r, r);
+        }
+        // the multi-launch kernel sums vertex t and t + 256 in one thread, then 8 warps: same tree here
+        pair[tid] = c;
+        __syncthreads();
+        const double c2 = tid < TPB ? pair[tid] + pair[tid + TPB] : 0.0;
+        double v = warp_sum(c2);
+        if (lane == 0) red[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) {
+          double s = 0.0;
+#pragma unroll
+          for (int q8 = 0; q8 < TPB / 32; q8++) s += red[q8];
+          P.partials[chunk] = s;
+        }
+        __syncthreads();
+      }
+    }
+    grid.sync();
+    persist_level2(P);
+    grid.sync();
+    {
+      const double total = persist_level3(P, sm);
+      if (tid == 0) {
+        F.what = FIN_MINRES_BETA;
+        fin_scalars(F, total);
+      }
+      __syncthreads();
+    }
+    // ---- C: w_h = (v_h - eps w_{h-2} - delta w_{h-1}) / gamma, x += phi w_h (only if the iteration completed) ----
+    if (s_st.iter == h) {
+      const double ib = s_st.inv_beta_prev, oe = s_st.oldeps, de = s_st.delta, ig = s_st.inv_gamma, ph = s_st.phi;
+      for (int64_t chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
+        const int64_t i = chunk * CHUNK + tid;
+        if (i < P.A.No) {
+          const double2 w = minres_w(rcur[i], w1[i], w2[i], ib, oe, de, ig);
+          wn[i] = w;
+          P.X[i] = axpy2(ph, w, P.X[i]);
+        }
+      }
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0) *P.st = s_st;
 }
 
 // Reduction descriptor.  Default: finalize_launch() runs the one-CTA k_finalize kernel after the
@@ -506,6 +682,51 @@ void minres_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, dou
   finalize_launch(ctx, F);
   KrylovState hs;
   int check = 4;
+  if (ctx->nranks == 1 && !pc && ctx->layout == NOSH_LAYOUT_SELL32 && ctx->persistent_minres && grid > 0 &&
+      (epi == EPI_DIAG || epi == EPI_NONE) && !F.counter) {
+    // the whole loop in one cooperative launch (k_minres_persistent)
+    PersistArgs PA;
+    memset(&PA, 0, sizeof(PA));
+    PA.A = A;
+    PA.R0 = Z[0];
+    PA.R1 = Z[1];
+    PA.Pv = Pv;
+    PA.W0 = W[0];
+    PA.W1 = W[1];
+    PA.W2 = W[2];
+    PA.X = X;
+    PA.st = ctx->kstate.p;
+    PA.partials = ctx->partials.p;
+    PA.gsums = ctx->group_sums.p;
+    PA.hist = ctx->hist.p;
+    PA.n_chunks = ctx->n_chunks;
+    PA.n_groups = ctx->n_groups_global;
+    PA.cpg = ctx->chunks_per_group;
+    PA.maxit = maxit;
+    const void *fn = epi == EPI_DIAG ? (const void *)k_minres_persistent<EPI_DIAG> : (const void *)k_minres_persistent<EPI_NONE>;
+    if (ctx->persist_grid == 0) {
+      int per_sm = 0, sms = 0;
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minres_persistent<EPI_DIAG>, CHUNK, 0));
+      CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+      ctx->persist_grid = per_sm * sms;
+    }
+    const unsigned pgrid = (unsigned)std::min<int64_t>(ctx->persist_grid, ctx->n_chunks);
+    void *kargs[] = {&PA};
+    CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(pgrid), dim3(CHUNK), kargs, 0, ctx->stream));
+    ctx->launches++;
+    poll_done(ctx, &hs);
+    if (res) {
+      res->iterations = hs.iter;
+      res->converged = hs.converged;
+      res->relres = hs.relres;
+    }
+    if (hist_host) {
+      CUDA_CHECK(cudaMemcpyAsync(hist_host, ctx->hist.p, sizeof(double) * (hs.iter + 1), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    return;
+  }
   // Multi-GPU schedule (same arithmetic, two streams): the halo of r_h travels on stream2
   // while the interior chunks of A(h) run; C(h-1) also runs on stream2, next to A(h) and the
   // alpha all-reduce, and must only be finished before B(h) overwrites the buffer it reads.

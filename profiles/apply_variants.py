@@ -53,4 +53,15 @@ for v in range(8):
     out.append({"variant": v, "what": DESC[v], "apply_ms": ms, "apply_gbs": bytes_apply / ms / 1e6,
                 "minres_ms_per_iteration": ms_minres, "bit_identical_to_variant_0": same})
     print(out[-1], file=sys.stderr)
-print(json.dumps({"n": a.n, "vertices": No, "bytes_per_apply": bytes_apply, "variants": out}))
+# the MINRES loop as one cooperative launch (krylov.cu k_minres_persistent) vs five launches per iteration
+ctx.set_tuning("apply_variant", 0)
+loop = {}
+for mode in (0, 1, 0, 1):
+    ctx.set_tuning("persistent_minres", mode)
+    ctx.minres(b, x, tol=0.0, maxit=50)
+    ctx.timer_start()
+    ctx.minres(b, x, tol=0.0, maxit=400)
+    loop.setdefault("persistent" if mode else "multi_launch", []).append(ctx.timer_stop() / 400)
+    print(mode, loop, file=sys.stderr)
+print(json.dumps({"n": a.n, "vertices": No, "bytes_per_apply": bytes_apply, "variants": out,
+                  "minres_ms_per_iteration": loop}))

@@ -20,6 +20,9 @@ ap.add_argument("--n", "--mesh-n", dest="n", type=int, default=100)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--layout", default="sell32")
 ap.add_argument("--precond", default="none", choices=["none", "amg"])
+ap.add_argument("--persistent", type=int, default=0,
+                help="0: the multi-launch MINRES loop (one launch per phase: readable launch lists); 1: the default "
+                     "one-launch cooperative kernel")
 ap.add_argument("--amg-degree", type=int, default=1)
 a = ap.parse_args()
 
@@ -37,6 +40,7 @@ x = torch.empty_like(b)
 par = {"g": 1.0, "mu": 1.0, "theta": 0.0}
 
 
+ctx.set_tuning("persistent_minres", a.persistent)
 if a.precond == "amg":
     ctx.amg_set_options(degree=a.amg_degree)
 

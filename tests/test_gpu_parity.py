@@ -476,3 +476,38 @@ def test_arclength_continuation(nb, orc):
     with pytest.raises(ValueError):
         ctx.continuation_arclength({"g": 1.0, "mu": 0.0}, "mu", xg, initial_step_size=0.0)
     ctx.close()
+
+
+@pytest.mark.parametrize("n", [7, 16])
+def test_persistent_minres_is_bit_identical(nb, orc, n):
+    """The one-launch cooperative MINRES (tuning key "persistent_minres") against the multi-launch loop:
+    same chunk partials, same reduction tree, same recurrences => identical bits, for a converging solve, a
+    solve cut off by maxit, the KEO operator, and a zero right-hand side."""
+    coords, cells = orc.meshgen.tetgrid(n)
+    ctx, P, psi = make_pair(nb, orc, coords, cells, 1, group=512)
+    x = orc.meshgen.random_state(P.N, 5)
+    b = orc.meshgen.random_state(P.N, 6)
+    par = {"g": 1.0, "mu": 0.3}
+    ctx.jac_rebuild(par, x)
+    runs = {}
+    for mode in (0, 1):
+        ctx.set_tuning("persistent_minres", mode)
+        l0 = ctx.launch_count()
+        runs[mode] = [ctx.minres(b, tol=1e-10, maxit=3000, history=True),
+                      ctx.minres(b, tol=1e-10, maxit=17, history=True),
+                      ctx.minres(b, tol=1e-8, maxit=3000, history=True, op=nb.OP_KEO),
+                      ctx.minres(np.zeros_like(b), tol=1e-10, maxit=50, history=True)]
+        runs[mode].append(ctx.launch_count() - l0)
+    for (xa, ra, ha), (xb, rb, hb) in zip(runs[0][:4], runs[1][:4]):
+        assert ra.iterations == rb.iterations and ra.converged == rb.converged
+        assert ra.relres == rb.relres
+        assert np.array_equal(ha, hb)
+        assert np.array_equal(xa, xb)
+    assert runs[0][0][1].converged == 1 and runs[0][1][1].iterations == 17 and runs[0][3][1].iterations == 0
+    assert runs[1][4] < runs[0][4] / 20          # a handful of launches instead of five per iteration
+    # and against the oracle
+    P.keo_fill(par["mu"])
+    P.jac_rebuild(par["g"], x)
+    xo, ito, _ = P.krylov(b, 1e-10, 3000)
+    assert runs[1][0][1].iterations == ito and relerr(runs[1][0][0], xo) <= 1e-8
+    ctx.close()
