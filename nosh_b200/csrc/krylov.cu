@@ -683,7 +683,7 @@ void minres_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, dou
   KrylovState hs;
   int check = 4;
   if (ctx->nranks == 1 && !pc && ctx->layout == NOSH_LAYOUT_SELL32 && ctx->persistent_minres && grid > 0 &&
-      (epi == EPI_DIAG || epi == EPI_NONE) && !F.counter) {
+      (epi == EPI_DIAG || epi == EPI_NONE) && !F.counter && ctx->persist_grid >= 0) {
     // the whole loop in one cooperative launch (k_minres_persistent)
     PersistArgs PA;
     memset(&PA, 0, sizeof(PA));
@@ -705,11 +705,14 @@ void minres_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, dou
     PA.maxit = maxit;
     const void *fn = epi == EPI_DIAG ? (const void *)k_minres_persistent<EPI_DIAG> : (const void *)k_minres_persistent<EPI_NONE>;
     if (ctx->persist_grid == 0) {
-      int per_sm = 0, sms = 0;
+      int per_sm = 0, sms = 0, coop = 0;
+      CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
       CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minres_persistent<EPI_DIAG>, CHUNK, 0));
       CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-      ctx->persist_grid = per_sm * sms;
+      ctx->persist_grid = coop ? per_sm * sms : -1;
     }
+    if (ctx->persist_grid <= 0) goto multi_launch;  // no cooperative launch on this device / configuration
+    {
     const unsigned pgrid = (unsigned)std::min<int64_t>(ctx->persist_grid, ctx->n_chunks);
     void *kargs[] = {&PA};
     CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(pgrid), dim3(CHUNK), kargs, 0, ctx->stream));
@@ -726,7 +729,9 @@ void minres_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, dou
       CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     }
     return;
+    }
   }
+multi_launch:
   // Multi-GPU schedule (same arithmetic, two streams): the halo of r_h travels on stream2
   // while the interior chunks of A(h) run; C(h-1) also runs on stream2, next to A(h) and the
   // alpha all-reduce, and must only be finished before B(h) overwrites the buffer it reads.
