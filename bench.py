@@ -63,6 +63,7 @@ def parse():
                     help="newton / continuation workloads: preconditioner of the MINRES solves (amg = one V-cycle "
                          "on the regularised KEO, keo_regularized::apply)")
     ap.add_argument("--amg-degree", type=int, default=1)
+    ap.add_argument("--amg-coarse-degree", type=int, default=2)
     ap.add_argument("--no-newton", action="store_true",
                     help="default workload: skip the extra keys that report one full Newton-MINRES solve of the "
                          "same mesh (BASELINE.json configs[2]) with and without the AMG preconditioner")
@@ -431,7 +432,7 @@ def run_solver_workload(args, ctx, mi, world, rank, local, barrier, real_stdout,
     results = []
     import nosh_b200
     if args.precond == "amg":
-        ctx.amg_set_options(degree=args.amg_degree)
+        ctx.amg_set_options(degree=args.amg_degree, coarse_degree=args.amg_coarse_degree)
         ctx.set_preconditioner(nosh_b200.PREC_KEOREG_AMG)
     for k in range(args.warmup + args.steps):
         psi = psi0.clone()
@@ -470,7 +471,7 @@ def run_solver_workload(args, ctx, mi, world, rank, local, barrier, real_stdout,
         ms = e0.elapsed_time(e1)
         if args.precond == "amg":
             ai = ctx.amg_info()
-            detail["amg"] = {"levels": int(ai.levels), "degree": int(ai.degree),
+            detail["amg"] = {"levels": int(ai.levels), "degree": int(ai.degree), "coarse_degree": int(ai.coarse_degree),
                              "nodes": [int(ai.nodes[l]) for l in range(ai.levels)],
                              "blocks": [int(ai.blocks[l]) for l in range(ai.levels)],
                              "prolongator_blocks": [int(ai.p_blocks[l]) for l in range(ai.levels - 1)],

@@ -237,17 +237,20 @@ NOSH_API nosh_status nosh_keoreg_apply(nosh_ctx *ctx, const double *X, int64_t l
                                        double beta);
 
 /* AMG options (before the hierarchy is built; changing them drops it): Chebyshev degree of the
- * pre-/post-smoother (>= 1; 1 = damped Jacobi), number of nodes at which coarsening stops and a
- * dense inverse is used (<= 4096), maximum number of levels, reuse policy.  Values <= 0 (reuse
- * < 0) keep the current setting.  Defaults: 1, 512, 10, FULL. */
-NOSH_API nosh_status nosh_amg_set_options(nosh_ctx *ctx, int degree, int coarse_max, int max_levels,
-                                          int reuse);
+ * pre-/post-smoother on the finest level (>= 1; 1 = damped l1-Jacobi) and on the coarse levels,
+ * number of nodes at which coarsening stops and a dense inverse is used (<= 4096), maximum number
+ * of levels, reuse policy.  Values <= 0 (reuse < 0) keep the current setting.
+ * Defaults: 1, 2, 512, 10, FULL. */
+NOSH_API nosh_status nosh_amg_set_options(nosh_ctx *ctx, int degree, int coarse_degree, int coarse_max,
+                                          int max_levels, int reuse);
 /* (re)build the hierarchy now for the current regularised KEO */
 NOSH_API nosh_status nosh_amg_setup(nosh_ctx *ctx);
 #define NOSH_AMG_MAX_LEVELS 16
 typedef struct {
   int32_t levels;
-  int32_t degree;
+  int32_t degree;        /* finest level */
+  int32_t coarse_degree; /* levels >= 1 */
+  int32_t reserved;
   int64_t nodes[NOSH_AMG_MAX_LEVELS];     /* block rows per level */
   int64_t blocks[NOSH_AMG_MAX_LEVELS];    /* 2x2 blocks per level (level 0: complex blocks of the owned columns) */
   int64_t p_blocks[NOSH_AMG_MAX_LEVELS];  /* blocks of the prolongator from level l+1 to l */

@@ -41,7 +41,8 @@ class ContinuationStep(C.Structure):
 
 
 class AmgInfo(C.Structure):
-    _fields_ = [("levels", C.c_int32), ("degree", C.c_int32), ("nodes", C.c_int64 * AMG_MAX_LEVELS),
+    _fields_ = [("levels", C.c_int32), ("degree", C.c_int32), ("coarse_degree", C.c_int32), ("reserved", C.c_int32),
+                ("nodes", C.c_int64 * AMG_MAX_LEVELS),
                 ("blocks", C.c_int64 * AMG_MAX_LEVELS), ("p_blocks", C.c_int64 * AMG_MAX_LEVELS),
                 ("lambda_max", C.c_double * AMG_MAX_LEVELS), ("setup_seconds", C.c_double)]
 
@@ -136,7 +137,7 @@ def lib():
         "nosh_keoreg_matrix_apply": (C.c_int, [vp, vp, i64, vp, i64, C.c_int]),
         "nosh_keoreg_get_diags": (C.c_int, [vp, vp, vp]),
         "nosh_keoreg_apply": (C.c_int, [vp, vp, i64, vp, i64, C.c_int, C.c_int, dbl, dbl]),
-        "nosh_amg_set_options": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "nosh_amg_set_options": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
         "nosh_amg_setup": (C.c_int, [vp]),
         "nosh_amg_info": (C.c_int, [vp, C.POINTER(AmgInfo)]),
         "nosh_amg_get_aggregates": (C.c_int, [vp, C.c_int, vp]),

@@ -368,8 +368,8 @@ class Context:
         return Y
 
     # ---- AMG hierarchy ------------------------------------------------------------------
-    def amg_set_options(self, degree=0, coarse_max=0, max_levels=0, reuse=-1):
-        self._ck(self.L.nosh_amg_set_options(self.h, int(degree), int(coarse_max), int(max_levels),
+    def amg_set_options(self, degree=0, coarse_degree=0, coarse_max=0, max_levels=0, reuse=-1):
+        self._ck(self.L.nosh_amg_set_options(self.h, int(degree), int(coarse_degree), int(coarse_max), int(max_levels),
                                              int(reuse)))
 
     def amg_setup(self):

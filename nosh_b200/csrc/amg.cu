@@ -13,7 +13,8 @@
 //                 to the oracle's sequential greedy sweep
 //   P           : (I - 4/3 / lambda_max D^-1 A) P0,   A_c = P^T A P   by expand-sort-compress SpGEMM
 //                 (stable radix sort => fixed summation order => run-to-run identical bits)
-//   smoother    : Chebyshev of degree `amg_degree` on S^-1 A over [1/20, 1], S = absolute row sums (l1-Jacobi
+//   smoother    : Chebyshev of degree `amg_degree` (finest level, default 1) / `amg_coarse_degree` (coarse
+//                 levels, default 2) on S^-1 A over [1/20, 1], S = absolute row sums (l1-Jacobi
 //                 scaling: lambda_max(S^-1 A) <= 1 is a true bound row by row, so the V-cycle stays positive
 //                 definite on any mesh); degree 1 = damped l1-Jacobi
 //   coarsest    : dense inverse (host Cholesky at set-up), warp-per-row matvec
@@ -1165,7 +1166,7 @@ double2 *vcycle_level(Ctx *ctx, Amg &H, int lev, const double2 *b, double2 *out,
     }
     return x;
   }
-  const int deg = ctx->amg_degree;
+  const int deg = lev == 0 ? ctx->amg_degree : ctx->amg_coarse_degree;
   const Cheb ch;
   // 2*deg - 1 buffer flips follow the first write: start so that the last one lands in `out`
   double2 *xa = L.x.p, *xb = out ? out : L.x2.p;

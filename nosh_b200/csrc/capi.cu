@@ -564,12 +564,14 @@ nosh_status nosh_keoreg_apply(nosh_ctx *ctx, const double *X, int64_t ldx, doubl
   API_END(ctx)
 }
 
-nosh_status nosh_amg_set_options(nosh_ctx *ctx, int degree, int coarse_max, int max_levels, int reuse) {
+nosh_status nosh_amg_set_options(nosh_ctx *ctx, int degree, int coarse_degree, int coarse_max, int max_levels,
+                                 int reuse) {
   API_BEGIN(ctx)
   if (coarse_max > 4096) NOSH_THROW(NOSH_EINVAL, "coarse_max > 4096");
   if (max_levels > NOSH_AMG_MAX_LEVELS) NOSH_THROW(NOSH_EINVAL, "max_levels > %d", NOSH_AMG_MAX_LEVELS);
   if (reuse > 1) NOSH_THROW(NOSH_EINVAL, "unknown reuse policy %d", reuse);
   if (degree > 0) ctx->amg_degree = degree;
+  if (coarse_degree > 0) ctx->amg_coarse_degree = coarse_degree;
   if (coarse_max > 0) ctx->amg_coarse_max = coarse_max;
   if (max_levels > 0) ctx->amg_max_levels = max_levels;
   if (reuse >= 0) ctx->amg_reuse = reuse;
@@ -594,6 +596,7 @@ nosh_status nosh_amg_info(nosh_ctx *ctx, nosh_amg_info_t *info) {
   memset(info, 0, sizeof(*info));
   info->levels = (int32_t)ctx->amg->levels.size();
   info->degree = ctx->amg_degree;
+  info->coarse_degree = ctx->amg_coarse_degree;
   info->setup_seconds = ctx->amg->setup_seconds;
   for (int l = 0; l < info->levels && l < NOSH_AMG_MAX_LEVELS; l++) {
     const AmgLevel &L = *ctx->amg->levels[l];

@@ -161,8 +161,9 @@ class Level:
 class Hierarchy:
     """Smoothed-aggregation hierarchy for the real 2N x 2N SPD matrix A (scipy CSR)."""
 
-    def __init__(self, A, G=None, coarse_max=512, max_levels=10, degree=2):
-        self.degree = degree
+    def __init__(self, A, G=None, coarse_max=512, max_levels=10, degree=1, coarse_degree=2):
+        self.degree = degree                # Chebyshev degree on the finest level
+        self.coarse_degree = coarse_degree  # ... on the coarse levels
         self.levels = []
         A = sp.csr_matrix(A)
         G = node_pattern(A) if G is None else G
@@ -225,7 +226,7 @@ class Hierarchy:
         r = b if zero_start else b - L.A @ x
         d = (L.sinv * r) / theta
         x = d.copy() if zero_start else x + d
-        for _ in range(1, self.degree):
+        for _ in range(1, self.degree if L is self.levels[0] else self.coarse_degree):
             rho_new = 1.0 / (2.0 * sigma - rho)
             r = b - L.A @ x
             d = (rho_new * rho) * d + (2.0 * rho_new / delta) * (L.sinv * r)

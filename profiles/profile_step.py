@@ -24,6 +24,7 @@ ap.add_argument("--persistent", type=int, default=0,
                 help="0: the multi-launch MINRES loop (one launch per phase: readable launch lists); 1: the default "
                      "one-launch cooperative kernel")
 ap.add_argument("--amg-degree", type=int, default=1)
+ap.add_argument("--amg-coarse-degree", type=int, default=2)
 a = ap.parse_args()
 
 ctx = nosh_b200.Context(layout={"csr": 0, "sell32": 1}[a.layout])
@@ -42,7 +43,7 @@ par = {"g": 1.0, "mu": 1.0, "theta": 0.0}
 
 ctx.set_tuning("persistent_minres", a.persistent)
 if a.precond == "amg":
-    ctx.amg_set_options(degree=a.amg_degree)
+    ctx.amg_set_options(degree=a.amg_degree, coarse_degree=a.amg_coarse_degree)
 
 
 def step(k):

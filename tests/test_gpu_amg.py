@@ -46,7 +46,7 @@ def block_csr_to_scipy(rp, cols, vals, ncols):
     return sp.csr_matrix((v, (r, c)), shape=(2 * n, 2 * ncols))
 
 
-def setup_pair(nb, orc, n=14, state="random", coarse_max=40, degree=1, mu=PARAMS["mu"]):
+def setup_pair(nb, orc, n=14, state="random", coarse_max=40, degree=1, mu=PARAMS["mu"], coarse_degree=2):
     from oracle import amg
     coords, cells = orc.meshgen.tetgrid(n)
     psi, A = orc.meshgen.plain_gl_fields(coords)
@@ -56,7 +56,7 @@ def setup_pair(nb, orc, n=14, state="random", coarse_max=40, degree=1, mu=PARAMS
     ctx.set_thickness(None, 1.0)
     ctx.set_potential_constant(-1.0)
     ctx.set_mvp_explicit(A)
-    ctx.amg_set_options(degree=degree, coarse_max=coarse_max)
+    ctx.amg_set_options(degree=degree, coarse_degree=coarse_degree, coarse_max=coarse_max)
     P = orc.OracleProblem(coords, cells, ("explicit", A))
     params = dict(PARAMS, mu=mu)
     ctx.keoreg_rebuild(params, x)
@@ -64,7 +64,7 @@ def setup_pair(nb, orc, n=14, state="random", coarse_max=40, degree=1, mu=PARAMS
     N = P.N
     Pm = sp.csr_matrix((P.keoreg_fill(mu, params["g"], x), P.cols, P.rowptr), shape=(2 * N, 2 * N))
     P.jac_rebuild(params["g"], x)
-    H = amg.Hierarchy(Pm, coarse_max=coarse_max, degree=degree)
+    H = amg.Hierarchy(Pm, coarse_max=coarse_max, degree=degree, coarse_degree=coarse_degree)
     return ctx, P, Pm, H, x, params
 
 
@@ -100,9 +100,9 @@ def test_hierarchy_matches_oracle(nb, orc):
         assert np.array_equal(cols, H.levels[l + 1].G.indices)
 
 
-@pytest.mark.parametrize("degree", [1, 2, 3])
-def test_vcycle_matches_oracle(nb, orc, degree):
-    ctx, P, Pm, H, x, params = setup_pair(nb, orc, degree=degree)
+@pytest.mark.parametrize("degree,coarse_degree", [(1, 1), (1, 2), (2, 2), (3, 1)])
+def test_vcycle_matches_oracle(nb, orc, degree, coarse_degree):
+    ctx, P, Pm, H, x, params = setup_pair(nb, orc, degree=degree, coarse_degree=coarse_degree)
     rng = np.random.default_rng(5)
     b = rng.standard_normal(2 * P.N)
     y = ctx.keoreg_apply(b)
