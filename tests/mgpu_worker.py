@@ -152,6 +152,14 @@ def main():
     assert rs.iterations == res.iterations
     assert np.array_equal(hs, hg), "residual history differs between 1 and %d GPUs" % world
     assert np.array_equal(xs[sl], xg)
+    # restarted GMRES: batched Gram-Schmidt reductions through the same tree + one all-reduce of the group sums
+    from oracle import gmres as og
+    xs3, rs3, hs3 = single.gmres(b, tol=1e-10, maxit=400, restart=40, history=True)
+    xg3, rg3, hg3 = ctx.gmres(b[sl].copy(), tol=1e-10, maxit=400, restart=40, history=True)
+    assert rs3.iterations == rg3.iterations and rg3.converged == 1
+    assert np.array_equal(hs3, hg3) and np.array_equal(xs3[sl], xg3)
+    _, ito3, _, _ = og.gmres(lambda t: P.jac_apply(t), None, b, 1e-10, 400, restart=40)
+    assert rg3.iterations == ito3, (rg3.iterations, ito3)
     single.close()
     ctx.close()
 
