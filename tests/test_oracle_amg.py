@@ -89,3 +89,29 @@ def test_gmres_restatement():
     H = amg.Hierarchy(Pm, coarse_max=64, degree=1)
     xp, itp, rr, _ = og.gmres(lambda t: J @ t, H.vcycle, b, 1e-10, 500, restart=50)
     assert itp < itg / 2 and np.linalg.norm(J @ xp - b) <= 1.0001e-10 * np.linalg.norm(b)
+
+
+def test_arclength_restatement_follows_the_branch_through_a_fold():
+    """oracle/continuation.py: the arc-length stepper reproduces the points natural continuation finds on the
+    way up, keeps going where natural continuation runs out of solutions (the fold), and every accepted point
+    is a solution of F(x, mu) = 0."""
+    from oracle import continuation
+    coords, cells = meshgen.tetgrid(7)
+    psi, A = meshgen.plain_gl_fields(coords)
+    P = oracle.OracleProblem(coords, cells, ("explicit", A), nthreads=2)
+    x, recs = continuation.arclength(P, 1.0, 0.0, psi, 0.05, 1e-7, 0.1, 2.0, 8)
+    assert len(recs) == 9 and recs[0]["param"] == 0.0
+    dp = [r["dparam_ds"] for r in recs[1:]]
+    mus = [r["param"] for r in recs]
+    assert dp[0] > 0.5 and min(dp) < 0                     # starts along +mu, turns around
+    k = int(np.argmax(mus))
+    assert 0 < k < len(mus) - 1                            # the largest mu is an interior point: a fold
+    assert all(r["fnorm"] < 1e-8 for r in recs)
+    P.keo_fill(mus[-1])
+    assert np.linalg.norm(P.compute_f(1.0, x)) < 1e-8      # the last point solves the equations
+    # ||psi|| decreases on the way up to the fold
+    norms = [r["norm"] for r in recs]
+    assert all(b < a for a, b in zip(norms[:k + 1], norms[1:k + 1]))
+    # natural continuation to mu = 0.1 lands on the same branch: same norm as the arc-length curve there
+    xn, nrecs = P.continuation(1.0, "mu", 0.0, 0.05, 2, psi)
+    assert np.interp(nrecs[-1]["param"], mus[:k + 1], norms[:k + 1]) == pytest.approx(nrecs[-1]["norm"], rel=2e-3)
