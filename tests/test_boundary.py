@@ -69,3 +69,16 @@ def test_oracle_library_builds_and_loads():
     import oracle
     oracle.build_library()
     assert oracle.num_threads() >= 1
+
+
+def test_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: include/nosh_b200.h must compile as C99 (cgo / JNI / ctypes consumers)"""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "nosh_b200.h"\n'
+                   "int main(void) { nosh_arclength_options o; nosh_amg_info_t i; nosh_mesh_info_t m;\n"
+                   "  (void)o; (void)i; (void)m; return nosh_version == 0; }\n")
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
