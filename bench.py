@@ -371,6 +371,10 @@ def run_b200(args):
     bytes_apply = nb * 20 + (No + 1) * 8 + No * (16 + 16 + 24)   # SURVEY.md 8(d), per launch per GPU
     peak, peak_src = measured_peak()
     achieved = bytes_apply / (ms_apply * 1e-3) / 1e9
+    # the whole MINRES iteration: apply + r1 read + kernel B (3 streams) + kernel C (6 streams) of 16 B per
+    # vertex; conservative: divided by the whole step time (assembly + rebuild included)
+    bytes_iter = bytes_apply + 10 * 16 * No
+    achieved_iter = bytes_iter * ITERS / (ms_step * 1e-3) / 1e9
     traffic = traffic_from_profiles()
 
     if rank == 0:
@@ -398,6 +402,10 @@ def run_b200(args):
                          "peak_source": peak_src, "bytes_per_launch": bytes_apply,
                          "ms_per_launch": ms_apply,
                          "traffic": (traffic or {}).get("jacobian_apply_dram_bytes_per_launch")},
+            "minres_iteration_roofline": {"bound": "hbm", "achieved": achieved_iter, "peak": peak, "unit": "GB/s",
+                                          "frac": achieved_iter / peak, "bytes_per_iteration": bytes_iter,
+                                          "note": "per GPU; algorithmic bytes of one MINRES iteration x %d / whole "
+                                                  "step time" % ITERS},
             "e2e": {"value": 2.0 * Nglob * ITERS / (ms_e2e * 1e-3) / 1e9, "unit": "GDOF/s",
                     "h2d_bytes_per_step": 2 * 16 * No * world, "d2h_bytes_per_step": 16 * No * world,
                     "ms_per_step": ms_e2e},
