@@ -19,6 +19,7 @@
 //  * meshes come from arrays or the synthetic generator (nosh::read needs MOAB)
 //  * the Thyra InArgs/OutArgs protocol is reduced to plain structs with the same members
 #pragma once
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -70,6 +71,77 @@ public:
     check(ctx_, nosh_mesh_tetgrid(ctx_, nx, ny, nz, lo, hi, jitter, seed));
     finish();
   }
+  // nosh::read(file) (src/mesh_reader.cpp:19-162): mesh + vertex tags from a legacy VTK file (MOAB's
+  // .h5m / Exodus need libraries that are not available: std::runtime_error with the conversion hint)
+  explicit mesh(const std::string &file_name, int device = 0) {
+    nosh_meshfile *f = nullptr;
+    const nosh_status st = nosh_meshfile_read(file_name.c_str(), &f);
+    if (st != NOSH_OK) throw std::runtime_error(std::string("nosh::read: ") + nosh_meshfile_last_error());
+    int32_t dim = 0, nf = 0;
+    int64_t nv = 0, nc = 0;
+    nosh_meshfile_info(f, &dim, &nv, &nc, &nf);
+    file_dim_ = dim;
+    file_coords_.resize((size_t)nv * 3);
+    file_cells_.resize((size_t)nc * (dim + 1));
+    nosh_meshfile_get(f, file_coords_.data(), file_cells_.data());
+    for (int32_t i = 0; i < nf; i++) {
+      const char *name = nullptr;
+      int32_t ncomp = 0;
+      nosh_meshfile_field_name(f, i, &name, &ncomp);
+      std::vector<double> v((size_t)nv * ncomp);
+      nosh_meshfile_get_field(f, name, nullptr, v.data());
+      tags_[name] = {ncomp, std::move(v)};
+    }
+    nosh_meshfile_free(f);
+    create(device);
+    check(ctx_, nosh_mesh_set(ctx_, dim, nv, file_coords_.data(), nc, file_cells_.data()));
+    finish();
+  }
+  // vertex tags of the file (src/mesh.cpp:249-446).  One rank: owned == all vertices.
+  std::shared_ptr<Tpetra::Vector<double, int, int>> get_vector(const std::string &tag) const {
+    const auto &t = tag_at(tag, 1);
+    auto v = std::make_shared<Tpetra::Vector<double, int, int>>(map_);
+    std::copy(t.begin(), t.end(), v->getDataNonConst());
+    return v;
+  }
+  std::shared_ptr<Tpetra::Vector<double, int, int>> get_complex_vector(const std::string &tag) const {
+    const auto &t = tag_at(tag, 2);  // (re, im) per vertex = the interleaved layout of complex_map
+    auto v = std::make_shared<Tpetra::Vector<double, int, int>>(complex_map_);
+    std::copy(t.begin(), t.end(), v->getDataNonConst());
+    return v;
+  }
+  std::shared_ptr<Tpetra::MultiVector<double, int, int>> get_multi_vector(const std::string &tag) const {
+    const auto &t = tag_at(tag, 3);  // file: (x,y,z) per vertex; MultiVector: one column per component
+    auto v = std::make_shared<Tpetra::MultiVector<double, int, int>>(map_, 3);
+    const size_t n = t.size() / 3;
+    for (size_t k = 0; k < n; k++)
+      for (int c = 0; c < 3; c++) v->getDataNonConst(c)[k] = t[3 * k + c];
+    return v;
+  }
+  const std::vector<double> &tag_data(const std::string &tag) const { return tags_.at(tag).second; }
+  // mesh::write (src/mesh.cpp:249-263), the outNNNN dumps of continuation_data_saver.hpp:24-50: the mesh of
+  // the file with `psi` replaced by the given state
+  void write(const std::string &file_name, const Tpetra::Vector<double, int, int> *psi = nullptr) const {
+    if (file_coords_.empty()) throw std::logic_error("mesh::write: this mesh was not read from a file");
+    std::vector<const char *> names;
+    std::vector<int32_t> ncomps;
+    std::vector<const double *> values;
+    for (const auto &kv : tags_) {
+      if (psi && kv.first == "psi") continue;
+      names.push_back(kv.first.c_str());
+      ncomps.push_back(kv.second.first);
+      values.push_back(kv.second.second.data());
+    }
+    if (psi) {
+      names.push_back("psi");
+      ncomps.push_back(2);
+      values.push_back(psi->getData());
+    }
+    if (nosh_meshfile_write(file_name.c_str(), file_dim_, (int64_t)file_coords_.size() / 3, file_coords_.data(),
+                            (int64_t)file_cells_.size() / (file_dim_ + 1), file_cells_.data(), (int32_t)names.size(),
+                            names.data(), ncomps.data(), values.data(), 1) != NOSH_OK)
+      throw std::runtime_error(std::string("mesh::write: ") + nosh_meshfile_last_error());
+  }
   ~mesh() { nosh_ctx_destroy(ctx_); }
   mesh(const mesh &) = delete;
   mesh &operator=(const mesh &) = delete;
@@ -99,11 +171,24 @@ private:
     complex_map_ = std::make_shared<Tpetra::Map<int, int>>(2 * info_.n_owned, 2 * info_.n_global,
                                                            2 * (1 + (int)info_.owned_begin));
   }
+  const std::vector<double> &tag_at(const std::string &tag, int ncomp) const {
+    auto it = tags_.find(tag);
+    if (it == tags_.end()) throw std::runtime_error("tag \"" + tag + "\" not found");  // moab_wrap.hpp:52-63
+    if (it->second.first != ncomp) throw std::logic_error("tag \"" + tag + "\" has the wrong number of components");
+    return it->second.second;
+  }
+  int file_dim_ = 0;
+  std::vector<double> file_coords_;
+  std::vector<int32_t> file_cells_;
+  std::map<std::string, std::pair<int, std::vector<double>>> tags_;
   nosh_ctx *ctx_ = nullptr;
   nosh_mesh_info_t info_;
   std::shared_ptr<const Tpetra::Map<int, int>> map_, complex_map_;
   mutable std::shared_ptr<const Tpetra::Vector<double, int, int>> cv_;
 };
+
+// src/mesh_reader.hpp: std::shared_ptr<nosh::mesh> read(const std::string & file_name)
+inline std::shared_ptr<nosh::mesh> read(const std::string &file_name) { return std::make_shared<nosh::mesh>(file_name); }
 
 // ---------------------------------------------------------------------------------------
 namespace scalar_field {

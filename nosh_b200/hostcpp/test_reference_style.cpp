@@ -216,10 +216,68 @@ static void run(const Fixture &fx) {
   std::printf("%s: done\n", fx.name.c_str());
 }
 
+// ---- test/io.cpp:51-59,95-103: the vertex tags of a mesh FILE (here: legacy VTK, written on the fly) ----
+static void run_io(const Fixture &fx, double a_inf_x, double a_inf_y) {
+  const size_t N = fx.coords.size() / 3;
+  std::vector<double> psi(2 * N, 0.0), A(3 * N, 0.0), V(N, -1.0);
+  for (size_t k = 0; k < N; k++) {
+    psi[2 * k] = 1.0;
+    A[3 * k] = -0.5 * fx.coords[3 * k + 1];
+    A[3 * k + 1] = 0.5 * fx.coords[3 * k];
+  }
+  const std::string path = std::string("/tmp/nosh_b200_") + fx.name + ".vtk";
+  const char *names[3] = {"psi", "A", "V"};
+  const int32_t ncomps[3] = {2, 3, 1};
+  const double *vals[3] = {psi.data(), A.data(), V.data()};
+  std::vector<int32_t> cells32(fx.cells.begin(), fx.cells.end());
+  g_checks++;
+  if (nosh_meshfile_write(path.c_str(), fx.dim, (int64_t)N, fx.coords.data(), (int64_t)cells32.size() / (fx.dim + 1),
+                          cells32.data(), 3, names, ncomps, vals, 1) != NOSH_OK) {
+    std::printf("FAIL write %s: %s\n", path.c_str(), nosh_meshfile_last_error());
+    g_fail++;
+    return;
+  }
+  auto mesh = nosh::read(path);
+  REQUIRE_APPROX((double)mesh->map()->getGlobalNumElements(), fx.n_nodes, 0.0);
+  auto z = mesh->get_complex_vector("psi");
+  REQUIRE_APPROX(z->norm1(), fx.n_nodes, 1e-15);   // io.cpp: 4.0 / 8.0
+  REQUIRE_APPROX(z->normInf(), 1.0, 1e-15);
+  auto mvp_vals = mesh->get_multi_vector("A");
+  double ninf[3] = {0, 0, 0};
+  for (int c = 0; c < 3; c++)
+    for (size_t k = 0; k < N; k++) ninf[c] = std::fmax(ninf[c], std::fabs(mvp_vals->getData(c)[k]));
+  REQUIRE_APPROX(ninf[0], a_inf_x, 1e-15);         // io.cpp: (0.25, 2.5, 0) / (0.25, 0.25, 0)
+  REQUIRE_APPROX(ninf[1], a_inf_y, 1e-15);
+  REQUIRE_APPROX(1.0 + ninf[2], 1.0, 1e-15);
+  REQUIRE_APPROX(mesh->get_vector("V")->norm1(), fx.n_nodes, 1e-15);
+  REQUIRE_THROWS_AS(mesh->get_vector("no such tag"), std::runtime_error);
+  REQUIRE_THROWS_AS(nosh::read("/tmp/pacman.h5m"), std::runtime_error);
+  // the file-read mesh drives the same operators: test/keo.cpp's quadratic form again
+  auto thickness = std::make_shared<nosh::scalar_field::constant>(*mesh, 1.0);
+  auto mvp = std::make_shared<nosh::vector_field::explicit_values>(*mesh, mesh->tag_data("A"), 1.0e-2);
+  nosh::parameter_matrix::keo keo(mesh, thickness, mvp);
+  keo.set_parameters({{"mu", 1.0e-2}}, {});
+  Tpetra::Vector<double, int, int> one(mesh->complex_map()), Kone(mesh->complex_map());
+  one.putScalar(1.0);
+  keo.apply(one, Kone);
+  REQUIRE_APPROX(one.dot(Kone), fx.keo_sum, 1e-8);
+  // outNNNN dump of a state and back
+  Tpetra::Vector<double, int, int> state(mesh->complex_map());
+  for (size_t k = 0; k < 2 * N; k++) state[k] = 0.25 * (double)k - 1.0;
+  const std::string out = std::string("/tmp/nosh_b200_") + fx.name + "_out0001.vtk";
+  mesh->write(out, &state);
+  auto back = nosh::read(out)->get_complex_vector("psi");
+  double worst = 0.0;
+  for (size_t k = 0; k < 2 * N; k++) worst = std::fmax(worst, std::fabs((*back)[k] - state[k]));
+  REQUIRE_APPROX(1.0 + worst, 1.0, 1e-15);
+}
+
 int main() {
   try {
     run(rectanglesmall());
     run(cubesmall());
+    run_io(rectanglesmall(), 0.25, 2.5);
+    run_io(cubesmall(), 0.25, 0.25);
   } catch (const std::exception &e) {
     std::printf("FAIL uncaught exception: %s\n", e.what());
     return 2;
