@@ -111,3 +111,34 @@ def test_morton_order_makes_contiguous_ranges_compact():
         return np.unique(t[cut]).size
     # contiguous ranges of the Morton numbering cut far fewer cells than ranges of the shuffled numbering
     assert cut_vertices(t2) < 0.5 * cut_vertices(t1)
+
+
+def test_vtk5_offsets_connectivity_layout(tmp_path):
+    """files written by VTK >= 9 / recent meshio use 'CELLS n+1 nconn' + OFFSETS / CONNECTIVITY arrays"""
+    path = tmp_path / "rect5.vtk"
+    path.write_text("""# vtk DataFile Version 5.1
+vtk output
+ASCII
+DATASET UNSTRUCTURED_GRID
+POINTS 4 double
+5 0.5 0 -5 -0.5 0 5 -0.5 0 -5 0.5 0
+CELLS 3 6
+OFFSETS vtktypeint64
+0 3 6
+CONNECTIVITY vtktypeint64
+0 1 2 0 3 1
+CELL_TYPES 2
+5
+5
+POINT_DATA 4
+FIELD FieldData 2
+V 1 4 double
+-1 -1 -1 -1
+psi 2 4 double
+1 0 1 0 1 0 1 0
+""")
+    coords, cells, fields = nosh_b200.read_mesh(path)
+    ref_c, ref_t = meshgen.rectanglesmall()
+    assert np.array_equal(coords, ref_c) and np.array_equal(cells, ref_t)
+    assert np.array_equal(fields["V"], -np.ones(4)) and fields["psi"].shape == (4, 2)
+    assert np.array_equal(fields["psi"][:, 0], np.ones(4))
