@@ -145,6 +145,7 @@ nosh_status nosh_ctx_create(int device, void *stream, nosh_ctx **out) {
     if (g >= CHUNK && g % CHUNK == 0) ctx->group_vertices = g;
   }
   if (const char *e = getenv("NOSH_B200_PERSISTENT_MINRES")) ctx->persistent_minres = atoi(e) != 0;
+  if (const char *e = getenv("NOSH_B200_PERSISTENT_MGPU")) ctx->persistent_mgpu = atoi(e) != 0;
   *out = ctx;
   return NOSH_OK;
 }

@@ -143,6 +143,7 @@ struct Ctx {
   int layout = NOSH_LAYOUT_SELL32;
   int persistent_minres = 1;        // single-GPU unpreconditioned MINRES as one cooperative launch (krylov.cu);
                                     // env NOSH_B200_PERSISTENT_MINRES=0 / tuning key "persistent_minres" turn it off
+  int persistent_mgpu = 0;          // EXPERIMENTAL multi-GPU persistent loop (env NOSH_B200_PERSISTENT_MGPU=1), off
   int persist_grid = 0;             // co-resident CTAs of that kernel (occupancy x SMs), computed once
   int apply_variant = 0;            // measurement knob: which k_apply_sell variant the MINRES loop uses (apply.cu)
   int64_t group_vertices = 65536;

@@ -452,6 +452,236 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent(const PersistArg
   if (blockIdx.x == 0 && tid == 0) *P.st = s_st;
 }
 
+// -------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL, OFF BY DEFAULT (NOSH_B200_PERSISTENT_MGPU=1): the persistent loop for several GPUs with the
+// peer-memory reductions of reduce.cuh (stage 3) moved inside the kernel.  Written at the end of round 1,
+// compiled, NOT yet run on hardware (no GPU minutes left to validate it at 2/4/8 ranks) -- DESIGN.md section
+// 11.  Per reduction:  level 2 | sync | CTA 0: store my group sums into every rank's slot, raise the epoch
+// flag, spin on the peers' flags | sync | level 3 from my slot.  The halo push of r_{h+1} is a grid-stride
+// loop in the phase after B; every pushing thread fences system-wide before the grid sync that precedes the
+// beta exchange, whose flags therefore also order the pushed ghosts (same argument as the multi-launch path).
+// -------------------------------------------------------------------------------------------------------
+struct PushView {
+  double2 *dst[MAX_RANKS];
+  int64_t off[MAX_RANKS + 1];
+};
+struct PersistMgpuArgs {
+  PersistArgs S;
+  P2PView q;            // q.epoch = epoch of the LAST reduction done before this launch
+  int64_t group_begin, n_groups_local;
+  const int32_t *send_idx;
+  int64_t n_send;
+  PushView push0, push1;  // targets when r_{h+1} lives in R0 / R1
+  unsigned long long *epoch_out;
+};
+
+__device__ __forceinline__ void persist_exchange(const PersistMgpuArgs &M, unsigned long long epoch) {
+  // CTA 0 only: all-gather of the group sums over NVLink (finalize_levels stage 3)
+  const P2PView &q = M.q;
+  const int slot = (int)(epoch & 1ull);
+  const int nloc = (int)M.n_groups_local;
+  for (int i = threadIdx.x; i < nloc * q.P; i += blockDim.x) {
+    const int r = i / nloc, g = (int)M.group_begin + i % nloc;
+    q.red[r][slot * MAX_GROUPS + g] = __ldcg(M.S.gsums + g);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < q.P) {
+    *((volatile unsigned long long *)&q.flags[threadIdx.x][q.me]) = epoch;
+    const volatile unsigned long long *mine = (const volatile unsigned long long *)&q.flags[q.me][threadIdx.x];
+    const long long t0 = clock64();
+    while (*mine < epoch) {
+      if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer is gone; fail instead of hanging
+        *q.err = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent_mgpu(const PersistMgpuArgs M) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  const PersistArgs &P = M.S;
+  __shared__ KrylovState s_st;
+  __shared__ double red[32], sm[32];
+  __shared__ double pair[CHUNK];
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) s_st = *P.st;
+  __syncthreads();
+  FinArgs F;
+  F.st = &s_st;
+  F.hist = blockIdx.x == 0 ? P.hist : nullptr;
+  F.out = nullptr;
+  F.tol = s_st.tol;
+  F.maxit = s_st.maxit;
+  unsigned long long epoch = M.q.epoch;
+  // level 2 over my groups, level 3 over the gathered sums of all ranks
+  auto level2 = [&]() {
+    const int64_t gw = (int64_t)blockIdx.x * (CHUNK / 32) + (tid >> 5), nw = (int64_t)gridDim.x * (CHUNK / 32);
+    const int per = (P.cpg + 31) / 32;
+    for (int64_t g = gw; g < M.n_groups_local; g += nw) {
+      const int64_t base = g * P.cpg;
+      double s = 0.0;
+      for (int t = 0; t < per; t++) {
+        const int k = lane * per + t;
+        if (k < P.cpg && base + k < P.n_chunks) s += __ldcg(P.partials + base + k);
+      }
+      s = warp_sum(s);
+      if (lane == 0) P.gsums[M.group_begin + g] = s;
+    }
+  };
+  auto level3 = [&](unsigned long long ep) -> double {
+    const double *gs = M.q.red[M.q.me] + (int)(ep & 1ull) * MAX_GROUPS;
+    const int nw = CHUNK / 32, w = tid >> 5;
+    for (int seg = w; seg < 32; seg += nw) {
+      const int i = 32 * seg + lane;
+      double v = i < P.n_groups ? __ldcg(gs + i) : 0.0;
+      v = warp_sum(v);
+      if (lane == 0) sm[seg] = v;
+    }
+    __syncthreads();
+    double t = 0.0;
+    if (w == 0) {
+      t = sm[lane];
+      t = warp_sum(t);
+    }
+    __syncthreads();
+    return t;
+  };
+  for (int h = 1; h <= P.maxit; h++) {
+    if (s_st.done) break;
+    double2 *rcur = (h & 1) ? P.R0 : P.R1, *rprev = (h & 1) ? P.R1 : P.R0;
+    const PushView &push = (h & 1) ? M.push1 : M.push0;  // r_{h+1} is written into rprev
+    double2 *w1 = h % 3 == 0 ? P.W1 : (h % 3 == 1 ? P.W2 : P.W0);
+    double2 *w2 = h % 3 == 0 ? P.W2 : (h % 3 == 1 ? P.W0 : P.W1);
+    double2 *wn = h % 3 == 0 ? P.W0 : (h % 3 == 1 ? P.W1 : P.W2);
+    // ---- A ----
+    {
+      const double scale = s_st.inv_beta, f = s_st.f_r1;
+      for (int64_t chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
+        const int64_t row = chunk * CHUNK + tid;
+        const int64_t slice = row >> 5;
+        double2 acc = make_double2(0.0, 0.0);
+        if (slice < P.A.nslices) {
+          int p = __ldg(P.A.slice_off + slice) + lane;
+          const int pend = __ldg(P.A.slice_off + slice + 1);
+          for (; p + 96 < pend; p += 128) {
+            int c[4];
+            double2 v[4], xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) c[u] = ld_stream_i32(P.A.col + p + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = ld_stream2(P.A.val + p + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) xv[u] = __ldcg(rcur + c[u]);  // ghosts are written by peers: L2 loads
+#pragma unroll
+            for (int u = 0; u < 4; u++) cfma(acc, v[u], scaled(xv[u], scale));
+          }
+          for (; p < pend; p += 32) {
+            const int c = ld_stream_i32(P.A.col + p);
+            const double2 v = ld_stream2(P.A.val + p);
+            cfma(acc, v, scaled(__ldcg(rcur + c), scale));
+          }
+        }
+        double contrib = 0.0;
+        if (row < P.A.No) {
+          const double2 xi = scaled(__ldcg(rcur + row), scale);
+          double2 yi = acc;
+          if (EPI == EPI_DIAG) yi = diag_epilogue(acc, ld_stream2(P.A.d0 + row), __ldg(P.A.d1 + row), xi);
+          if (f != 0.0) yi = sub_scaled(yi, f, rprev[row]);
+          contrib = cdot(xi, yi);
+          P.Pv[row] = yi;
+        }
+        const double s = block_sum<CHUNK / 32>(contrib, red);
+        if (tid == 0) P.partials[chunk] = s;
+      }
+    }
+    grid.sync();
+    level2();
+    grid.sync();
+    epoch++;
+    if (blockIdx.x == 0) persist_exchange(M, epoch);
+    grid.sync();
+    if (__ldcg(M.q.err)) break;  // a peer timed out: every CTA sees the flag after the sync and leaves
+    {
+      const double total = level3(epoch);
+      if (tid == 0) {
+        F.what = FIN_MINRES_ALPHA;
+        fin_scalars(F, total);
+      }
+      __syncthreads();
+    }
+    // ---- B ----
+    {
+      const double f = s_st.f_r2;
+      for (int64_t chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
+        const int64_t i = chunk * CHUNK + tid;
+        double c = 0.0;
+        if (i < P.A.No) {
+          const double2 r = sub_scaled(P.Pv[i], f, rcur[i]);
+          rprev[i] = r;
+          c = cdot(r, r);
+        }
+        pair[tid] = c;
+        __syncthreads();
+        const double c2 = tid < TPB ? pair[tid] + pair[tid + TPB] : 0.0;
+        double v = warp_sum(c2);
+        if (lane == 0) red[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) {
+          double s = 0.0;
+#pragma unroll
+          for (int q8 = 0; q8 < TPB / 32; q8++) s += red[q8];
+          P.partials[chunk] = s;
+        }
+        __syncthreads();
+      }
+    }
+    grid.sync();
+    level2();
+    // halo push of r_{h+1}: my boundary entries into the neighbours' ghost segments over NVLink
+    for (int64_t i = (int64_t)blockIdx.x * CHUNK + tid; i < M.n_send; i += (int64_t)gridDim.x * CHUNK) {
+      int r = 0;
+      while (r + 1 < M.q.P && i >= push.off[r + 1]) r++;
+      push.dst[r][i - push.off[r]] = rprev[M.send_idx[i]];
+    }
+    __threadfence_system();
+    grid.sync();
+    epoch++;
+    if (blockIdx.x == 0) persist_exchange(M, epoch);
+    grid.sync();
+    if (__ldcg(M.q.err)) break;  // a peer timed out: every CTA sees the flag after the sync and leaves
+    {
+      const double total = level3(epoch);
+      if (tid == 0) {
+        F.what = FIN_MINRES_BETA;
+        fin_scalars(F, total);
+      }
+      __syncthreads();
+    }
+    // ---- C ----
+    if (s_st.iter == h) {
+      const double ib = s_st.inv_beta_prev, oe = s_st.oldeps, de = s_st.delta, ig = s_st.inv_gamma, ph = s_st.phi;
+      for (int64_t chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
+        const int64_t i = chunk * CHUNK + tid;
+        if (i < P.A.No) {
+          const double2 w = minres_w(rcur[i], w1[i], w2[i], ib, oe, de, ig);
+          wn[i] = w;
+          P.X[i] = axpy2(ph, w, P.X[i]);
+        }
+      }
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    *P.st = s_st;
+    *M.epoch_out = epoch;
+  }
+}
+
 // Reduction descriptor.  Default: finalize_launch() runs the one-CTA k_finalize kernel after the
 // producer.  With NOSH_B200_INKERNEL_FIN=1 (one GPU) the producer's last CTA finishes the reduction
 // itself (fin.counter set).  MEASURED SLOWER on B200 (profiles/r1_summary.md, section 4): the
@@ -732,6 +962,69 @@ void minres_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, dou
     }
   }
 multi_launch:
+  if (ctx->nranks > 1 && ctx->p2p.ok && !pc && ctx->layout == NOSH_LAYOUT_SELL32 && ctx->persistent_mgpu && grid > 0 &&
+      (epi == EPI_DIAG || epi == EPI_NONE)) {
+    // EXPERIMENTAL (NOSH_B200_PERSISTENT_MGPU=1, not validated on hardware yet): see k_minres_persistent_mgpu
+    int coop = 0, per_sm = 0, sms = 0;
+    CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minres_persistent_mgpu<EPI_DIAG>, CHUNK, 0));
+    CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    if (coop && per_sm > 0) {
+      PersistMgpuArgs MA;
+      memset(&MA, 0, sizeof(MA));
+      MA.S.A = A;
+      MA.S.R0 = Z[0];
+      MA.S.R1 = Z[1];
+      MA.S.Pv = Pv;
+      MA.S.W0 = W[0];
+      MA.S.W1 = W[1];
+      MA.S.W2 = W[2];
+      MA.S.X = X;
+      MA.S.st = ctx->kstate.p;
+      MA.S.partials = ctx->partials.p;
+      MA.S.gsums = ctx->group_sums.p;
+      MA.S.hist = ctx->hist.p;
+      MA.S.n_chunks = ctx->n_chunks;
+      MA.S.n_groups = ctx->n_groups_global;
+      MA.S.cpg = ctx->chunks_per_group;
+      MA.S.maxit = maxit;
+      MA.q = ctx->p2p.view;
+      MA.q.epoch = ctx->p2p.epoch;
+      MA.group_begin = ctx->group_begin;
+      MA.n_groups_local = ctx->n_groups_local;
+      MA.send_idx = ctx->send_idx.p;
+      MA.n_send = ctx->n_send;
+      for (int r = 0; r < ctx->nranks; r++) {
+        MA.push0.dst[r] = ctx->p2p.R[0][r] + ctx->p2p.ghost_base[r];
+        MA.push1.dst[r] = ctx->p2p.R[1][r] + ctx->p2p.ghost_base[r];
+        MA.push0.off[r] = MA.push1.off[r] = ctx->send_off[r];
+      }
+      MA.push0.off[ctx->nranks] = MA.push1.off[ctx->nranks] = ctx->send_off[ctx->nranks];
+      MA.epoch_out = (unsigned long long *)(ctx->scalar_out.p + 4);
+      const void *fn = epi == EPI_DIAG ? (const void *)k_minres_persistent_mgpu<EPI_DIAG>
+                                       : (const void *)k_minres_persistent_mgpu<EPI_NONE>;
+      const unsigned pgrid = (unsigned)std::min<int64_t>((int64_t)per_sm * sms, ctx->n_chunks);
+      void *kargs[] = {&MA};
+      CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(pgrid), dim3(CHUNK), kargs, 0, ctx->stream));
+      ctx->launches++;
+      unsigned long long ep = 0;
+      CUDA_CHECK(cudaMemcpyAsync(&ep, MA.epoch_out, sizeof(ep), cudaMemcpyDeviceToHost, ctx->stream));
+      poll_done(ctx, &hs);
+      ctx->p2p.epoch = ep;
+      if (p2p_check_error(ctx)) NOSH_THROW(NOSH_ECOMM, "peer-memory reduction timed out (a rank is not responding)");
+      if (res) {
+        res->iterations = hs.iter;
+        res->converged = hs.converged;
+        res->relres = hs.relres;
+      }
+      if (hist_host) {
+        CUDA_CHECK(cudaMemcpyAsync(hist_host, ctx->hist.p, sizeof(double) * (hs.iter + 1), cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      }
+      return;
+    }
+  }
   // Multi-GPU schedule (same arithmetic, two streams): the halo of r_h travels on stream2
   // while the interior chunks of A(h) run; C(h-1) also runs on stream2, next to A(h) and the
   // alpha all-reduce, and must only be finished before B(h) overwrites the buffer it reads.
