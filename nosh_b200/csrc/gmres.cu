@@ -342,6 +342,12 @@ void gmres_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, doub
   }
   if (hist_host)
     for (size_t i = 0; i < hist.size() && (int)i <= maxit; i++) hist_host[i] = hist[i];
+  // the Arnoldi basis is (restart+1) full vectors (38 GB for GMRES(300) on 8.0M vertices): keep a small one
+  // for the next solve, give a large one back
+  if (ctx->gmres_basis.n * sizeof(double2) > ((size_t)4 << 30)) {
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->gmres_basis.release();
+  }
 }
 
 }  // namespace nosh
