@@ -1,0 +1,60 @@
+"""The bench.py contract (task brief, section 4): the reference arm runs here on the CPU and prints ONE JSON line
+with the required keys; the committed B200 line of the final tree carries every key the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e"]
+
+
+def test_reference_arm_runs_on_the_cpu_and_prints_one_json_line():
+    env = dict(os.environ, OMP_NUM_THREADS="1")     # what torchrun exports: the arm must still use every core
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--cpu-n", "16",
+                        "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in BASE_KEYS + ["impl", "cpu_baseline"]:
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "jacobian_apply_gdof_per_s" and d["unit"] == "GDOF/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64"
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["value"] == d["value"] and "sample" in cb
+    assert cb["cores"] == len(os.sched_getaffinity(0))
+    assert "workload" in d["config"]
+
+
+def test_rank_other_than_zero_of_the_reference_arm_does_no_work():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_committed_b200_line_has_every_contract_key():
+    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_default_1gpu_v5.json")))
+    for k in BASE_KEYS + ["roofline", "cpu_baseline", "gpu_launches", "clocks"]:
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["data"] == "synthetic" and d["dtype"] == "f64"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    rf = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in rf, k
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    assert 0.7 <= rf["frac"] <= 1.1                      # BASELINE.json's target is >= 70 % of the HBM roofline
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in d["cpu_baseline"], k
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert 0 < d["e2e"]["value"] < d["value"]            # host copies inside the timed region cost something
+    assert d["gpu_launches"] > 0
+    for k in ("sm_mhz", "sm_max_mhz", "reasons"):
+        assert k in d["clocks"], k
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
