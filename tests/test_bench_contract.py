@@ -58,3 +58,17 @@ def test_committed_b200_line_has_every_contract_key():
     for k in ("sm_mhz", "sm_max_mhz", "reasons"):
         assert k in d["clocks"], k
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_b200_arm_fails_loudly_without_a_gpu():
+    """no CPU fallback: on a machine without a CUDA device the product arm exits non-zero and prints no line"""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            import pytest
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and r.stdout.strip() == ""
