@@ -12,8 +12,14 @@ which is one fused Jacobian apply plus the fused vector/reduction kernels.
   roofline: the fused Jacobian-apply kernel timed alone with CUDA events on the ctx stream,
            algorithmic bytes / time, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline / --impl reference: the oracle (the reference's algorithm restated in the
-           reference's Tpetra data layout; Trilinos cannot be built here) on all host cores, on
-           a bounded sample mesh of the same generator.
+           reference's Tpetra data layout; Trilinos cannot be built here) on all host cores.
+           --impl reference runs the SAME mesh and the same step as the b200 arm (n=200: about two
+           minutes of set-up, ~12 s per step on 16 cores); the number of timed steps is capped by a
+           time budget (--ref-budget-s) and the line says so when it ran fewer than --steps.
+  parity : before anything is timed the GPU path is checked against the oracle -- entry-wise KEO, F,
+           J.x, dF/dmu <= 1e-12 and the MINRES iteration count on the 1.0M-vertex mesh (one GPU), or
+           partitioned F / J.x / dF/dmu, MINRES and Newton counts and bit-identity with a one-GPU
+           context on a small mesh (several GPUs).  A failure aborts with exit code 3.
 
 N > 1 (torchrun): the mesh grows with N along z (weak scaling), vertex-partitioned, halo
 exchange per apply and group-sum all-reduces over NCCL.
@@ -51,6 +57,15 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=100,
                     help="sample mesh of the CPU baseline (100 -> 1.0M vertices = BASELINE.json configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity gate (profiling runs only)")
+    ap.add_argument("--parity-n", type=int, default=24, help="mesh of the multi-GPU parity gate")
+    ap.add_argument("--ref-n", type=int, default=0,
+                    help="--impl reference: mesh (0 = the b200 arm's --mesh-n, i.e. like for like)")
+    ap.add_argument("--ref-budget-s", type=float, default=200.0,
+                    help="--impl reference: wall-clock budget of its warm-up + timed steps")
+    ap.add_argument("--comm", default="host", choices=["host", "nccl"],
+                    help="several GPUs: set-up exchange through torch.distributed (host, default: the library "
+                         "owns no NCCL communicator) or through a library-owned NCCL communicator")
     ap.add_argument("--apply-reps", type=int, default=50)
     ap.add_argument("--workload", default="minres200", choices=["minres200", "newton", "continuation", "arclength"],
                     help="minres200: the default step (configs[1]); newton: one full Newton-MINRES solve per "
@@ -135,37 +150,67 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_from_profiles():
+def traffic_from_profiles(n, world, strong):
+    """dram bytes per launch of the fused Jacobian apply from an `ncu --set full` capture of THIS
+    configuration (profiles/traffic.json, keyed by mesh and GPU count); None where never captured."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p))
-        except Exception:
-            return None
-    return None
+    try:
+        tab = json.load(open(p))
+        key = "n%d_gpus%d%s" % (n, world, "_strong" if strong and world > 1 else "")
+        return tab.get("jacobian_apply", {}).get(key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_step(n, threads, steps, warmup):
-    """The reference's algorithm (oracle, Tpetra data layout) on host cores: the same step."""
+def oracle_problem(n, threads):
     from oracle import OracleProblem, meshgen
     coords, cells = meshgen.tetgrid(n)
-    P = OracleProblem(coords, cells, ("constcurl", (0.0, 0.0, 1.0), None), nthreads=threads)
+    return OracleProblem(coords, cells, ("constcurl", (0.0, 0.0, 1.0), None), nthreads=threads)
+
+
+def cpu_step(P, threads, steps, warmup, budget_s=None):
+    """The reference's algorithm (oracle, Tpetra data layout) on host cores: the same step.  With a
+    budget the number of timed steps is cut so that warm-up + timed steps stay inside it (at least 1)."""
+    from oracle import meshgen
     N = P.N
     psi = meshgen.random_state(N, 42)
     b = meshgen.random_state(N, 43)
     times = []
-    for s in range(warmup + steps):
+    t_begin = time.perf_counter()
+    done_warm = 0
+    s = 0
+    while True:
         t0 = time.perf_counter()
         P.keo_fill(PARAMS["mu"] * (1.0 + 1e-9 * s), nthreads=threads)
         P.jac_rebuild(PARAMS["g"], psi)
         _, it, _ = P.krylov(b, 0.0, ITERS)
         t1 = time.perf_counter()
         assert it == ITERS
-        if s >= warmup:
+        s += 1
+        if done_warm < warmup:
+            done_warm += 1
+            if budget_s is not None and (t1 - t_begin) + 2 * (t1 - t0) > budget_s and done_warm >= 1:
+                done_warm = warmup       # no time for further warm-up steps
+        else:
             times.append(t1 - t0)
+            if len(times) >= steps:
+                break
+            if budget_s is not None and (t1 - t_begin) + (t1 - t0) > budget_s:
+                break
     t = float(np.mean(times))
-    return {"N": N, "sec_per_step": t, "gdofs": 2.0 * N * ITERS / t / 1e9, "iters_per_s": ITERS / t}
+    return {"N": N, "sec_per_step": t, "gdofs": 2.0 * N * ITERS / t / 1e9, "iters_per_s": ITERS / t,
+            "steps_run": len(times), "warmup_run": s - len(times)}
+
+
+def workload_text(n, nz, Nglob, No):
+    return ("tetgrid %dx%dx%d = %d vertices (%d per GPU), 6 Kuhn tets/hex, jitter 0.2, const-curl B=(0,0,1), "
+            "mu=1, g=1, V=-1, t=1: KEO assembly + Jacobian rebuild + %d MINRES iterations per step"
+            % (n, n, nz, Nglob, No, ITERS))
+
+
+def l2_text(nb):
+    return "inputs larger than L2 (matrix %.0f MB per GPU)" % (nb * 20 / 1e6)
 
 
 def host_threads():
@@ -183,27 +228,201 @@ def run_reference(args):
     if rank != 0:
         return
     threads = host_threads()
-    steps = max(1, min(args.steps, 3))
-    warm = max(1, min(args.warmup, 1))
-    r = cpu_step(args.cpu_n, threads, steps, warm)
+    n = args.ref_n if args.ref_n > 0 else args.n
+    t0 = time.perf_counter()
+    P = oracle_problem(n, threads)
+    t_setup = time.perf_counter() - t0
+    r = cpu_step(P, threads, max(1, args.steps), max(1, args.warmup), budget_s=args.ref_budget_s)
+    N = r["N"]
+    nb = 2 * int(P.E) + N
+    note = None
+    if r["steps_run"] < args.steps or r["warmup_run"] < args.warmup:
+        note = ("ran %d of %d timed steps and %d of %d warm-up steps: one step of this workload takes %.1f s on %d "
+                "host cores and the arm keeps its steps inside --ref-budget-s = %.0f s (set-up %.0f s on top)"
+                % (r["steps_run"], args.steps, r["warmup_run"], args.warmup, r["sec_per_step"], threads,
+                   args.ref_budget_s, t_setup))
+    if args.gpus > 1:
+        note = ((note + "; ") if note else "") + ("the b200 arm's mesh grows with the GPU count (weak scaling); the CPU "
+                                                  "arm runs one GPU's share of it, per-DOF throughput")
     out = {
         "impl": "reference",
         "metric": "jacobian_apply_gdof_per_s", "value": r["gdofs"], "unit": "GDOF/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "n_gpus": args.gpus, "steps": r["steps_run"], "warmup": r["warmup_run"],
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
         "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "minres_iters_per_s": r["iters_per_s"],
-        "config": {"workload": "tetgrid n=%d (%d vertices), const-curl B=(0,0,1), mu=1, g=1: KEO assembly + "
-                               "Jacobian rebuild + %d MINRES iterations (bounded sample of the b200 arm's "
-                               "workload; per-DOF throughput)" % (args.cpu_n, r["N"], ITERS)},
+        "config": {"workload": workload_text(n, n, N, N), "l2": l2_text(nb)},
+        "setup_s": t_setup,
         "cpu_baseline": {"value": r["gdofs"], "unit": "GDOF/s", "cores": threads, "kind": "port",
-                         "sample": "tetgrid n=%d, %d vertices, %d steps; oracle = reference algorithm "
-                                   "restated in Tpetra layout (Trilinos/MOAB not buildable offline)"
-                                   % (args.cpu_n, r["N"], steps)},
+                         "sample": "tetgrid n=%d, %d vertices, %d full steps (assembly + rebuild + %d MINRES "
+                                   "iterations each); oracle = reference algorithm restated in Tpetra layout "
+                                   "(Trilinos/MOAB not buildable offline)" % (n, N, r["steps_run"], ITERS)},
         "e2e": {"value": r["gdofs"], "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if note:
+        out["note"] = note
     print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------
+def relerr(a, b):
+    s = float(np.abs(b).max())
+    return float(np.abs(a - b).max() / (s if s > 0 else 1.0))
+
+
+def fields(ctx):
+    ctx.set_thickness(None, 1.0)
+    ctx.set_potential_constant(-1.0)
+    ctx.set_mvp_constcurl((0.0, 0.0, 1.0))
+
+
+def counts_golden(n):
+    p = os.path.join(ROOT, "tests", "golden", "counts_n%d.json" % n)
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+def minres_count_verdict(gpu_it, oracle_counts, oracle_relres, tol):
+    """'Identical iteration counts' can only be asked for up to the summation order of the dot products:
+    equal to one of the oracle's counts, or one off while the oracle's own final residual sits within 10 %
+    of the tolerance (the stopping test straddles)."""
+    if gpu_it in oracle_counts:
+        return True
+    near = any(abs(gpu_it - c) <= 1 for c in oracle_counts)
+    straddle = any(r > 0.9 * tol for r in oracle_relres)
+    return bool(near and (straddle or len(set(oracle_counts)) > 1))
+
+
+def parity_one_gpu(nosh_b200, device, P, n, threads):
+    """World size 1: the GPU path against the oracle on the 1.0M-vertex mesh (configs[1]) -- entry-wise."""
+    import oracle
+    from oracle import meshgen
+    t0 = time.perf_counter()
+    ctx = nosh_b200.Context(device=device)
+    ctx.mesh_tetgrid(n)
+    fields(ctx)
+    N = P.N
+    par = dict(PARAMS)
+    x = meshgen.random_state(N, 42)
+    b = meshgen.random_state(N, 43)
+    out = {"mesh": "tetgrid n=%d (%d vertices)" % (n, N), "tolerance": 1e-12}
+    P.keo_fill(par["mu"])
+    ctx.keo_fill(par)
+    _, _, K = ctx.block_csr()
+    _, _, oK = P.complex_blocks(P.vals)
+    out["keo_entries_relerr"] = relerr(K, oK)
+    out["keo_entries_compared"] = int(K.size)
+    out["f_relerr"] = relerr(ctx.compute_f(par, x), P.compute_f(par["g"], x))
+    ctx.jac_rebuild(par, x)
+    P.jac_rebuild(par["g"], x)
+    out["jx_relerr"] = relerr(ctx.jac_apply(b), P.jac_apply(b))
+    P.dkeo_fill(par["mu"], 0.0, "mu")
+    out["dfdmu_relerr"] = relerr(ctx.compute_dfdp(par, "mu", x), P.compute_dfdp(x, False, np.zeros(N)))
+    # MINRES to 1e-10 on the benchmark operator
+    tol = 1e-10
+    xg, res, hg = ctx.minres(b, tol=tol, maxit=20000, history=True)
+    counts, relres, hist_dev = {}, {}, 0.0
+    for parts in (0, 1):                    # one part per thread (= MPI rank per core) and the serial sum
+        oracle.set_dot_parts(parts)
+        xo, ito, rr, ho = P.krylov(b, tol, 20000, history=True)
+        key = "%d" % (threads if parts == 0 else 1)
+        counts[key], relres[key] = int(ito), float(rr)
+        m = min(len(ho), len(hg), 201)
+        hist_dev = max(hist_dev, float(np.abs(hg[:m] / ho[:m] - 1.0).max()))
+        if parts == 0:
+            out["minres_solution_relerr"] = relerr(xg, xo)
+    oracle.set_dot_parts(0)
+    gold = counts_golden(n)
+    if gold:
+        for k, v in gold["minres"]["by_parts"].items():
+            counts.setdefault(k, int(v["iterations"]))
+            relres.setdefault(k, float(v["relres"]))
+    out["minres_iterations_gpu"] = int(res.iterations)
+    out["minres_iterations_oracle_by_dot_parts"] = counts
+    out["minres_history_max_rel_dev_first_200"] = hist_dev
+    out["minres_count_ok"] = minres_count_verdict(int(res.iterations), list(counts.values()), list(relres.values()), tol)
+    out["ok"] = bool(max(out["keo_entries_relerr"], out["f_relerr"], out["jx_relerr"], out["dfdmu_relerr"]) <= 1e-12
+                     and out["minres_count_ok"] and res.converged == 1 and hist_dev <= 1e-6
+                     and out["minres_solution_relerr"] <= 1e-6)
+    out["seconds"] = time.perf_counter() - t0
+    ctx.close()
+    return out
+
+
+def parity_multi_gpu(nosh_b200, make_ctx, device, rank, world, n):
+    """World size > 1: partitioned results against the oracle on the global mesh and, bit for bit, against a
+    one-GPU context (the reference runs every test with 1, 2 and 7 ranks: test/CMakeLists.txt:18-23)."""
+    from oracle import OracleProblem, meshgen
+    t0 = time.perf_counter()
+    group = 512
+    ctx = make_ctx(group)
+    mi = ctx.mesh_tetgrid(n)
+    fields(ctx)
+    vb, No = int(mi.owned_begin), int(mi.n_owned)
+    sl = slice(2 * vb, 2 * (vb + No))
+    coords, cells = meshgen.tetgrid(n)
+    N = coords.shape[0]
+    P = OracleProblem(coords, cells, ("constcurl", (0.0, 0.0, 1.0), None), nthreads=1)
+    single = nosh_b200.Context(device=device, group_vertices=group)
+    single.mesh_tetgrid(n)
+    fields(single)
+    par = {"g": 1.0, "mu": 0.3, "theta": 0.0}
+    x = meshgen.random_state(N, 42)
+    y = meshgen.random_state(N, 43)
+    b = meshgen.random_state(N, 4)
+    out = {"mesh": "tetgrid n=%d (%d vertices), group 512, %d ranks" % (n, N, world), "tolerance": 1e-12,
+           "peer_memory": bool(ctx.stat("p2p") == 1.0)}
+    bits = True
+    P.keo_fill(par["mu"])
+    P.jac_rebuild(par["g"], x)
+    for c, v in ((ctx, x[sl].copy()), (single, x)):
+        c.keo_fill(par)
+        c.jac_rebuild(par, v)
+    F = ctx.compute_f(par, x[sl].copy())
+    Jy = ctx.jac_apply(y[sl].copy())
+    dF = ctx.compute_dfdp(par, "mu", x[sl].copy())
+    P.dkeo_fill(par["mu"], 0.0, "mu")
+    out["f_relerr"] = relerr(F, P.compute_f(par["g"], x)[sl]) if No else 0.0
+    out["jx_relerr"] = relerr(Jy, P.jac_apply(y)[sl]) if No else 0.0
+    out["dfdmu_relerr"] = relerr(dF, P.compute_dfdp(x, False, np.zeros(N))[sl]) if No else 0.0
+    bits &= np.array_equal(single.compute_f(par, x)[sl], F) and np.array_equal(single.jac_apply(y)[sl], Jy)
+    xo, ito, _ = P.krylov(b, 1e-10, 5000)
+    xs, rs, hs = single.minres(b, tol=1e-10, maxit=5000, history=True)
+    its = {}
+    for persistent in (1, 0):
+        ctx.set_tuning("persistent_mgpu", persistent)
+        xg, res, hg = ctx.minres(b[sl].copy(), tol=1e-10, maxit=5000, history=True)
+        its["persistent" if persistent else "multi_launch"] = int(res.iterations)
+        bits &= res.iterations == rs.iterations and np.array_equal(hs, hg) and np.array_equal(xs[sl], xg)
+    ctx.set_tuning("persistent_mgpu", 1)
+    out["minres_iterations_gpu"] = its
+    out["minres_iterations_one_gpu"] = int(rs.iterations)
+    out["minres_iterations_oracle"] = int(ito)
+    psi0 = np.zeros(2 * N)
+    psi0[0::2] = 1.0
+    parn = {"g": 1.0, "mu": 0.1, "theta": 0.0}
+    P.keo_fill(parn["mu"])
+    xn, steps, lin, fn = P.newton(1.0, psi0, 1e-8, 20, 1e-10, 5000)
+    psi = psi0[sl].copy()
+    nres, glin, gfn = ctx.newton(parn, psi, 1e-8, 20, 1e-10, 5000)
+    psis = psi0.copy()
+    single.newton(parn, psis, 1e-8, 20, 1e-10, 5000)
+    bits &= np.array_equal(psis[sl], psi)
+    out["newton_minres_iterations_gpu"] = [int(v) for v in glin]
+    out["newton_minres_iterations_oracle"] = [int(v) for v in lin]
+    out["newton_solution_relerr"] = relerr(psi, xn[sl]) if No else 0.0
+    out["bits_equal_one_gpu"] = bool(bits)
+    out["ok"] = bool(max(out["f_relerr"], out["jx_relerr"], out["dfdmu_relerr"]) <= 1e-12 and bits
+                     and set(its.values()) == {int(ito)} and list(glin) == list(lin) and int(nres.steps) == int(steps)
+                     and out["newton_solution_relerr"] <= 1e-8)
+    out["seconds"] = time.perf_counter() - t0
+    single.close()
+    ctx.close()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -227,11 +446,50 @@ def run_b200(args):
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     layout = {None: None, "csr": nosh_b200.LAYOUT_CSR, "sell32": nosh_b200.LAYOUT_SELL32}[args.layout]
-    ctx = nosh_b200.Context(device=local, stream=stream, layout=layout)
-    if world > 1:
-        obj = [nosh_b200.Context.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(obj, src=0)
-        ctx.comm_init(obj[0], rank, world)
+    gloo = dist.new_group(backend="gloo") if world > 1 and args.comm == "host" else None
+
+    def make_ctx(group_vertices=None, stream=None):
+        c = nosh_b200.Context(device=local, stream=stream, layout=layout, group_vertices=group_vertices)
+        if world > 1:
+            if args.comm == "host":      # set-up through OUR communicator; data path = CUDA-IPC peer memory
+                c.comm_init_torch(gloo)
+            else:
+                obj = [nosh_b200.Context.unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(obj, src=0)
+                c.comm_init(obj[0], rank, world)
+        return c
+
+    def emit(out):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
+
+    # ---- parity gate: nothing is timed before the GPU path has been checked against the oracle ----------
+    parity = None
+    oracle_P = None
+    if not args.no_parity:
+        try:
+            if world == 1:
+                oracle_P = oracle_problem(args.cpu_n, host_threads())
+                parity = parity_one_gpu(nosh_b200, local, oracle_P, args.cpu_n, host_threads())
+            else:
+                parity = parity_multi_gpu(nosh_b200, make_ctx, local, rank, world, args.parity_n)
+                t = torch.tensor([1.0 if parity["ok"] else 0.0], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                parity["ok_all_ranks"] = bool(t.item() == 1.0)
+        except Exception as e:
+            parity = {"ok": False, "error": "%s: %s" % (type(e).__name__, e)}
+        ok = parity.get("ok_all_ranks", parity["ok"]) if world > 1 else parity["ok"]
+        if not parity["ok"]:
+            print("PARITY FAILED on rank %d: %s" % (rank, json.dumps(parity)), file=sys.stderr, flush=True)
+        if not ok:
+            if rank == 0:
+                emit({"metric": "jacobian_apply_gdof_per_s", "value": None, "unit": "GDOF/s", "n_gpus": world,
+                      "error": "parity gate failed; nothing was timed", "parity": parity})
+            sys.exit(3)
+
+    ctx = make_ctx(stream=stream)
 
     n = args.n
     zs = 1 if args.strong else world
@@ -244,6 +502,12 @@ def run_b200(args):
     ctx.synchronize()
     t_setup = time.perf_counter() - t_setup
     No, Nglob = int(mi.n_owned), int(mi.n_global)
+    setup_stats = {}
+    for k in ("setup.mesh_s", "setup.halo_s", "setup.p2p_s"):
+        try:
+            setup_stats[k[6:]] = ctx.stat(k)
+        except KeyError:
+            pass
 
     # synthetic state resident in HBM (random phases), generated on the device
     gen = torch.Generator(device="cuda")
@@ -292,7 +556,7 @@ def run_b200(args):
         return ms / steps, ctx.launch_count() - l0
 
     if args.workload != "minres200":
-        run_solver_workload(args, ctx, mi, world, rank, local, barrier, real_stdout, t_setup)
+        run_solver_workload(args, ctx, mi, world, rank, local, barrier, emit, t_setup, parity)
         ctx.close()
         if world > 1:
             dist.destroy_process_group()
@@ -375,7 +639,7 @@ def run_b200(args):
     # vertex; conservative: divided by the whole step time (assembly + rebuild included)
     bytes_iter = bytes_apply + 10 * 16 * No
     achieved_iter = bytes_iter * ITERS / (ms_step * 1e-3) / 1e9
-    traffic = traffic_from_profiles()
+    traffic = traffic_from_profiles(n, world, args.strong)
 
     if rank == 0:
         out = {
@@ -385,14 +649,12 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": "tetgrid %dx%dx%d = %d vertices (%d per GPU), 6 Kuhn tets/hex, jitter 0.2, "
-                            "const-curl B=(0,0,1), mu=1, g=1, V=-1, t=1: KEO assembly + Jacobian rebuild + "
-                            "%d MINRES iterations per step" % (n, n, nz, Nglob, No, ITERS),
-                "layout": "sell32" if mi.n_stored != mi.n_blocks or args.layout == "sell32" else "csr",
-                "l2": "inputs larger than L2 (matrix %.0f MB per GPU)" % (nb * 20 / 1e6),
-                "setup_s": t_setup,
-            },
+            "config": {"workload": workload_text(n, nz, Nglob, No), "l2": l2_text(nb)},
+            "layout": "sell32" if mi.n_stored != mi.n_blocks or args.layout == "sell32" else "csr",
+            "setup_s": t_setup, "setup_breakdown_s": setup_stats,
+            "comm": None if world == 1 else {"setup": args.comm, "peer_memory": bool(ctx.stat("p2p") == 1.0),
+                                             "data_path": "CUDA IPC peer memory over NVLink (in-kernel halo push + "
+                                                          "group-sum all-gather)" if ctx.stat("p2p") == 1.0 else "NCCL"},
             "minres_iters_per_s": ITERS / (ms_step * 1e-3),
             "jacobian_apply_alone_gdof_per_s": 2.0 * Nglob / (ms_apply * 1e-3) / 1e9,
             "keo_assembly_ms": ms_fill,
@@ -401,7 +663,7 @@ def run_b200(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "bytes_per_launch": bytes_apply,
                          "ms_per_launch": ms_apply,
-                         "traffic": (traffic or {}).get("jacobian_apply_dram_bytes_per_launch")},
+                         "traffic": traffic},
             "minres_iteration_roofline": {"bound": "hbm", "achieved": achieved_iter, "peak": peak, "unit": "GB/s",
                                           "frac": achieved_iter / peak, "bytes_per_iteration": bytes_iter,
                                           "note": "per GPU; algorithmic bytes of one MINRES iteration x %d / whole "
@@ -414,23 +676,25 @@ def run_b200(args):
         }
         if newton:
             out["newton_solve"] = newton
+        if parity is not None:
+            out["parity"] = parity
         if not args.no_cpu_baseline and world == 1:
             th = host_threads()
-            r = cpu_step(args.cpu_n, th, 1, 1)
+            if oracle_P is None:
+                oracle_P = oracle_problem(args.cpu_n, th)
+            r = cpu_step(oracle_P, th, 1, 1)
             out["cpu_baseline"] = {
                 "value": r["gdofs"], "unit": "GDOF/s", "cores": th, "kind": "port",
-                "sample": "tetgrid n=%d (%d vertices), 1 step of the same workload after 1 warm-up; "
-                          "oracle = reference algorithm restated in Tpetra layout" % (args.cpu_n, r["N"])}
-        sys.stdout.flush()
-        os.dup2(real_stdout, 1)
-        print(json.dumps(out), flush=True)
-        os.dup2(2, 1)
+                "sample": "tetgrid n=%d (%d vertices), 1 step of the same workload after 1 warm-up (the like-for-like "
+                          "run on the b200 arm's own mesh is `--impl reference`); oracle = reference algorithm "
+                          "restated in Tpetra layout" % (args.cpu_n, r["N"])}
+        emit(out)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_solver_workload(args, ctx, mi, world, rank, local, barrier, real_stdout, t_setup):
+def run_solver_workload(args, ctx, mi, world, rank, local, barrier, emit, t_setup, parity):
     """configs[2] / configs[3]: full Newton-MINRES solve, or a continuation sweep in mu."""
     import torch
     import torch.distributed as dist
@@ -506,10 +770,9 @@ def run_solver_workload(args, ctx, mi, world, rank, local, barrier, real_stdout,
                "minres_iterations": its, "minres_iters_per_s": its / (ms * 1e-3),
                "solve_seconds": ms * 1e-3, "gpu_launches": int(results[-1][2])}
         out.update(results[-1][3])
-        sys.stdout.flush()
-        os.dup2(real_stdout, 1)
-        print(json.dumps(out), flush=True)
-        os.dup2(2, 1)
+        if parity is not None:
+            out["parity"] = parity
+        emit(out)
 
 
 if __name__ == "__main__":

@@ -5,7 +5,7 @@
  * Every entry point names the reference interface (file:line under the
  * reference tree) it replaces.  The C++ mirror of the reference's classes
  * (nosh::parameter_matrix::keo, nosh::jacobian_operator,
- * nosh::model_evaluator::nls, ...) lives in nosh_b200/hostcpp/nosh/ and is a thin
+ * nosh::model_evaluator::nls, ...) lives in nosh_b200/hostcpp/nosh.hpp and is a thin
  * forwarder to these functions; INTEGRATION.md shows the binding a reference
  * maintainer would add.
  *
@@ -57,8 +57,8 @@ typedef enum {
   NOSH_ESTATE = 3,       /* call sequence error (e.g. apply before fill) */
   NOSH_EMESH = 4,        /* illegal mesh (flat tetrahedron, degenerate cell) */
   NOSH_EKEY = 5,         /* parameter name missing (std::out_of_range in the reference) */
-  NOSH_ECOMM = 6,        /* NCCL failure */
-  NOSH_EUNSUPPORTED = 7  /* out of scope (e.g. the MueLu V-cycle) */
+  NOSH_ECOMM = 6,        /* communication failure (peer-memory time-out, NCCL error, callback error) */
+  NOSH_EUNSUPPORTED = 7  /* out of scope (e.g. .h5m / Exodus mesh files: MOAB is not available) */
 } nosh_status;
 
 /* Teuchos::ETransp of Tpetra::Operator::apply */
@@ -112,6 +112,18 @@ NOSH_API nosh_status nosh_partition_range(int64_t n_global, int nranks, int rank
                                           int64_t group_vertices, int64_t *begin, int64_t *end,
                                           int64_t *group_used);
 NOSH_API nosh_status nosh_ctx_comm_init(nosh_ctx *ctx, const void *id128, int rank, int nranks);
+/* The same with the CALLER'S communicator instead of a library-owned NCCL one: `allgather` is the image of
+ * MPI_Allgather on the Teuchos::Comm the reference's mesh carries (src/mesh_reader.cpp:53-57) -- it receives
+ * one host record of bytes_per_rank bytes and must return the records of all ranks, in rank order, in recv
+ * (0 = success).  It is only called during set-up (nosh_mesh_*: halo plan, CUDA IPC handles) and by GMRES'
+ * batched sums; every other exchange -- halos, MINRES / CG / Newton reductions -- is done by kernels that
+ * store into the peers' HBM over NVLink (CUDA IPC).  Ranks may also share one GPU (tests). */
+typedef int (*nosh_allgather_fn)(void *user, const void *send, void *recv, int64_t bytes_per_rank);
+NOSH_API nosh_status nosh_ctx_comm_init_host(nosh_ctx *ctx, int rank, int nranks, nosh_allgather_fn allgather,
+                                             void *user);
+/* set-up timings and counters by name ("setup.mesh_s", "setup.halo_s", "setup.p2p_s", "p2p", "sell_sigma", ...);
+ * NOSH_EKEY if unknown */
+NOSH_API nosh_status nosh_ctx_get_stat(nosh_ctx *ctx, const char *key, double *value);
 
 /* ---- mesh (a1-a3).  Replaces nosh::read + mesh_tetra/mesh_tri ctor:
  * src/mesh_reader.cpp:19-162, src/mesh.cpp:18-51,629-691, src/mesh_tetra.cpp:14-35,
@@ -278,7 +290,9 @@ NOSH_API nosh_status nosh_norm2(nosh_ctx *ctx, const double *x, double *result);
 typedef struct {
   int32_t iterations;
   int32_t converged;
-  double relres; /* final implicit relative residual */
+  double relres;     /* final implicit relative residual */
+  int32_t breakdown; /* 1: the recurrence broke down (gamma == 0, or <r, M r> < 0 with an indefinite M) */
+  int32_t reserved;
 } nosh_krylov_result;
 NOSH_API nosh_status nosh_minres(nosh_ctx *ctx, nosh_operator_id op, const double *b, double *x,
                                  double tol, int maxit, nosh_krylov_result *res, double *hist);
@@ -317,6 +331,8 @@ typedef struct {
   int32_t steps;
   int32_t converged;
   int32_t total_linear_iterations;
+  int32_t linear_solve_status; /* 0: every linear solve converged; 1: one hit lin_maxit (its step was still
+                                  taken, as NOX does); 2: one broke down -- no step taken, Newton stopped */
   double fnorm;
 } nosh_newton_result;
 NOSH_API nosh_status nosh_newton(nosh_ctx *ctx, int np, const char *const *names,

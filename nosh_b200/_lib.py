@@ -30,7 +30,8 @@ class MeshInfo(C.Structure):
 
 
 class KrylovResult(C.Structure):
-    _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("relres", C.c_double)]
+    _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("relres", C.c_double),
+                ("breakdown", C.c_int32), ("reserved", C.c_int32)]
 
 
 class ContinuationStep(C.Structure):
@@ -64,7 +65,12 @@ class ArclengthStep(C.Structure):
 
 class NewtonResult(C.Structure):
     _fields_ = [("steps", C.c_int32), ("converged", C.c_int32),
-                ("total_linear_iterations", C.c_int32), ("fnorm", C.c_double)]
+                ("total_linear_iterations", C.c_int32), ("linear_solve_status", C.c_int32),
+                ("fnorm", C.c_double)]
+
+
+# nosh_allgather_fn: int (*)(void *user, const void *send, void *recv, int64_t bytes_per_rank)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
 
 
 def build(force=False):
@@ -106,6 +112,8 @@ def lib():
         "nosh_ctx_synchronize": (C.c_int, [vp]),
         "nosh_comm_unique_id": (C.c_int, [vp]),
         "nosh_ctx_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "nosh_ctx_comm_init_host": (C.c_int, [vp, C.c_int, C.c_int, ALLGATHER_FN, vp]),
+        "nosh_ctx_get_stat": (C.c_int, [vp, C.c_char_p, C.POINTER(dbl)]),
         "nosh_partition_range": (C.c_int, [i64, C.c_int, C.c_int, i64, C.POINTER(i64), C.POINTER(i64),
                                            C.POINTER(i64)]),
         "nosh_mesh_set": (C.c_int, [vp, C.c_int, i64, vp, i64, vp]),

@@ -168,6 +168,39 @@ class Context:
         b = (C.c_char * 128).from_buffer_copy(uid)
         self._ck(self.L.nosh_ctx_comm_init(self.h, b, int(rank), int(nranks)))
 
+    def comm_init_host(self, rank, nranks, allgather):
+        """Use the caller's communicator for set-up (no NCCL communicator inside the library):
+        allgather(bytes) -> list of every rank's bytes, in rank order.  All data-path exchange then goes
+        over CUDA-IPC peer memory."""
+        def _cb(user, send, recv, nbytes):
+            try:
+                parts = allgather(C.string_at(send, nbytes))
+                if len(parts) != nranks or any(len(q) != nbytes for q in parts):
+                    return 2
+                C.memmove(recv, b"".join(parts), nbytes * nranks)
+                return 0
+            except Exception:          # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._ag_cb = _lib.ALLGATHER_FN(_cb)      # keep the trampoline alive as long as the ctx
+        self._ck(self.L.nosh_ctx_comm_init_host(self.h, int(rank), int(nranks), self._ag_cb, None))
+
+    def comm_init_torch(self, group=None):
+        """comm_init_host over torch.distributed (any backend that can all_gather_object)."""
+        import torch.distributed as dist
+
+        def ag(b):
+            out = [None] * dist.get_world_size(group)
+            dist.all_gather_object(out, b, group=group)
+            return out
+        self.comm_init_host(dist.get_rank(group), dist.get_world_size(group), ag)
+
+    def stat(self, key):
+        v = C.c_double()
+        self._ck(self.L.nosh_ctx_get_stat(self.h, key.encode(), C.byref(v)))
+        return v.value
+
     def synchronize(self):
         self._ck(self.L.nosh_ctx_synchronize(self.h))
 

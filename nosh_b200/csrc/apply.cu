@@ -59,7 +59,17 @@ __device__ __forceinline__ bool krylov_skip(const ApplyArgs &A) {
 // sized for (2 -> 64 registers, 1 -> up to 128); PF: load the next batch's columns before the current
 // batch's gathers are consumed (software pipelining of the col -> x dependency).  The variants exist
 // for measurement (profiles/apply_variants.py); launch2 picks the one that measured best.
-template <int EPI, int FUSE, int U, int MINB, bool PF>
+// GH: ghost columns (c >= No) are read from A.xg, the landing slot the neighbours stored into over NVLink
+// (L2 loads: written by another device), instead of from x[No..).
+template <bool GH>
+__device__ __forceinline__ double2 gather_x(const ApplyArgs &A, int c) {
+  if (GH) {
+    if (c >= A.No) return __ldcg(A.xg + (c - A.No));
+  }
+  return __ldg(A.x + c);
+}
+
+template <int EPI, int FUSE, int U, int MINB, bool PF, bool GH = false>
 __global__ void __launch_bounds__(CHUNK, MINB) k_apply_sell(const ApplyArgs A) {
   if (krylov_skip<FUSE>(A)) return;
   if (A.gate && A.gate->done) return;
@@ -85,7 +95,7 @@ __global__ void __launch_bounds__(CHUNK, MINB) k_apply_sell(const ApplyArgs A) {
 #pragma unroll
         for (int u = 0; u < U; u++) v[u] = ld_stream2(A.val + p + 32 * u);
 #pragma unroll
-        for (int u = 0; u < U; u++) xv[u] = __ldg(A.x + c[u]);
+        for (int u = 0; u < U; u++) xv[u] = gather_x<GH>(A, c[u]);
         p += 32 * U;
         have = p + 32 * (U - 1) < pend;
         if (have) {
@@ -110,7 +120,7 @@ __global__ void __launch_bounds__(CHUNK, MINB) k_apply_sell(const ApplyArgs A) {
 #pragma unroll
         for (int u = 0; u < U; u++) v[u] = ld_stream2(A.val + p + 32 * u);
 #pragma unroll
-        for (int u = 0; u < U; u++) xv[u] = __ldg(A.x + c[u]);
+        for (int u = 0; u < U; u++) xv[u] = gather_x<GH>(A, c[u]);
 #pragma unroll
         for (int u = 0; u < U; u++) {
           if (FUSE == FUSE_MINRES) {
@@ -123,7 +133,7 @@ __global__ void __launch_bounds__(CHUNK, MINB) k_apply_sell(const ApplyArgs A) {
     for (; p < pend; p += 32) {
       const int c = ld_stream_i32(A.col + p);
       const double2 v = ld_stream2(A.val + p);
-      double2 xv = __ldg(A.x + c);
+      double2 xv = gather_x<GH>(A, c);
       if (FUSE == FUSE_MINRES) {
         xv = scaled(xv, scale);
       }
@@ -187,7 +197,7 @@ __global__ void __launch_bounds__(CHUNK, 2) k_apply_csr(const ApplyArgs A) {
       for (int p = b + sl; p < e; p += LPR) {
         const int c = ld_stream_i32(A.col + p);
         const double2 v = ld_stream2(A.val + p);
-        double2 xv = __ldg(A.x + c);
+        double2 xv = (A.xg && c >= A.No) ? __ldcg(A.xg + (c - A.No)) : __ldg(A.x + c);
         if (FUSE == FUSE_MINRES) {
           xv = scaled(xv, scale);
         }
@@ -238,7 +248,11 @@ template <int EPI, int FUSE>
 void launch2(Ctx *ctx, const ApplyArgs &A) {
   const unsigned grid = A.chunk_list ? (unsigned)A.n_list : (unsigned)cdiv(A.No, CHUNK);
   if (grid == 0) return;
-  if (ctx->layout == NOSH_LAYOUT_SELL32) {
+  constexpr bool ghost_ok = FUSE == FUSE_NONE || FUSE == FUSE_AXPBY;
+  if (A.xg && !ghost_ok) NOSH_THROW(NOSH_EINVAL, "internal: separate ghost vector with a fused Krylov/smoother apply");
+  if (ctx->layout == NOSH_LAYOUT_SELL32 && A.xg) {
+    if constexpr (ghost_ok) k_apply_sell<EPI, FUSE, 4, 2, false, true><<<grid, CHUNK, 0, ctx->stream>>>(A);
+  } else if (ctx->layout == NOSH_LAYOUT_SELL32) {
     // measurement variants exist for the two kernels of the MINRES loop only (compile time)
     constexpr bool tunable = EPI == EPI_DIAG && (FUSE == FUSE_NONE || FUSE == FUSE_MINRES);
     const int v = tunable ? ctx->apply_variant : 0;

@@ -37,7 +37,9 @@ struct ApplyArgs {
   const int32_t *slice_off;  // SELL: nslices+1
   const int32_t *col;
   const double2 *val;
-  const double2 *x;  // Nl entries (owned + ghosts)
+  const double2 *x;  // Nl entries (owned + ghosts); owned entries only when xg is set
+  const double2 *xg; // optional: ghost entries (column c >= No reads xg[c - No]) -- the landing slot of the
+                     // peer-memory halo exchange, so the caller's vector needs no ghost room (FUSE_NONE/AXPBY)
   double2 *y;        // No entries
   // epilogues
   const double2 *d0;

@@ -30,6 +30,12 @@ namespace {
   }                                         \
   return NOSH_OK;
 
+double wall_s() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
 bool is_device_ptr(const void *p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -44,6 +50,10 @@ void require_mesh(Ctx *ctx) {
 }
 
 // input vector of 2*No doubles -> device pointer with room for ghosts when needed
+// does an operator apply need its input to carry a ghost segment?  With peer memory the ghosts are read from
+// the landing buffer (krylov.cu:apply_halo_dev), so a device vector of the caller is used in place.
+bool ghost_room(const Ctx *ctx) { return ctx->nranks > 1 && !ctx->p2p.ok; }
+
 double2 *stage_in(Ctx *ctx, const double *p, DBuf<double2> &buf, bool need_ghost_room) {
   if (!p && ctx->No > 0) NOSH_THROW(NOSH_EINVAL, "NULL vector");
   const bool dev = p && is_device_ptr(p);
@@ -213,12 +223,41 @@ nosh_status nosh_ctx_comm_init(nosh_ctx *ctx, const void *id128, int rank, int n
   API_END(ctx)
 }
 
+nosh_status nosh_ctx_comm_init_host(nosh_ctx *ctx, int rank, int nranks, nosh_allgather_fn allgather, void *user) {
+  API_BEGIN(ctx)
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  comm_init_host(ctx, rank, nranks, allgather, user);
+  API_END(ctx)
+}
+
+nosh_status nosh_ctx_get_stat(nosh_ctx *ctx, const char *key, double *value) {
+  API_BEGIN(ctx)
+  if (!key || !value) NOSH_THROW(NOSH_EINVAL, "NULL argument");
+  if (strcmp(key, "p2p") == 0) {
+    *value = ctx->p2p.ok ? 1.0 : 0.0;
+  } else if (strcmp(key, "n_chunks_interior") == 0) {
+    *value = (double)ctx->n_chunks_int;
+  } else if (strcmp(key, "n_chunks_boundary") == 0) {
+    *value = (double)ctx->n_chunks_bnd;
+  } else if (strcmp(key, "n_send") == 0) {
+    *value = (double)ctx->n_send;
+  } else {
+    auto it = ctx->stats.find(key);
+    if (it == ctx->stats.end()) NOSH_THROW(NOSH_EKEY, "unknown stat \"%s\"", key);
+    *value = it->second;
+  }
+  API_END(ctx)
+}
+
 nosh_status nosh_mesh_set(nosh_ctx *ctx, int dim, int64_t nv, const double *coords, int64_t nc,
                           const int32_t *cells) {
   API_BEGIN(ctx)
   CUDA_CHECK(cudaSetDevice(ctx->device));
   ctx->has_mesh = false;
+  const double t0 = wall_s();
   mesh_from_host(ctx, dim, nv, coords, nc, cells);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->stats["setup.mesh_s"] = wall_s() - t0;
   after_mesh(ctx);
   API_END(ctx)
 }
@@ -229,7 +268,10 @@ nosh_status nosh_mesh_tetgrid(nosh_ctx *ctx, int nx, int ny, int nz, const doubl
   CUDA_CHECK(cudaSetDevice(ctx->device));
   if (!lo || !hi) NOSH_THROW(NOSH_EINVAL, "NULL bounds");
   ctx->has_mesh = false;
+  const double t0 = wall_s();
   mesh_tetgrid(ctx, nx, ny, nz, lo, hi, jitter, seed);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->stats["setup.mesh_s"] = wall_s() - t0;
   after_mesh(ctx);
   API_END(ctx)
 }
@@ -391,7 +433,7 @@ nosh_status nosh_matrix_apply(nosh_ctx *ctx, nosh_matrix_id which, const double 
   }
   ensure_work(ctx);
   for (int v = 0; v < nvec; v++) {
-    double2 *x = stage_in(ctx, X + (size_t)v * ldx, ctx->stage_x, ctx->nranks > 1);
+    double2 *x = stage_in(ctx, X + (size_t)v * ldx, ctx->stage_x, ghost_room(ctx));
     OutVec o = stage_out(ctx, Y + (size_t)v * ldy, ctx->stage_y);
     if (o.host && beta != 0.0)
       CUDA_CHECK(cudaMemcpyAsync(o.dev, o.user, sizeof(double2) * ctx->No, cudaMemcpyHostToDevice, ctx->stream));
@@ -407,8 +449,7 @@ nosh_status nosh_matrix_apply(nosh_ctx *ctx, nosh_matrix_id which, const double 
     A.y = o.dev;
     A.a = alpha;
     A.b = beta;
-    halo_exchange(ctx, x);
-    launch_apply(ctx, EPI_NONE, (alpha == 1.0 && beta == 0.0) ? FUSE_NONE : FUSE_AXPBY, A);
+    apply_halo_dev(ctx, EPI_NONE, (alpha == 1.0 && beta == 0.0) ? FUSE_NONE : FUSE_AXPBY, A, x);
     finish_out(ctx, o);
   }
   API_END(ctx)
@@ -464,7 +505,7 @@ nosh_status nosh_jac_apply(nosh_ctx *ctx, const double *X, int64_t ldx, double *
   if (beta != 0.0) NOSH_THROW(NOSH_EINVAL, "Only beta==0.0 supported.");
   check_apply_shape(ctx, ldx, ldy, nvec);
   for (int v = 0; v < nvec; v++) {
-    double2 *x = stage_in(ctx, X + (size_t)v * ldx, ctx->stage_x, ctx->nranks > 1);
+    double2 *x = stage_in(ctx, X + (size_t)v * ldx, ctx->stage_x, ghost_room(ctx));
     OutVec o = stage_out(ctx, Y + (size_t)v * ldy, ctx->stage_y);
     apply_op_dev(ctx, NOSH_OP_JACOBIAN, x, o.dev);
     finish_out(ctx, o);
@@ -487,7 +528,7 @@ nosh_status nosh_compute_f(nosh_ctx *ctx, int np, const char *const *names, cons
   keo_fill(ctx, np, names, values, false);            // src/model_evaluator_nls.cpp:536
   const double g = param_at(np, names, values, "g");  // :559
   update_potential(ctx, np, names, values);
-  double2 *x = stage_in(ctx, psi, ctx->stage_x, ctx->nranks > 1);
+  double2 *x = stage_in(ctx, psi, ctx->stage_x, ghost_room(ctx));
   OutVec o = stage_out(ctx, f, ctx->stage_y);
   compute_f_dev(ctx, g, x, o.dev);
   finish_out(ctx, o);
@@ -499,7 +540,7 @@ nosh_status nosh_compute_dfdp(nosh_ctx *ctx, int np, const char *const *names, c
   API_BEGIN(ctx)
   require_mesh(ctx);
   if (!pname) NOSH_THROW(NOSH_EINVAL, "NULL parameter name");
-  double2 *x = stage_in(ctx, psi, ctx->stage_x, ctx->nranks > 1);
+  double2 *x = stage_in(ctx, psi, ctx->stage_x, ghost_room(ctx));
   OutVec o = stage_out(ctx, dfdp, ctx->stage_y);
   compute_dfdp_dev(ctx, np, names, values, pname, x, o.dev);
   finish_out(ctx, o);
@@ -524,7 +565,7 @@ nosh_status nosh_keoreg_matrix_apply(nosh_ctx *ctx, const double *X, int64_t ldx
   require_mesh(ctx);
   check_apply_shape(ctx, ldx, ldy, nvec);
   for (int v = 0; v < nvec; v++) {
-    double2 *x = stage_in(ctx, X + (size_t)v * ldx, ctx->stage_x, ctx->nranks > 1);
+    double2 *x = stage_in(ctx, X + (size_t)v * ldx, ctx->stage_x, ghost_room(ctx));
     OutVec o = stage_out(ctx, Y + (size_t)v * ldy, ctx->stage_y);
     apply_op_dev(ctx, NOSH_OP_KEOREG, x, o.dev);
     finish_out(ctx, o);
@@ -834,6 +875,8 @@ nosh_status nosh_ctx_set_tuning(nosh_ctx *ctx, const char *key, int value) {
     ctx->apply_variant = value;
   } else if (strcmp(key, "persistent_minres") == 0) {
     ctx->persistent_minres = value != 0;
+  } else if (strcmp(key, "persistent_mgpu") == 0) {
+    ctx->persistent_mgpu = value != 0;
   } else {
     NOSH_THROW(NOSH_EKEY, "unknown tuning key \"%s\"", key);
   }

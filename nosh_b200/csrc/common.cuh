@@ -107,18 +107,40 @@ struct P2PView {
   double *red[MAX_RANKS];               // rank r's gather buffer: 2 slots x MAX_GROUPS doubles
   unsigned long long *flags[MAX_RANKS]; // rank r's arrival flags: one per source rank
   int P, me;
-  unsigned long long epoch;
+  unsigned long long *epoch_ctr;        // local: number of reductions EXECUTED so far (slot = parity); bumped on
+                                        // the device only, so launches skipped after convergence do not count
   int *err;                             // local: set on a spin time-out
+  long long timeout;                    // spin time-out in clock64 ticks
+};
+// Stand-alone halo exchange through peer memory (operator applies outside the persistent Krylov loop):
+// every rank owns a ghost landing buffer G (2 slots x Ng entries) that its neighbours store into.
+struct HaloView {
+  double2 *dst[MAX_RANKS];              // where my block starts in rank r's landing buffer (slot 0)
+  int64_t slot_stride[MAX_RANKS];       // rank r's Ng (distance between its two slots)
+  int64_t send_off[MAX_RANKS + 1];      // my send list, grouped by destination rank
+  int64_t recv_cnt[MAX_RANKS];          // how many ghosts rank r sends me
+  unsigned long long *flag_of[MAX_RANKS];  // rank r's halo flag for source `me`
+  unsigned long long *my_flags;         // my halo flags, one per source rank
+  unsigned int *ticket;                 // last-CTA ticket of the push kernel
+  int *err;
+  long long timeout;
+  int P, me;
 };
 struct P2P {
   bool ok = false;
-  DBuf<unsigned long long> local;       // [2*MAX_GROUPS | MAX_RANKS flags | err]
-  void *opened[3][MAX_RANKS] = {};
+  DBuf<unsigned long long> local;       // [2*MAX_GROUPS sums | MAX_RANKS flags | err | epoch | MAX_RANKS halo flags | ticket]
+  DBuf<double2> ghost;                  // 2 x Ng landing buffer of the stand-alone halo exchange
+  void *opened[4][MAX_RANKS] = {};
   P2PView view;
+  HaloView halo;
   double2 *R[2][MAX_RANKS] = {};        // rank r's MINRES r-buffers (work[0], work[1])
   int64_t ghost_base[MAX_RANKS] = {};   // where my block starts inside rank r's vectors
-  unsigned long long epoch = 0;
+  unsigned long long hepoch = 0;        // halo exchanges issued (all ranks call them collectively)
 };
+
+// Host-side all-gather of fixed-size records, supplied by the caller (MPI_Allgather on the communicator the
+// reference's mesh carries, torch.distributed in the tests): recv = P consecutive records in rank order.
+typedef int (*HostAllgather)(void *user, const void *send, void *recv, int64_t bytes_per_rank);
 
 enum MvpKind { MVP_NONE = 0, MVP_EXPLICIT = 1, MVP_CONSTCURL = 2 };
 enum PotKind { POT_NONE = 0, POT_CONSTANT = 1, POT_VALUES = 2 };
@@ -138,12 +160,17 @@ struct Ctx {
   int rank = 0, nranks = 1;
   NcclApi *nccl = nullptr;
   void *comm = nullptr;  // ncclComm_t
+  HostAllgather host_ag = nullptr;  // set-up exchange through the caller's communicator (no NCCL in the library)
+  void *host_ag_user = nullptr;
+  std::map<std::string, double> stats;  // set-up timings etc. (nosh_ctx_get_stat)
 
   // options
   int layout = NOSH_LAYOUT_SELL32;
   int persistent_minres = 1;        // single-GPU unpreconditioned MINRES as one cooperative launch (krylov.cu);
                                     // env NOSH_B200_PERSISTENT_MINRES=0 / tuning key "persistent_minres" turn it off
-  int persistent_mgpu = 0;          // EXPERIMENTAL multi-GPU persistent loop (env NOSH_B200_PERSISTENT_MGPU=1), off
+  int persistent_mgpu = 1;          // multi-GPU persistent loop over peer memory (env NOSH_B200_PERSISTENT_MGPU=0 /
+                                    // tuning key "persistent_mgpu" select the multi-launch loop)
+  int persist_grid_mgpu = 0;
   int persist_grid = 0;             // co-resident CTAs of that kernel (occupancy x SMs), computed once
   int apply_variant = 0;            // measurement knob: which k_apply_sell variant the MINRES loop uses (apply.cu)
   int64_t group_vertices = 65536;

@@ -339,6 +339,7 @@ void gmres_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, doub
     res->iterations = iters;
     res->converged = converged;
     res->relres = relres;
+    res->breakdown = 0;
   }
   if (hist_host)
     for (size_t i = 0; i < hist.size() && (int)i <= maxit; i++) hist_host[i] = hist[i];

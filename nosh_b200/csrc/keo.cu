@@ -198,6 +198,7 @@ void set_thickness(Ctx *ctx, const double *values, double c) {
   ctx->thick_set = true;
   ctx->alpha_ok = false;
   ctx->keo_filled = ctx->dkeo_filled = false;
+  ctx->amg_valid = false;  // a new field invalidates the whole hierarchy, not only its finest diagonal
 }
 
 void set_mvp_explicit(Ctx *ctx, const double *A_host, const double *B) {
@@ -214,6 +215,7 @@ void set_mvp_explicit(Ctx *ctx, const double *A_host, const double *B) {
   ctx->mvp_kind = MVP_EXPLICIT;
   ctx->cc_has_u = false;
   ctx->keo_filled = ctx->dkeo_filled = false;
+  ctx->amg_valid = false;  // a new field invalidates the whole hierarchy, not only its finest diagonal
 }
 
 void set_mvp_constcurl(Ctx *ctx, const double b[3], const double u[3]) {
@@ -233,6 +235,7 @@ void set_mvp_constcurl(Ctx *ctx, const double b[3], const double u[3]) {
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   ctx->mvp_kind = MVP_CONSTCURL;
   ctx->keo_filled = ctx->dkeo_filled = false;
+  ctx->amg_valid = false;  // a new field invalidates the whole hierarchy, not only its finest diagonal
 }
 
 // keo::build_alpha_cache_ (first refill only) + the parameter-independent diagonal

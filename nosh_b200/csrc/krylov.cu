@@ -453,13 +453,16 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent(const PersistArg
 }
 
 // -------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL, OFF BY DEFAULT (NOSH_B200_PERSISTENT_MGPU=1): the persistent loop for several GPUs with the
-// peer-memory reductions of reduce.cuh (stage 3) moved inside the kernel.  Written at the end of round 1,
-// compiled, NOT yet run on hardware (no GPU minutes left to validate it at 2/4/8 ranks) -- DESIGN.md section
-// 11.  Per reduction:  level 2 | sync | CTA 0: store my group sums into every rank's slot, raise the epoch
-// flag, spin on the peers' flags | sync | level 3 from my slot.  The halo push of r_{h+1} is a grid-stride
-// loop in the phase after B; every pushing thread fences system-wide before the grid sync that precedes the
-// beta exchange, whose flags therefore also order the pushed ghosts (same argument as the multi-launch path).
+// The persistent loop for several GPUs: the same kernel with the peer-memory reductions of reduce.cuh
+// (stage 3) and the halo push moved inside -- ONE launch per MINRES solve and rank, no NCCL call, the
+// compute step and its NVLink exchange in one kernel.  Per reduction:
+//     level 2 | sync | CTA 0: store my group sums into every rank's slot, raise the epoch flag, spin on the
+//     peers' flags | sync | level 3 from my slot (every CTA, redundantly).
+// The halo push of r_{h+1} is a grid-stride loop in the phase after B; every pushing thread fences
+// system-wide before the grid sync that precedes the beta exchange, whose flags therefore also order the
+// pushed ghosts (same argument as the multi-launch path).  Gathers of OWNED entries go through L1 (the grid
+// syncs invalidate it, as in the one-GPU kernel); ghost entries, written by the peers, are read from L2.
+// Same chunk partials, same tree, same scalar recurrences => bit-identical to the one-GPU kernel.
 // -------------------------------------------------------------------------------------------------------
 struct PushView {
   double2 *dst[MAX_RANKS];
@@ -467,12 +470,11 @@ struct PushView {
 };
 struct PersistMgpuArgs {
   PersistArgs S;
-  P2PView q;            // q.epoch = epoch of the LAST reduction done before this launch
+  P2PView q;
   int64_t group_begin, n_groups_local;
   const int32_t *send_idx;
   int64_t n_send;
   PushView push0, push1;  // targets when r_{h+1} lives in R0 / R1
-  unsigned long long *epoch_out;
 };
 
 __device__ __forceinline__ void persist_exchange(const PersistMgpuArgs &M, unsigned long long epoch) {
@@ -491,7 +493,7 @@ __device__ __forceinline__ void persist_exchange(const PersistMgpuArgs &M, unsig
     const volatile unsigned long long *mine = (const volatile unsigned long long *)&q.flags[q.me][threadIdx.x];
     const long long t0 = clock64();
     while (*mine < epoch) {
-      if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer is gone; fail instead of hanging
+      if (clock64() - t0 > q.timeout) {  // a peer is gone; fail instead of hanging
         *q.err = 1;
         break;
       }
@@ -518,7 +520,8 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent_mgpu(const Persi
   F.out = nullptr;
   F.tol = s_st.tol;
   F.maxit = s_st.maxit;
-  unsigned long long epoch = M.q.epoch;
+  unsigned long long epoch = *M.q.epoch_ctr;  // reductions executed before this launch
+  const int64_t No = P.A.No;
   // level 2 over my groups, level 3 over the gathered sums of all ranks
   auto level2 = [&]() {
     const int64_t gw = (int64_t)blockIdx.x * (CHUNK / 32) + (tid >> 5), nw = (int64_t)gridDim.x * (CHUNK / 32);
@@ -577,19 +580,19 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent_mgpu(const Persi
 #pragma unroll
             for (int u = 0; u < 4; u++) v[u] = ld_stream2(P.A.val + p + 32 * u);
 #pragma unroll
-            for (int u = 0; u < 4; u++) xv[u] = __ldcg(rcur + c[u]);  // ghosts are written by peers: L2 loads
+            for (int u = 0; u < 4; u++) xv[u] = c[u] < No ? rcur[c[u]] : __ldcg(rcur + c[u]);  // ghosts: written by peers
 #pragma unroll
             for (int u = 0; u < 4; u++) cfma(acc, v[u], scaled(xv[u], scale));
           }
           for (; p < pend; p += 32) {
             const int c = ld_stream_i32(P.A.col + p);
             const double2 v = ld_stream2(P.A.val + p);
-            cfma(acc, v, scaled(__ldcg(rcur + c), scale));
+            cfma(acc, v, scaled(c < No ? rcur[c] : __ldcg(rcur + c), scale));
           }
         }
         double contrib = 0.0;
         if (row < P.A.No) {
-          const double2 xi = scaled(__ldcg(rcur + row), scale);
+          const double2 xi = scaled(rcur[row], scale);
           double2 yi = acc;
           if (EPI == EPI_DIAG) yi = diag_epilogue(acc, ld_stream2(P.A.d0 + row), __ldg(P.A.d1 + row), xi);
           if (f != 0.0) yi = sub_scaled(yi, f, rprev[row]);
@@ -678,7 +681,7 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent_mgpu(const Persi
   }
   if (blockIdx.x == 0 && tid == 0) {
     *P.st = s_st;
-    *M.epoch_out = epoch;
+    *M.q.epoch_ctr = epoch;
   }
 }
 
@@ -723,7 +726,6 @@ void finalize_launch(Ctx *ctx, FinArgs &F) {
   } else if (ctx->p2p.ok) {
     F.stage = 3;
     F.p2p = ctx->p2p.view;
-    F.p2p.epoch = ++ctx->p2p.epoch;
     KLAUNCH(ctx, k_finalize, 1, 1024, F);
   } else {
     F.stage = 1;
@@ -803,7 +805,19 @@ void ensure_work(Ctx *ctx) {
     ctx->ticket.alloc(1);
     CUDA_CHECK(cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned int), ctx->stream));
   }
-  if (!ctx->scalar_out.p) ctx->scalar_out.alloc(8);
+  if (!ctx->scalar_out.p) {
+    ctx->scalar_out.alloc(8);
+    CUDA_CHECK(cudaMemsetAsync(ctx->scalar_out.p, 0, sizeof(double) * 8, ctx->stream));
+  }
+}
+
+// scalar_out[0] = the reduced value, scalar_out[1] != 0: the peer-memory exchange timed out (stale sums)
+static double fetch_scalar(Ctx *ctx) {
+  double h[2];
+  CUDA_CHECK(cudaMemcpyAsync(h, ctx->scalar_out.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (h[1] != 0.0) NOSH_THROW(NOSH_ECOMM, "peer-memory reduction timed out (a rank is not responding)");
+  return h[0];
 }
 
 double dot_dev(Ctx *ctx, const double2 *x, const double2 *y) {
@@ -811,10 +825,7 @@ double dot_dev(Ctx *ctx, const double2 *x, const double2 *y) {
   FinArgs F = fin_args(ctx, FIN_DOT, 0, 0.0, 0, ctx->scalar_out.p);
   if (ctx->n_chunks) KLAUNCH(ctx, k_dot, (unsigned)ctx->n_chunks, TPB, x, y, ctx->No, ctx->partials.p, F);
   finalize_launch(ctx, F);
-  double h;
-  CUDA_CHECK(cudaMemcpyAsync(&h, ctx->scalar_out.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  return h;
+  return fetch_scalar(ctx);
 }
 
 double weighted_sum_dev(Ctx *ctx, int mode, const double2 *a, const double2 *b) {
@@ -823,10 +834,7 @@ double weighted_sum_dev(Ctx *ctx, int mode, const double2 *a, const double2 *b) 
   if (ctx->n_chunks)
     KLAUNCH(ctx, k_weighted, (unsigned)ctx->n_chunks, TPB, mode, ctx->cv.p, a, b, ctx->No, ctx->partials.p, F);
   finalize_launch(ctx, F);
-  double h;
-  CUDA_CHECK(cudaMemcpyAsync(&h, ctx->scalar_out.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  return h;
+  return fetch_scalar(ctx);
 }
 
 void jac_diags_dev(Ctx *ctx, double g, const double2 *psi) {
@@ -853,14 +861,40 @@ void axpy_dev(Ctx *ctx, double a, const double2 *x, double2 *y) {
   if (ctx->No) KLAUNCH(ctx, k_axpy, (unsigned)cdiv(ctx->No, 256), 256, a, x, y, ctx->No);
 }
 
-// y = op(x) with the plain/diag epilogues; x must have Nl entries when nranks > 1
+// One operator apply with its halo exchange (the Tpetra Import + local SpMV of CrsMatrix::apply,
+// src/jacobian_operator.cpp:65).  Several GPUs with peer memory: my boundary entries start travelling
+// into the neighbours' landing buffers, the chunks whose rows reference no ghost run meanwhile, then a
+// one-CTA wait, then the boundary chunks with the ghosts read straight from the landing slot (A.xg) --
+// x itself needs no ghost room and is never copied.  NCCL fallback: exchange into x[No..), one launch.
+void apply_halo_dev(Ctx *ctx, int epi, int fuse, ApplyArgs &A, double2 *x) {
+  if (ctx->nranks == 1) {
+    launch_apply(ctx, epi, fuse, A);
+    return;
+  }
+  if (!ctx->p2p.ok) {
+    halo_exchange(ctx, x);
+    launch_apply(ctx, epi, fuse, A);
+    return;
+  }
+  halo_begin(ctx, x);
+  A.chunk_list = ctx->chunks_int.p;
+  A.n_list = (int)ctx->n_chunks_int;
+  launch_apply(ctx, epi, fuse, A);
+  A.xg = halo_end(ctx, nullptr);
+  A.chunk_list = ctx->chunks_bnd.p;
+  A.n_list = (int)ctx->n_chunks_bnd;
+  launch_apply(ctx, epi, fuse, A);
+  A.chunk_list = nullptr;
+  A.xg = nullptr;
+}
+
+// y = op(x) with the plain/diag epilogues.  nranks > 1 without peer memory: x must have Nl entries.
 void apply_op_dev(Ctx *ctx, int op, double2 *x, double2 *y) {
   ensure_work(ctx);
   ApplyArgs A = base_args(ctx, nullptr, x, y);
   int epi;
   op_args(ctx, op, A, &epi);
-  halo_exchange(ctx, x);
-  launch_apply(ctx, epi, FUSE_NONE, A);
+  apply_halo_dev(ctx, epi, FUSE_NONE, A, x);
 }
 
 // F(psi) = K psi + c t (V + g |psi|^2) psi   (nls::compute_f_)
@@ -871,8 +905,7 @@ void compute_f_dev(Ctx *ctx, double g, double2 *psi, double2 *f) {
   A.thick = ctx->thick.p;
   A.V = ctx->Vcur.p;
   A.g = g;
-  halo_exchange(ctx, psi);
-  launch_apply(ctx, EPI_F, FUSE_NONE, A);
+  apply_halo_dev(ctx, EPI_F, FUSE_NONE, A, psi);
 }
 
 // z = M r with the selected preconditioner (M = I is handled by the callers: z aliases r)
@@ -952,6 +985,7 @@ void minres_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, dou
       res->iterations = hs.iter;
       res->converged = hs.converged;
       res->relres = hs.relres;
+      res->breakdown = hs.breakdown;
     }
     if (hist_host) {
       CUDA_CHECK(cudaMemcpyAsync(hist_host, ctx->hist.p, sizeof(double) * (hs.iter + 1), cudaMemcpyDeviceToHost,
@@ -963,13 +997,20 @@ void minres_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, dou
   }
 multi_launch:
   if (ctx->nranks > 1 && ctx->p2p.ok && !pc && ctx->layout == NOSH_LAYOUT_SELL32 && ctx->persistent_mgpu && grid > 0 &&
-      (epi == EPI_DIAG || epi == EPI_NONE)) {
-    // EXPERIMENTAL (NOSH_B200_PERSISTENT_MGPU=1, not validated on hardware yet): see k_minres_persistent_mgpu
-    int coop = 0, per_sm = 0, sms = 0;
-    CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minres_persistent_mgpu<EPI_DIAG>, CHUNK, 0));
-    CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-    if (coop && per_sm > 0) {
+      (epi == EPI_DIAG || epi == EPI_NONE) && ctx->persist_grid_mgpu >= 0) {
+    // one cooperative launch per solve and rank (k_minres_persistent_mgpu).  Every rank must take the same
+    // decision: all of them run the same binary on the same kind of device, and n_chunks > 0 everywhere is
+    // checked at set-up (a rank that owns nothing makes every rank use the multi-launch loop).
+    if (ctx->persist_grid_mgpu == 0) {
+      int coop = 0, per_sm = 0, sms = 0;
+      CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minres_persistent_mgpu<EPI_DIAG>, CHUNK, 0));
+      CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+      ctx->persist_grid_mgpu = (coop && per_sm > 0) ? per_sm * sms : -1;
+    }
+    bool all_own = true;  // part_begin is the same table on every rank
+    for (int r = 0; r < ctx->nranks; r++) all_own = all_own && ctx->part_begin[r + 1] > ctx->part_begin[r];
+    if (ctx->persist_grid_mgpu > 0 && all_own) {
       PersistMgpuArgs MA;
       memset(&MA, 0, sizeof(MA));
       MA.S.A = A;
@@ -989,7 +1030,6 @@ multi_launch:
       MA.S.cpg = ctx->chunks_per_group;
       MA.S.maxit = maxit;
       MA.q = ctx->p2p.view;
-      MA.q.epoch = ctx->p2p.epoch;
       MA.group_begin = ctx->group_begin;
       MA.n_groups_local = ctx->n_groups_local;
       MA.send_idx = ctx->send_idx.p;
@@ -1000,22 +1040,19 @@ multi_launch:
         MA.push0.off[r] = MA.push1.off[r] = ctx->send_off[r];
       }
       MA.push0.off[ctx->nranks] = MA.push1.off[ctx->nranks] = ctx->send_off[ctx->nranks];
-      MA.epoch_out = (unsigned long long *)(ctx->scalar_out.p + 4);
       const void *fn = epi == EPI_DIAG ? (const void *)k_minres_persistent_mgpu<EPI_DIAG>
                                        : (const void *)k_minres_persistent_mgpu<EPI_NONE>;
-      const unsigned pgrid = (unsigned)std::min<int64_t>((int64_t)per_sm * sms, ctx->n_chunks);
+      const unsigned pgrid = (unsigned)std::min<int64_t>(ctx->persist_grid_mgpu, ctx->n_chunks);
       void *kargs[] = {&MA};
       CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(pgrid), dim3(CHUNK), kargs, 0, ctx->stream));
       ctx->launches++;
-      unsigned long long ep = 0;
-      CUDA_CHECK(cudaMemcpyAsync(&ep, MA.epoch_out, sizeof(ep), cudaMemcpyDeviceToHost, ctx->stream));
       poll_done(ctx, &hs);
-      ctx->p2p.epoch = ep;
       if (p2p_check_error(ctx)) NOSH_THROW(NOSH_ECOMM, "peer-memory reduction timed out (a rank is not responding)");
       if (res) {
         res->iterations = hs.iter;
         res->converged = hs.converged;
         res->relres = hs.relres;
+        res->breakdown = hs.breakdown;
       }
       if (hist_host) {
         CUDA_CHECK(cudaMemcpyAsync(hist_host, ctx->hist.p, sizeof(double) * (hs.iter + 1), cudaMemcpyDeviceToHost,
@@ -1117,6 +1154,7 @@ multi_launch:
     res->iterations = hs.iter;
     res->converged = hs.converged;
     res->relres = hs.relres;
+    res->breakdown = hs.breakdown;
   }
   if (hist_host) {
     CUDA_CHECK(cudaMemcpyAsync(hist_host, ctx->hist.p, sizeof(double) * (hs.iter + 1), cudaMemcpyDeviceToHost,
@@ -1183,6 +1221,7 @@ void cg_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, double2
     res->iterations = hs.iter;
     res->converged = hs.converged;
     res->relres = hs.relres;
+    res->breakdown = hs.breakdown;
   }
   if (hist_host) {
     CUDA_CHECK(cudaMemcpyAsync(hist_host, ctx->hist.p, sizeof(double) * (hs.iter + 1), cudaMemcpyDeviceToHost,
@@ -1217,14 +1256,13 @@ void compute_dfdp_dev(Ctx *ctx, int np, const char *const *names, const double *
   ApplyArgs A = base_args(ctx, ctx->dKval.p, psi, out);
   A.cv = ctx->cv.p;
   A.thick = ctx->thick.p;
-  halo_exchange(ctx, psi);
   if (strcmp(pname, "g") == 0) {  // src/model_evaluator_nls.cpp:665-674
-    launch_apply(ctx, EPI_DG, FUSE_NONE, A);
+    apply_halo_dev(ctx, EPI_DG, FUSE_NONE, A, psi);
   } else {  // :676-691
     ctx->dvdp.ensure(ctx->No > 0 ? ctx->No : 1);
     potential_dvdp(ctx, pname, ctx->dvdp.p);
     A.V = ctx->dvdp.p;
-    launch_apply(ctx, EPI_DV, FUSE_NONE, A);
+    apply_halo_dev(ctx, EPI_DV, FUSE_NONE, A, psi);
   }
 }
 
@@ -1237,7 +1275,7 @@ void newton_dev(Ctx *ctx, int np, const char *const *names, const double *values
   keo_fill(ctx, np, names, values, false);
   update_potential(ctx, np, names, values);
   double2 *F = ctx->work[6].p, *D = ctx->work[7].p;
-  int k = 0, total = 0;
+  int k = 0, total = 0, lin_failed = 0;
   compute_f_dev(ctx, g, psi, F);
   double fn = sqrt(dot_dev(ctx, F, F));
   if (fnorms) fnorms[0] = fn;
@@ -1247,20 +1285,28 @@ void newton_dev(Ctx *ctx, int np, const char *const *names, const double *values
     // evalModel(W_prec): keo_regularized::rebuild at the current state (src/model_evaluator_nls.cpp:507-522)
     if (ctx->precond != NOSH_PREC_NONE) keoreg_diags_dev(ctx, g, psi);
     nosh_krylov_result kr;
+    memset(&kr, 0, sizeof(kr));
     jacobian_solve(ctx, F, -1.0, D, lin_tol, lin_maxit, &kr);
     if (lin_iters) lin_iters[k] = kr.iterations;
     total += kr.iterations;
+    if (kr.breakdown) {  // Lanczos breakdown / indefinite preconditioner: D is not a Newton direction
+      lin_failed = 2;
+      break;
+    }
+    if (!kr.converged) lin_failed = 1;  // NOX takes the step of an unconverged linear solve, too; recorded
     axpy_dev(ctx, 1.0, D, psi);
     compute_f_dev(ctx, g, psi, F);
     fn = sqrt(dot_dev(ctx, F, F));
     k++;
     if (fnorms) fnorms[k] = fn;
+    if (!(fn == fn)) break;  // NaN residual: nothing further to gain
   }
   if (res) {
     res->steps = k;
     res->converged = fn < nl_tol;
     res->total_linear_iterations = total;
     res->fnorm = fn;
+    res->linear_solve_status = lin_failed;
   }
 }
 
@@ -1434,9 +1480,12 @@ void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *val
         if (its >= opt->nl_maxit || !(nrm == nrm)) break;
         compute_dfdp_dev(ctx, np, names, vals.data(), pname, psi, Fp.p);
         nosh_krylov_result ka, kb;
+        memset(&ka, 0, sizeof(ka));
+        memset(&kb, 0, sizeof(kb));
         jacobian_solve(ctx, F, -1.0, Av.p, opt->lin_tol, opt->lin_maxit, &ka);
         jacobian_solve(ctx, Fp.p, -1.0, Bv.p, opt->lin_tol, opt->lin_maxit, &kb);
         lin += ka.iterations + kb.iterations;
+        if (ka.breakdown || kb.breakdown) break;  // failed step: halved below
         const double xa = dot_dev(ctx, XD.p, Av.p) / len, xb = dot_dev(ctx, XD.p, Bv.p) / len;
         const double dp = -(gc + xa) / (pdot + xb);
         axpy_dev(ctx, 1.0, Av.p, psi);

@@ -1,7 +1,11 @@
 // krylov.h -- solvers and vector utilities on device pointers (krylov.cu)
 #pragma once
+#include "apply.cuh"
 #include "common.cuh"
 namespace nosh {
+// one operator apply including its halo exchange (overlapped over peer memory); x: owned entries suffice when
+// ctx->p2p.ok, otherwise Nl entries
+void apply_halo_dev(Ctx *ctx, int epi, int fuse, ApplyArgs &A, double2 *x);
 void ensure_work(Ctx *ctx);
 double dot_dev(Ctx *ctx, const double2 *x, const double2 *y);
 void jac_diags_dev(Ctx *ctx, double g, const double2 *psi);

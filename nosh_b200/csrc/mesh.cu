@@ -186,6 +186,32 @@ __global__ void k_tetgrid_cells(int64_t hex_begin, int64_t nhex, int nx, int ny,
   cells[t] = make_int4(v[0], v[1], v[2], v[3]);
 }
 
+// ---- validation of caller-supplied connectivity (the generator's cells are valid by construction) ----
+// err: 1 = vertex index outside [0, nv); 2 = a vertex repeated inside one cell.  first: lowest offending cell.
+template <int NVC>
+__global__ void k_validate_cells(const int32_t *cellsG, int64_t nc, int64_t nv, int *err, unsigned long long *first) {
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  int32_t v[NVC];
+  int bad = 0;
+#pragma unroll
+  for (int i = 0; i < NVC; i++) {
+    v[i] = cellsG[c * NVC + i];
+    if (v[i] < 0 || (int64_t)v[i] >= nv) bad = 1;
+  }
+  if (!bad) {
+#pragma unroll
+    for (int i = 0; i < NVC; i++)
+#pragma unroll
+      for (int j = i + 1; j < NVC; j++)
+        if (v[i] == v[j]) bad = 2;
+  }
+  if (bad) {
+    atomicMax(err, bad == 1 ? 2 : 1);  // an out-of-range index outranks a repeated vertex
+    atomicMin(first, (unsigned long long)c);
+  }
+}
+
 // ---- localisation ----------------------------------------------------------------------
 template <int NVC>
 __global__ void k_flag_cells(const int32_t *cellsG, int64_t nc, int64_t vb, int64_t ve, int32_t *flag) {
@@ -787,6 +813,27 @@ void mesh_from_host(Ctx *ctx, int dim, int64_t nv, const double *coords, int64_t
   cellsG.alloc(ncells * nvc);
   CUDA_CHECK(cudaMemcpyAsync(cellsG.p, cells, sizeof(int32_t) * ncells * nvc, cudaMemcpyHostToDevice,
                              ctx->stream));
+  // the connectivity comes from the caller: every later kernel indexes with it, so check it first
+  // (negative / too large indices would read and write out of bounds on the device)
+  {
+    DBuf<int> verr;
+    DBuf<unsigned long long> vfirst;
+    verr.alloc(1);
+    vfirst.alloc(1);
+    CUDA_CHECK(cudaMemsetAsync(verr.p, 0, sizeof(int), ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(vfirst.p, 0xFF, sizeof(unsigned long long), ctx->stream));
+    if (dim == 3)
+      LAUNCH(ctx, (k_validate_cells<4>), ncells, cellsG.p, ncells, nv, verr.p, vfirst.p);
+    else
+      LAUNCH(ctx, (k_validate_cells<3>), ncells, cellsG.p, ncells, nv, verr.p, vfirst.p);
+    const int e = fetch(ctx, verr.p);
+    if (e) {
+      const unsigned long long c = fetch(ctx, vfirst.p);
+      if (e == 2)
+        NOSH_THROW(NOSH_EMESH, "Illegal mesh: cell %llu references a vertex outside [0, %lld)", c, (long long)nv);
+      NOSH_THROW(NOSH_EMESH, "Illegal mesh: cell %llu references the same vertex twice", c);
+    }
+  }
   DBuf<double> gc;
   gc.alloc(nv * 3);
   CUDA_CHECK(cudaMemcpyAsync(gc.p, coords, sizeof(double) * nv * 3, cudaMemcpyHostToDevice, ctx->stream));

@@ -220,13 +220,17 @@ static __device__ __forceinline__ void finalize_levels(const FinArgs &F, double 
     __syncthreads();
   }
   const double *gs = F.stage == 2 ? F.grecv : F.gsend;
+  bool comm_failed = false;
   if (WITH_P2P && F.stage == 3) {
     // all-gather of the group sums over NVLink: store mine into every rank's slot (own included),
     // publish an epoch flag to every rank, wait for everybody's flag.  Ranks are never more
-    // than one reduction apart, so two slots are enough.  Peer r's flag also tells me that all
+    // than one reduction apart, so two slots are enough; the epoch counts the reductions that were
+    // EXECUTED (device-side counter: launches skipped after convergence do not advance it, so two
+    // consecutive executed reductions never share a slot).  Peer r's flag also tells me that all
     // NVLink stores r issued before it (its halo push) have landed.
     const P2PView &q = F.p2p;
-    const int slot = (int)(q.epoch & 1ull);
+    const unsigned long long epoch = *q.epoch_ctr + 1ull;  // read by all threads before thread 0 bumps it below
+    const int slot = (int)(epoch & 1ull);
     const int nloc = (int)F.n_groups_local;
     for (int i = threadIdx.x; i < nloc * q.P; i += blockDim.x) {
       const int r = i / nloc, g = (int)F.group_begin + i % nloc;
@@ -235,11 +239,11 @@ static __device__ __forceinline__ void finalize_levels(const FinArgs &F, double 
     __threadfence_system();
     __syncthreads();
     if ((int)threadIdx.x < q.P) {
-      *((volatile unsigned long long *)&q.flags[threadIdx.x][q.me]) = q.epoch;
+      *((volatile unsigned long long *)&q.flags[threadIdx.x][q.me]) = epoch;
       const volatile unsigned long long *mine = (const volatile unsigned long long *)&q.flags[q.me][threadIdx.x];
       const long long t0 = clock64();
-      while (*mine < q.epoch) {
-        if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer is gone; fail instead of hanging
+      while (*mine < epoch) {
+        if (clock64() - t0 > q.timeout) {  // a peer is gone; fail instead of hanging
           *q.err = 1;
           break;
         }
@@ -247,6 +251,8 @@ static __device__ __forceinline__ void finalize_levels(const FinArgs &F, double 
     }
     __syncthreads();
     __threadfence_system();
+    if (threadIdx.x == 0) *q.epoch_ctr = epoch;
+    comm_failed = *((volatile int *)q.err) != 0;
     gs = q.red[q.me] + slot * MAX_GROUPS;
   }
   for (int seg = w; seg < 32; seg += nw) {
@@ -259,7 +265,20 @@ static __device__ __forceinline__ void finalize_levels(const FinArgs &F, double 
   if (w == 0) {
     double t = sm[l];
     t = warp_sum(t);
-    if (l == 0) fin_scalars(F, t);
+    if (l == 0) {
+      if (comm_failed) {
+        // stale group sums: do not advance the recurrences; stop the solver / flag the scalar
+        if (F.what == FIN_DOT) {
+          F.out[0] = t;
+          F.out[1] = 1.0;
+        } else {
+          F.st->done = 1;
+          F.st->converged = 0;
+        }
+      } else {
+        fin_scalars(F, t);
+      }
+    }
   }
 }
 

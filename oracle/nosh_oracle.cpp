@@ -668,26 +668,27 @@ ORC_API void orc_compute_dfdp(int64_t nv, const int64_t *rowptr, const int32_t *
 // all-reduce over ranks does).
 // -----------------------------------------------------------------------------
 namespace {
+// g_dot_parts > 0: the sum is split into that many contiguous parts ("ranks") whatever the number of
+// threads executing it, so iteration counts can be generated for the reference's rank counts (1, 2, 7:
+// test/CMakeLists.txt:18-23) independently of the machine the oracle runs on.  0: parts = threads.
+int g_dot_parts = 0;
 double pdot(int64_t n, const double *a, const double *b, int nt) {
-  if (nt <= 1) {
+  const int parts = g_dot_parts > 0 ? g_dot_parts : (nt > 1 ? nt : 1);
+  if (parts <= 1) {
     double s = 0.0;
     for (int64_t i = 0; i < n; i++) s += a[i] * b[i];
     return s;
   }
-  std::vector<double> part(nt, 0.0);
-#pragma omp parallel num_threads(nt)
-  {
-    int t = 0;
-#ifdef _OPENMP
-    t = omp_get_thread_num();
-#endif
-    int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+  std::vector<double> part(parts, 0.0);
+#pragma omp parallel for schedule(static) num_threads(nt > 0 ? nt : 1)
+  for (int t = 0; t < parts; t++) {
+    int64_t lo = n * t / parts, hi = n * (t + 1) / parts;
     double s = 0.0;
     for (int64_t i = lo; i < hi; i++) s += a[i] * b[i];
     part[t] = s;
   }
   double s = 0.0;
-  for (int t = 0; t < nt; t++) s += part[t];
+  for (int t = 0; t < parts; t++) s += part[t];
   return s;
 }
 
@@ -860,6 +861,8 @@ ORC_API int orc_newton(int64_t nv, const int64_t *rowptr, const int32_t *cols, c
   }
   return k;
 }
+
+ORC_API void orc_set_dot_parts(int parts) { g_dot_parts = parts > 0 ? parts : 0; }
 
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP

@@ -83,12 +83,20 @@ def lib():
                                  _f64p, C.c_double, C.c_int, C.c_double, C.c_int, _i32p, _f64p,
                                  C.c_int]
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_dot_parts.restype = None
+        L.orc_set_dot_parts.argtypes = [C.c_int]
         _lib = L
     return _lib
 
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def set_dot_parts(parts):
+    """Split every dot product of the Krylov solvers into `parts` contiguous partial sums (the image of
+    `parts` MPI ranks), independently of the number of threads; 0 = one part per thread (default)."""
+    lib().orc_set_dot_parts(int(parts))
 
 
 def _ptr(a):

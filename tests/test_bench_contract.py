@@ -12,7 +12,7 @@ BASE_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 def test_reference_arm_runs_on_the_cpu_and_prints_one_json_line():
     env = dict(os.environ, OMP_NUM_THREADS="1")     # what torchrun exports: the arm must still use every core
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--cpu-n", "16",
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--ref-n", "16",
                         "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
