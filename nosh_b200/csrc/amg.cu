@@ -201,13 +201,14 @@ __global__ void k_l0_fill(const int32_t *rowptr, const int32_t *col, const int32
 // storage (both scalar rows of a complex block row have the same one).  They depend on mu through
 // |cos a| + |sin a|, so they are refreshed with the diagonal whenever the matrix changes -- a hierarchy
 // kept across a continuation run must not smooth with stale bounds.
-__global__ void k_l0_offsum(const int32_t *slice_off, const int32_t *col, const double2 *K, int64_t No,
-                            double *offsum) {
+__global__ void k_l0_offsum(const int32_t *slice_off, const int32_t *sell_pos, const int32_t *col, const double2 *K,
+                            int64_t No, double *offsum) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= No) return;
-  const int base = slice_off[i >> 5], end = slice_off[(i >> 5) + 1];
+  const int64_t q = sell_pos ? (int64_t)sell_pos[i] : i;  // SELL position of row i (SELL-32-sigma, mesh.cu)
+  const int base = slice_off[q >> 5], end = slice_off[(q >> 5) + 1];
   double s = 0.0;
-  for (int p = base + (int)(i & 31); p < end; p += 32) {
+  for (int p = base + (int)(q & 31); p < end; p += 32) {
     const int c = col[p];
     if (c != i && c < No) {
       const double2 k = K[p];
@@ -794,6 +795,7 @@ void level_apply(Ctx *ctx, AmgLevel &L, int lev, int mode, const double2 *x, dou
     A.nslices = ctx->nslices;
     A.rowptr = ctx->rowptr.p;
     A.slice_off = ctx->slice_off.p;
+    A.sell_row = ctx->sell_permuted ? ctx->sell_row.p : nullptr;
     A.col = ctx->col.p;
     A.val = ctx->Kval.p;
     A.x = x;
@@ -850,7 +852,8 @@ double estimate_lambda(Ctx *ctx, AmgLevel &L, int lev, DBuf<double> &scratch) {
 }
 
 void l0_refresh_diag(Ctx *ctx, AmgLevel &L) {
-  ALAUNCH(ctx, k_l0_offsum, ctx->No, ctx->slice_off.p, ctx->col.p, ctx->Kval.p, ctx->No, L.offsum.p);
+  ALAUNCH(ctx, k_l0_offsum, ctx->No, ctx->slice_off.p, ctx->sell_permuted ? ctx->sell_pos.p : nullptr, ctx->col.p,
+          ctx->Kval.p, ctx->No, L.offsum.p);
   ALAUNCH(ctx, k_l0_dinv, ctx->No, ctx->Kval.p, ctx->diag_slot.p, ctx->pd0.p, ctx->pd1.p, L.offsum.p, ctx->No,
           L.dinv.p, L.sinv.p);
 }

@@ -75,8 +75,9 @@ __global__ void __launch_bounds__(CHUNK, MINB) k_apply_sell(const ApplyArgs A) {
   if (A.gate && A.gate->done) return;
   __shared__ double red[32];
   const int chunk = A.chunk_list ? __ldg(A.chunk_list + blockIdx.x) : (int)blockIdx.x;
-  const int64_t row = (int64_t)chunk * CHUNK + threadIdx.x;
-  const int64_t slice = row >> 5;
+  const int64_t pos = (int64_t)chunk * CHUNK + threadIdx.x;  // SELL position; the row stored there:
+  const int64_t row = A.sell_row ? (int64_t)__ldg(A.sell_row + pos) : pos;
+  const int64_t slice = pos >> 5;
   const int lane = threadIdx.x & 31;
   const double scale = (FUSE == FUSE_MINRES) ? A.st->inv_beta : 1.0;
   double2 acc = make_double2(0.0, 0.0);

@@ -35,6 +35,7 @@ struct ApplyArgs {
   int64_t nslices;
   const int32_t *rowptr;     // CSR: No+1
   const int32_t *slice_off;  // SELL: nslices+1
+  const int32_t *sell_row;   // SELL-32-sigma: row stored at a SELL position (NULL: identity); mesh.cu
   const int32_t *col;
   const double2 *val;
   const double2 *x;  // Nl entries (owned + ghosts); owned entries only when xg is set

@@ -156,6 +156,7 @@ nosh_status nosh_ctx_create(int device, void *stream, nosh_ctx **out) {
   }
   if (const char *e = getenv("NOSH_B200_PERSISTENT_MINRES")) ctx->persistent_minres = atoi(e) != 0;
   if (const char *e = getenv("NOSH_B200_PERSISTENT_MGPU")) ctx->persistent_mgpu = atoi(e) != 0;
+  if (const char *e = getenv("NOSH_B200_SELL_SIGMA")) ctx->sell_sigma = atoi(e) < 0 ? -1 : (atoi(e) != 0);
   *out = ctx;
   return NOSH_OK;
 }
@@ -443,6 +444,7 @@ nosh_status nosh_matrix_apply(nosh_ctx *ctx, nosh_matrix_id which, const double 
     A.nslices = ctx->nslices;
     A.rowptr = ctx->rowptr.p;
     A.slice_off = ctx->slice_off.p;
+    A.sell_row = ctx->sell_permuted ? ctx->sell_row.p : nullptr;
     A.col = ctx->col.p;
     A.val = val;
     A.x = x;
@@ -877,6 +879,10 @@ nosh_status nosh_ctx_set_tuning(nosh_ctx *ctx, const char *key, int value) {
     ctx->persistent_minres = value != 0;
   } else if (strcmp(key, "persistent_mgpu") == 0) {
     ctx->persistent_mgpu = value != 0;
+  } else if (strcmp(key, "sell_sigma") == 0) {
+    if (ctx->has_mesh) NOSH_THROW(NOSH_ESTATE, "sell_sigma must be chosen before the mesh is set");
+    if (value < -1 || value > 1) NOSH_THROW(NOSH_EINVAL, "sell_sigma: -1 auto, 0 off, 1 on");
+    ctx->sell_sigma = value;
   } else {
     NOSH_THROW(NOSH_EKEY, "unknown tuning key \"%s\"", key);
   }

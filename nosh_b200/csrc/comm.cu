@@ -132,7 +132,7 @@ void comm_destroy(Ctx *ctx) {
 }
 
 // set-up only: all-gather of one fixed-size HOST record per rank
-static void exchange_allgather(Ctx *ctx, const void *send, void *recv, size_t bytes) {
+void exchange_allgather(Ctx *ctx, const void *send, void *recv, size_t bytes) {
   if (ctx->host_ag) {
     const int rc = ctx->host_ag(ctx->host_ag_user, send, recv, (int64_t)bytes);
     if (rc != 0) NOSH_THROW(NOSH_ECOMM, "host all-gather callback failed (%d)", rc);

@@ -7,6 +7,8 @@ void comm_init(Ctx *ctx, const void *id128, int rank, int nranks);
 // set-up through the caller's communicator (host all-gather callback), data path over peer memory only
 void comm_init_host(Ctx *ctx, int rank, int nranks, HostAllgather fn, void *user);
 void comm_destroy(Ctx *ctx);
+// set-up only: all-gather of one fixed-size HOST record per rank (caller's communicator or NCCL)
+void exchange_allgather(Ctx *ctx, const void *send, void *recv, size_t bytes);
 void comm_allreduce_sum(Ctx *ctx, const double *send, double *recv, int64_t n);
 void halo_setup(Ctx *ctx);
 void halo_exchange(Ctx *ctx, double2 *vec, cudaStream_t stream = nullptr);

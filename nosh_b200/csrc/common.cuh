@@ -197,6 +197,9 @@ struct Ctx {
   DBuf<int32_t> edge_of;            // nb: edge of a CSR position (-1: diagonal)
   DBuf<int32_t> col;                // nstored local col ids (storage order)
   DBuf<int32_t> slice_off;          // nslices+1 (SELL)
+  DBuf<int32_t> sell_row, sell_pos; // SELL-32-sigma: row stored at a position / position of a row (mesh.cu)
+  bool sell_permuted = false;
+  int sell_sigma = -1;              // -1 auto (sort when the padding exceeds 5 %; always with several ranks), 0 off, 1 on
   DBuf<int32_t> slot_ij, slot_ji;   // E storage positions (-1: row not owned)
   DBuf<int32_t> diag_slot;          // No storage positions
   DBuf<double2> Kval, dKval;        // nstored

@@ -350,8 +350,9 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent(const PersistArg
     {
       const double scale = s_st.inv_beta, f = s_st.f_r1;
       for (int64_t chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
-        const int64_t row = chunk * CHUNK + tid;
-        const int64_t slice = row >> 5;
+        const int64_t pos = chunk * CHUNK + tid;
+        const int64_t row = P.A.sell_row ? (int64_t)__ldg(P.A.sell_row + pos) : pos;
+        const int64_t slice = pos >> 5;
         double2 acc = make_double2(0.0, 0.0);
         if (slice < P.A.nslices) {
           int p = __ldg(P.A.slice_off + slice) + lane;
@@ -566,8 +567,9 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent_mgpu(const Persi
     {
       const double scale = s_st.inv_beta, f = s_st.f_r1;
       for (int64_t chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
-        const int64_t row = chunk * CHUNK + tid;
-        const int64_t slice = row >> 5;
+        const int64_t pos = chunk * CHUNK + tid;
+        const int64_t row = P.A.sell_row ? (int64_t)__ldg(P.A.sell_row + pos) : pos;
+        const int64_t slice = pos >> 5;
         double2 acc = make_double2(0.0, 0.0);
         if (slice < P.A.nslices) {
           int p = __ldg(P.A.slice_off + slice) + lane;
@@ -743,6 +745,7 @@ ApplyArgs base_args(Ctx *ctx, const double2 *val, const double2 *x, double2 *y) 
   A.nslices = ctx->nslices;
   A.rowptr = ctx->rowptr.p;
   A.slice_off = ctx->slice_off.p;
+  A.sell_row = ctx->sell_permuted ? ctx->sell_row.p : nullptr;
   A.col = ctx->col.p;
   A.val = val;
   A.x = x;

