@@ -54,6 +54,16 @@ struct ApplyArgs {
   const double2 *r1;
   double *partials;
   int host_iter;
+  // with xg: CTAs with blockIdx.x >= halo_first_block wait for the neighbours' halo flags of exchange
+  // halo_epoch before they gather (the chunk list puts the chunks that reference ghosts last)
+  const HaloView *halo;
+  unsigned long long halo_epoch;
+  int halo_first_block;
+  // ... and the first push_blocks CTAs first store my boundary entries of x into the neighbours' landing buffers
+  // (SELL-32 kernels; 0 = the push was launched separately)
+  const int32_t *send_idx;
+  int64_t n_send;
+  int push_blocks;
   // optional list of chunks to process (interior / boundary split); NULL = all chunks
   const int32_t *chunk_list;
   int n_list;

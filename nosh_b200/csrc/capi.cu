@@ -156,6 +156,7 @@ nosh_status nosh_ctx_create(int device, void *stream, nosh_ctx **out) {
   }
   if (const char *e = getenv("NOSH_B200_PERSISTENT_MINRES")) ctx->persistent_minres = atoi(e) != 0;
   if (const char *e = getenv("NOSH_B200_PERSISTENT_MGPU")) ctx->persistent_mgpu = atoi(e) != 0;
+  if (const char *e = getenv("NOSH_B200_MGPU_FENCE")) ctx->mgpu_fence = atoi(e);
   if (const char *e = getenv("NOSH_B200_SELL_SIGMA")) ctx->sell_sigma = atoi(e) < 0 ? -1 : (atoi(e) != 0);
   *out = ctx;
   return NOSH_OK;
@@ -879,6 +880,8 @@ nosh_status nosh_ctx_set_tuning(nosh_ctx *ctx, const char *key, int value) {
     ctx->persistent_minres = value != 0;
   } else if (strcmp(key, "persistent_mgpu") == 0) {
     ctx->persistent_mgpu = value != 0;
+  } else if (strcmp(key, "mgpu_fence") == 0) {
+    ctx->mgpu_fence = value;
   } else if (strcmp(key, "sell_sigma") == 0) {
     if (ctx->has_mesh) NOSH_THROW(NOSH_ESTATE, "sell_sigma must be chosen before the mesh is set");
     if (value < -1 || value > 1) NOSH_THROW(NOSH_EINVAL, "sell_sigma: -1 auto, 0 off, 1 on");

@@ -289,6 +289,11 @@ void halo_setup(Ctx *ctx) {
     if (!lb.empty())
       CUDA_CHECK(cudaMemcpyAsync(ctx->chunks_bnd.p, lb.data(), sizeof(int32_t) * lb.size(), cudaMemcpyHostToDevice,
                                  ctx->stream));
+    li.insert(li.end(), lb.begin(), lb.end());
+    ctx->chunks_all.alloc(li.size());
+    CUDA_CHECK(cudaMemcpyAsync(ctx->chunks_all.p, li.data(), sizeof(int32_t) * li.size(), cudaMemcpyHostToDevice,
+                               ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // li / lb are about to go out of scope
   }
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   ctx->stats["setup.halo_s"] = now_s() - t0;
@@ -345,20 +350,9 @@ __global__ void __launch_bounds__(256) k_halo_push_signal(const double2 *vec, co
 
 // Consumer side: wait until every neighbour's flag has reached `epoch`; with vec != NULL also copy the
 // landed ghosts behind the owned entries (callers that need one contiguous vector).
-__global__ void __launch_bounds__(256) k_halo_wait(const HaloView h, unsigned long long epoch, const double2 *G,
+__global__ void __launch_bounds__(256) k_halo_wait(const HaloView *h, unsigned long long epoch, const double2 *G,
                                                    int64_t ng, double2 *ghost_out) {
-  if ((int)threadIdx.x < h.P && h.recv_cnt[threadIdx.x] > 0) {
-    const volatile unsigned long long *f = (const volatile unsigned long long *)&h.my_flags[threadIdx.x];
-    const long long t0 = clock64();
-    while (*f < epoch) {
-      if (clock64() - t0 > h.timeout) {
-        *h.err = 1;
-        break;
-      }
-    }
-  }
-  __syncthreads();
-  __threadfence_system();
+  halo_wait_cta(h, epoch);
   if (ghost_out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < ng) ghost_out[i] = __ldcg(G + (int64_t)(epoch & 1ull) * ng + i);
@@ -475,6 +469,8 @@ void p2p_setup(Ctx *ctx) {
     pp.halo.recv_cnt[r] = ctx->recv_count[r];
   }
   pp.halo.send_off[P] = ctx->send_off[P];
+  pp.halo_dev.alloc(1);
+  CUDA_CHECK(cudaMemcpyAsync(pp.halo_dev.p, &pp.halo, sizeof(HaloView), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   pp.ok = true;
   ctx->stats["setup.p2p_s"] = now_s() - t0;
@@ -492,6 +488,13 @@ void halo_begin(Ctx *ctx, const double2 *vec, cudaStream_t stream) {
   ctx->launches++;
   CUDA_CHECK(cudaGetLastError());
 }
+// a new exchange whose push is done by the caller's own kernel (apply.cu: halo_push_cta)
+unsigned long long halo_next_epoch(Ctx *ctx) { return ++ctx->p2p.hepoch; }
+// where the ghosts of the exchange begun last land (Ng entries, ghost order)
+const double2 *halo_slot(Ctx *ctx) {
+  const int64_t ng = ctx->Ng > 0 ? ctx->Ng : 1;
+  return ctx->p2p.ghost.p + (int64_t)(ctx->p2p.hepoch & 1ull) * ng;
+}
 // end: wait for the neighbours' entries of this exchange.  Returns the landing slot (Ng entries, ghost order);
 // with ghost_out != NULL the ghosts are also copied there (vec + No of a contiguous local vector).
 const double2 *halo_end(Ctx *ctx, double2 *ghost_out, cudaStream_t stream) {
@@ -501,7 +504,7 @@ const double2 *halo_end(Ctx *ctx, double2 *ghost_out, cudaStream_t stream) {
   if (ctx->Ng == 0) return slot;
   if (!stream) stream = ctx->stream;
   const unsigned grid = ghost_out ? (unsigned)cdiv(ctx->Ng, 256) : 1u;
-  k_halo_wait<<<grid, 256, 0, stream>>>(pp.halo, pp.hepoch, pp.ghost.p, ctx->Ng, ghost_out);
+  k_halo_wait<<<grid, 256, 0, stream>>>(pp.halo_dev.p, pp.hepoch, pp.ghost.p, ctx->Ng, ghost_out);
   ctx->launches++;
   CUDA_CHECK(cudaGetLastError());
   return slot;

@@ -20,5 +20,7 @@ void p2p_halo_push(Ctx *ctx, int which_r, const double2 *vec);
 // exchange are at the returned pointer (Ng entries) and, with ghost_out != NULL, also copied there
 void halo_begin(Ctx *ctx, const double2 *vec, cudaStream_t stream = nullptr);
 const double2 *halo_end(Ctx *ctx, double2 *ghost_out, cudaStream_t stream = nullptr);
+const double2 *halo_slot(Ctx *ctx);
+unsigned long long halo_next_epoch(Ctx *ctx);
 int p2p_check_error(Ctx *ctx);
 }  // namespace nosh

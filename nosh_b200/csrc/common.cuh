@@ -130,6 +130,7 @@ struct P2P {
   bool ok = false;
   DBuf<unsigned long long> local;       // [2*MAX_GROUPS sums | MAX_RANKS flags | err | epoch | MAX_RANKS halo flags | ticket]
   DBuf<double2> ghost;                  // 2 x Ng landing buffer of the stand-alone halo exchange
+  DBuf<HaloView> halo_dev;              // device copy of `halo` (read by the boundary CTAs of the apply kernels)
   void *opened[4][MAX_RANKS] = {};
   P2PView view;
   HaloView halo;
@@ -171,6 +172,7 @@ struct Ctx {
   int persistent_mgpu = 1;          // multi-GPU persistent loop over peer memory (env NOSH_B200_PERSISTENT_MGPU=0 /
                                     // tuning key "persistent_mgpu" select the multi-launch loop)
   int persist_grid_mgpu = 0;
+  int mgpu_fence = 1;               // measurement knob of k_minres_persistent_mgpu (krylov.cu)
   int persist_grid = 0;             // co-resident CTAs of that kernel (occupancy x SMs), computed once
   int apply_variant = 0;            // measurement knob: which k_apply_sell variant the MINRES loop uses (apply.cu)
   int64_t group_vertices = 65536;
@@ -266,6 +268,7 @@ struct Ctx {
   P2P p2p;
   // chunks (512 rows) whose rows reference no ghost column can be applied before the halo lands
   DBuf<int32_t> chunks_int, chunks_bnd;
+  DBuf<int32_t> chunks_all;         // interior chunks first, boundary chunks last (one launch, the last CTAs wait)
   int64_t n_chunks_int = 0, n_chunks_bnd = 0;
 };
 
@@ -304,6 +307,50 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// Producer side of the stand-alone halo exchange, called by ALL threads of the first `nblocks` CTAs of a grid:
+// store my boundary entries of `vec` into the neighbours' landing buffers (slot = epoch parity) over NVLink;
+// the CTA that draws the last ticket raises my flag in every neighbour.
+__device__ __forceinline__ void halo_push_cta(const HaloView *h, const double2 *vec, const int32_t *idx, int64_t n,
+                                              unsigned long long epoch, int nblocks) {
+  __shared__ int s_last;
+  const int64_t slot = (int64_t)(epoch & 1ull);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)nblocks * blockDim.x) {
+    int r = 0;
+    while (r + 1 < h->P && i >= h->send_off[r + 1]) r++;
+    h->dst[r][slot * h->slot_stride[r] + (i - h->send_off[r])] = vec[idx[i]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(h->ticket, 1u);
+    s_last = (t == (unsigned int)nblocks - 1u);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence_system();
+    if ((int)threadIdx.x < h->P && h->send_off[threadIdx.x + 1] > h->send_off[threadIdx.x])
+      *((volatile unsigned long long *)h->flag_of[threadIdx.x]) = epoch;
+    if (threadIdx.x == 0) *h->ticket = 0u;
+  }
+}
+
+// Consumer side of the stand-alone halo exchange, called by ALL threads of a CTA: wait until every neighbour's
+// flag has reached `epoch` (its entries of this exchange have landed in my buffer), then acquire.
+__device__ __forceinline__ void halo_wait_cta(const HaloView *h, unsigned long long epoch) {
+  if ((int)threadIdx.x < h->P && h->recv_cnt[threadIdx.x] > 0) {
+    const volatile unsigned long long *f = (const volatile unsigned long long *)&h->my_flags[threadIdx.x];
+    const long long t0 = clock64();
+    while (*f < epoch) {
+      if (clock64() - t0 > h->timeout) {
+        *h->err = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
 }
 
 // Deterministic CTA sum (fixed tree: xor-shuffle inside each warp, then the warp

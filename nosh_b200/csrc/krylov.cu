@@ -461,8 +461,9 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent(const PersistArg
 //     peers' flags | sync | level 3 from my slot (every CTA, redundantly).
 // The halo push of r_{h+1} is a grid-stride loop in the phase after B; every pushing thread fences
 // system-wide before the grid sync that precedes the beta exchange, whose flags therefore also order the
-// pushed ghosts (same argument as the multi-launch path).  Gathers of OWNED entries go through L1 (the grid
-// syncs invalidate it, as in the one-GPU kernel); ghost entries, written by the peers, are read from L2.
+// pushed ghosts (same argument as the multi-launch path).  All gathers are plain loads through L1, as in the
+// one-GPU kernel: entries written by other SMs and ghost entries written by the peers are both ordered before
+// them by the chain  store -> fence -> flag -> CTA 0's spin + fence -> grid sync  (the acquire side invalidates L1).
 // Same chunk partials, same tree, same scalar recurrences => bit-identical to the one-GPU kernel.
 // -------------------------------------------------------------------------------------------------------
 struct PushView {
@@ -476,6 +477,7 @@ struct PersistMgpuArgs {
   const int32_t *send_idx;
   int64_t n_send;
   PushView push0, push1;  // targets when r_{h+1} lives in R0 / R1
+  int fence_mode;
 };
 
 __device__ __forceinline__ void persist_exchange(const PersistMgpuArgs &M, unsigned long long epoch) {
@@ -522,7 +524,6 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent_mgpu(const Persi
   F.tol = s_st.tol;
   F.maxit = s_st.maxit;
   unsigned long long epoch = *M.q.epoch_ctr;  // reductions executed before this launch
-  const int64_t No = P.A.No;
   // level 2 over my groups, level 3 over the gathered sums of all ranks
   auto level2 = [&]() {
     const int64_t gw = (int64_t)blockIdx.x * (CHUNK / 32) + (tid >> 5), nw = (int64_t)gridDim.x * (CHUNK / 32);
@@ -582,14 +583,15 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent_mgpu(const Persi
 #pragma unroll
             for (int u = 0; u < 4; u++) v[u] = ld_stream2(P.A.val + p + 32 * u);
 #pragma unroll
-            for (int u = 0; u < 4; u++) xv[u] = c[u] < No ? rcur[c[u]] : __ldcg(rcur + c[u]);  // ghosts: written by peers
+            for (int u = 0; u < 4; u++) xv[u] = rcur[c[u]];  // owned: other SMs wrote them, ghosts: the peers did --
+                                                             // both ordered by the exchange + grid sync (acquire)
 #pragma unroll
             for (int u = 0; u < 4; u++) cfma(acc, v[u], scaled(xv[u], scale));
           }
           for (; p < pend; p += 32) {
             const int c = ld_stream_i32(P.A.col + p);
             const double2 v = ld_stream2(P.A.val + p);
-            cfma(acc, v, scaled(c < No ? rcur[c] : __ldcg(rcur + c), scale));
+            cfma(acc, v, scaled(rcur[c], scale));
           }
         }
         double contrib = 0.0;
@@ -649,12 +651,19 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent_mgpu(const Persi
     grid.sync();
     level2();
     // halo push of r_{h+1}: my boundary entries into the neighbours' ghost segments over NVLink
-    for (int64_t i = (int64_t)blockIdx.x * CHUNK + tid; i < M.n_send; i += (int64_t)gridDim.x * CHUNK) {
-      int r = 0;
-      while (r + 1 < M.q.P && i >= push.off[r + 1]) r++;
-      push.dst[r][i - push.off[r]] = rprev[M.send_idx[i]];
+    {
+      bool pushed = false;
+      for (int64_t i = (int64_t)blockIdx.x * CHUNK + tid; i < M.n_send; i += (int64_t)gridDim.x * CHUNK) {
+        int r = 0;
+        while (r + 1 < M.q.P && i >= push.off[r + 1]) r++;
+        push.dst[r][i - push.off[r]] = rprev[M.send_idx[i]];
+        pushed = true;
+      }
+      // only the threads that stored into a peer fence at system scope (fence_mode 1, default); 0 = every
+      // thread (the first version: measured slower), 2 = none here -- the grid sync orders the stores at GPU
+      // scope and CTA 0 fences system-wide before it raises the flags (measurement knob)
+      if (M.fence_mode == 0 || (M.fence_mode == 1 && pushed)) __threadfence_system();
     }
-    __threadfence_system();
     grid.sync();
     epoch++;
     if (blockIdx.x == 0) persist_exchange(M, epoch);
@@ -866,9 +875,9 @@ void axpy_dev(Ctx *ctx, double a, const double2 *x, double2 *y) {
 
 // One operator apply with its halo exchange (the Tpetra Import + local SpMV of CrsMatrix::apply,
 // src/jacobian_operator.cpp:65).  Several GPUs with peer memory: my boundary entries start travelling
-// into the neighbours' landing buffers, the chunks whose rows reference no ghost run meanwhile, then a
-// one-CTA wait, then the boundary chunks with the ghosts read straight from the landing slot (A.xg) --
-// x itself needs no ghost room and is never copied.  NCCL fallback: exchange into x[No..), one launch.
+// into the neighbours' landing buffers, pushed by the first CTAs of the ONE apply launch, whose chunk list puts
+// the chunks that reference no ghost first; the CTAs of the boundary chunks wait for the neighbours' flags and
+// read the ghosts straight from the landing slot (A.xg) -- x itself needs no ghost room and is never copied.  NCCL fallback: exchange into x[No..), one launch.
 void apply_halo_dev(Ctx *ctx, int epi, int fuse, ApplyArgs &A, double2 *x) {
   if (ctx->nranks == 1) {
     launch_apply(ctx, epi, fuse, A);
@@ -879,16 +888,29 @@ void apply_halo_dev(Ctx *ctx, int epi, int fuse, ApplyArgs &A, double2 *x) {
     launch_apply(ctx, epi, fuse, A);
     return;
   }
-  halo_begin(ctx, x);
-  A.chunk_list = ctx->chunks_int.p;
-  A.n_list = (int)ctx->n_chunks_int;
-  launch_apply(ctx, epi, fuse, A);
-  A.xg = halo_end(ctx, nullptr);
-  A.chunk_list = ctx->chunks_bnd.p;
-  A.n_list = (int)ctx->n_chunks_bnd;
+  // one launch over all chunks, interior first: the CTAs of the boundary chunks (the last ones to be scheduled)
+  // wait for the neighbours' flags themselves, so the exchange hides behind the interior rows
+  A.chunk_list = ctx->chunks_all.p;
+  A.n_list = (int)(ctx->n_chunks_int + ctx->n_chunks_bnd);
+  if (ctx->layout == NOSH_LAYOUT_SELL32 && A.n_list > 0) {
+    // the push rides on the first CTAs of the same launch: ONE kernel per apply, exchange included
+    A.halo_epoch = halo_next_epoch(ctx);
+    A.send_idx = ctx->send_idx.p;
+    A.n_send = ctx->n_send;
+    A.push_blocks = (int)std::min<int64_t>(A.n_list, cdiv(ctx->n_send, CHUNK));
+  } else {
+    halo_begin(ctx, x);
+    A.halo_epoch = ctx->p2p.hepoch;
+    A.push_blocks = 0;
+  }
+  A.xg = halo_slot(ctx);
+  A.halo = ctx->p2p.halo_dev.p;
+  A.halo_first_block = ctx->Ng > 0 ? (int)ctx->n_chunks_int : A.n_list;
   launch_apply(ctx, epi, fuse, A);
   A.chunk_list = nullptr;
   A.xg = nullptr;
+  A.halo = nullptr;
+  A.push_blocks = 0;
 }
 
 // y = op(x) with the plain/diag epilogues.  nranks > 1 without peer memory: x must have Nl entries.
@@ -1037,6 +1059,7 @@ multi_launch:
       MA.n_groups_local = ctx->n_groups_local;
       MA.send_idx = ctx->send_idx.p;
       MA.n_send = ctx->n_send;
+      MA.fence_mode = ctx->mgpu_fence;
       for (int r = 0; r < ctx->nranks; r++) {
         MA.push0.dst[r] = ctx->p2p.R[0][r] + ctx->p2p.ghost_base[r];
         MA.push1.dst[r] = ctx->p2p.R[1][r] + ctx->p2p.ghost_base[r];
