@@ -136,6 +136,16 @@ NOSH_API nosh_status nosh_mesh_set(nosh_ctx *ctx, int dim, int64_t n_vertices,
                                    const double *coords /* host, n_vertices x 3 */,
                                    int64_t n_cells,
                                    const int32_t *cells /* host, n_cells x (dim+1) */);
+/* Partitioned ingestion -- the analogue of MOAB's "PARALLEL=READ_PART;PARTITION=PARALLEL_PARTITION;
+ * PARALLEL_RESOLVE_SHARED_ENTS" read of src/mesh_reader.cpp:32-35: every rank passes only ITS part of a mesh with
+ * n_global vertices: the cells that touch a vertex of its owned range (nosh_partition_range; further cells are
+ * allowed and dropped), the nv_local vertices those cells use -- global id and coordinates -- and the cells as
+ * indices into that local vertex list.  Nothing global is uploaded; results are identical to nosh_mesh_set with
+ * the whole mesh on every rank.  NOSH_EMESH for ids out of range, duplicate ids or degenerate cells. */
+NOSH_API nosh_status nosh_mesh_set_local(nosh_ctx *ctx, int dim, int64_t n_global, int64_t nv_local,
+                                         const int64_t *vertex_gids /* host, nv_local */,
+                                         const double *coords /* host, nv_local x 3 */, int64_t nc_local,
+                                         const int32_t *cells /* host, nc_local x (dim+1), local indices */);
 /* Synthetic input of SURVEY.md 8(d): nx*ny*nz structured vertices on [lo,hi], x fastest,
  * 6 Kuhn tetrahedra per hex cell, interior vertices displaced by jitter*h*U(-1,1)
  * (splitmix64 keyed on seed and the global vertex id).  Generated on the device, each

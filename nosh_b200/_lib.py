@@ -117,6 +117,7 @@ def lib():
         "nosh_partition_range": (C.c_int, [i64, C.c_int, C.c_int, i64, C.POINTER(i64), C.POINTER(i64),
                                            C.POINTER(i64)]),
         "nosh_mesh_set": (C.c_int, [vp, C.c_int, i64, vp, i64, vp]),
+        "nosh_mesh_set_local": (C.c_int, [vp, C.c_int, i64, i64, vp, vp, i64, vp]),
         "nosh_mesh_tetgrid": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, dbl, C.c_uint64]),
         "nosh_mesh_info": (C.c_int, [vp, C.POINTER(MeshInfo)]),
         "nosh_mesh_local_gids": (C.c_int, [vp, vp]),

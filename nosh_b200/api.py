@@ -212,6 +212,25 @@ class Context:
                                       cells.shape[0], _ptr(cells)))
         return self.info()
 
+    def mesh_set_local(self, n_global, vertex_gids, coords, cells):
+        """Partitioned ingestion: this rank's vertices (global ids + coordinates) and cells (indices into them)."""
+        gids = np.ascontiguousarray(vertex_gids, np.int64)
+        coords = np.ascontiguousarray(coords, np.float64)
+        cells = np.ascontiguousarray(cells, np.int32)
+        self._ck(self.L.nosh_mesh_set_local(self.h, cells.shape[1] - 1, int(n_global), gids.shape[0], _ptr(gids),
+                                            _ptr(coords), cells.shape[0], _ptr(cells)))
+        return self.info()
+
+    @staticmethod
+    def local_part(coords, cells, begin, end):
+        """Host helper: the part of a global mesh a rank owning the vertex range [begin, end) has to pass to
+        mesh_set_local -- the cells touching an owned vertex, their vertices, local connectivity."""
+        cells = np.asarray(cells)
+        keep = ((cells >= begin) & (cells < end)).any(axis=1)
+        sub = cells[keep]
+        gids, inv = np.unique(sub, return_inverse=True)
+        return gids.astype(np.int64), np.asarray(coords)[gids], inv.reshape(sub.shape).astype(np.int32)
+
     def mesh_tetgrid(self, nx, ny=None, nz=None, lo=(-5.0, -5.0, -5.0), hi=(5.0, 5.0, 5.0),
                      jitter=0.2, seed=1234):
         ny = nx if ny is None else ny

@@ -264,6 +264,19 @@ nosh_status nosh_mesh_set(nosh_ctx *ctx, int dim, int64_t nv, const double *coor
   API_END(ctx)
 }
 
+nosh_status nosh_mesh_set_local(nosh_ctx *ctx, int dim, int64_t n_global, int64_t nv_local, const int64_t *vertex_gids,
+                                const double *coords, int64_t nc_local, const int32_t *cells) {
+  API_BEGIN(ctx)
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  ctx->has_mesh = false;
+  const double t0 = wall_s();
+  mesh_from_host_local(ctx, dim, n_global, nv_local, vertex_gids, coords, nc_local, cells);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->stats["setup.mesh_s"] = wall_s() - t0;
+  after_mesh(ctx);
+  API_END(ctx)
+}
+
 nosh_status nosh_mesh_tetgrid(nosh_ctx *ctx, int nx, int ny, int nz, const double lo[3], const double hi[3],
                               double jitter, uint64_t seed) {
   API_BEGIN(ctx)

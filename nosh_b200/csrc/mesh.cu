@@ -272,6 +272,50 @@ __global__ void k_gather_coords(const double *gcoords, const int32_t *gid, int64
   coords[3 * i + 1] = gcoords[3 * g + 1];
   coords[3 * i + 2] = gcoords[3 * g + 2];
 }
+// partitioned ingestion (mesh_from_host_local): the caller's vertex list is sorted by global id once; the
+// coordinates of my owned + ghost vertices are found by binary search
+struct LocalCoords {
+  const uint32_t *sorted_gid;  // nv_local, ascending
+  const uint32_t *sorted_idx;  // position in the caller's arrays
+  int64_t nv_local;
+  const double *coords;        // nv_local x 3, caller's order
+};
+__global__ void k_gather_coords_local(LocalCoords lc, const int32_t *gid, int64_t Nl, double *coords, int *err) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= Nl) return;
+  const uint32_t g = (uint32_t)gid[i];
+  int64_t lo = 0, hi = lc.nv_local;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (lc.sorted_gid[mid] < g) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= lc.nv_local || lc.sorted_gid[lo] != g) {
+    atomicMax(err, 3);
+    coords[3 * i] = coords[3 * i + 1] = coords[3 * i + 2] = 0.0;
+    return;
+  }
+  const int64_t j = lc.sorted_idx[lo];
+  coords[3 * i] = lc.coords[3 * j];
+  coords[3 * i + 1] = lc.coords[3 * j + 1];
+  coords[3 * i + 2] = lc.coords[3 * j + 2];
+}
+__global__ void k_gids_to_keys(const int64_t *gids, int64_t n, int64_t n_global, uint32_t *keys, uint32_t *vals,
+                               int *err) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t g = gids[i];
+  if (g < 0 || g >= n_global) atomicMax(err, 1);
+  keys[i] = (uint32_t)g;
+  vals[i] = (uint32_t)i;
+}
+__global__ void k_check_unique_sorted(const uint32_t *keys, int64_t n, int *err) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i + 1 < n && keys[i] == keys[i + 1]) atomicMax(err, 2);
+}
+__global__ void k_cells_to_global(const int32_t *cells_local, const int64_t *gids, int64_t n, int32_t *cellsG) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) cellsG[i] = (int32_t)gids[cells_local[i]];
+}
 
 // ---- edges --------------------------------------------------------------------------------
 // one key per (cell, local edge): (gmin << 32 | gmax) if an endpoint is owned, else sentinel
@@ -621,7 +665,7 @@ __global__ void k_remap(int32_t *slots, int64_t n, const int32_t *csr_pos) {
 
 template <int NVC, int NE>
 void build_from_cells(Ctx *ctx, DBuf<int32_t> &cellsG, int64_t ncand, const double *gcoords_dev,
-                      const GridDesc *grid) {
+                      const GridDesc *grid, const LocalCoords *lc = nullptr) {
   Temp tmp;
   const int64_t vb = ctx->vb, ve = ctx->ve, No = ve - vb;
   ctx->No = No;
@@ -673,7 +717,13 @@ void build_from_cells(Ctx *ctx, DBuf<int32_t> &cellsG, int64_t ncand, const doub
   ctx->coords.alloc(Nl * 3);
   if (grid)
     LAUNCH(ctx, k_tetgrid_coords, Nl, ctx->gid.p, Nl, *grid, ctx->coords.p);
-  else
+  else if (lc) {
+    DBuf<int> cerr;
+    cerr.alloc(1);
+    CUDA_CHECK(cudaMemsetAsync(cerr.p, 0, sizeof(int), ctx->stream));
+    LAUNCH(ctx, k_gather_coords_local, Nl, *lc, ctx->gid.p, Nl, ctx->coords.p, cerr.p);
+    if (fetch(ctx, cerr.p)) NOSH_THROW(NOSH_EMESH, "internal: a vertex of a local cell has no coordinates");
+  } else
     LAUNCH(ctx, k_gather_coords, Nl, gcoords_dev, ctx->gid.p, Nl, ctx->coords.p);
   // ---- 4. unique edges, cell->edge, edge->cell incidence -------------------------------
   const int64_t nke = nc * NE;
@@ -929,6 +979,67 @@ void mesh_from_host(Ctx *ctx, int dim, int64_t nv, const double *coords, int64_t
     build_from_cells<4, 6>(ctx, cellsG, ncells, gc.p, nullptr);
   else
     build_from_cells<3, 3>(ctx, cellsG, ncells, gc.p, nullptr);
+}
+
+// Partitioned ingestion (the READ_PART analogue of src/mesh_reader.cpp:32-35): every rank passes only ITS part --
+// the cells that touch a vertex of its owned range [nosh_partition_range) (more cells are allowed and dropped),
+// the vertices those cells use with their global ids and coordinates, cells indexing into that local list.
+void mesh_from_host_local(Ctx *ctx, int dim, int64_t n_global, int64_t nv_local, const int64_t *gids,
+                          const double *coords, int64_t ncells, const int32_t *cells) {
+  if (dim != 2 && dim != 3) NOSH_THROW(NOSH_EINVAL, "dim must be 2 or 3");
+  if (n_global <= 0 || nv_local < 0 || ncells < 0) NOSH_THROW(NOSH_EINVAL, "negative size");
+  if ((nv_local > 0 && (!gids || !coords)) || (ncells > 0 && !cells)) NOSH_THROW(NOSH_EINVAL, "NULL array");
+  ctx->dim = dim;
+  setup_partition(ctx, n_global);
+  const int nvc = dim + 1;
+  Temp tmp;
+  DBuf<int64_t> dg;
+  DBuf<uint32_t> keys, vals;
+  DBuf<double> dc;
+  DBuf<int> derr;
+  dg.alloc(nv_local);
+  keys.alloc(nv_local);
+  vals.alloc(nv_local);
+  dc.alloc(nv_local * 3);
+  derr.alloc(1);
+  CUDA_CHECK(cudaMemsetAsync(derr.p, 0, sizeof(int), ctx->stream));
+  if (nv_local) {
+    CUDA_CHECK(cudaMemcpyAsync(dg.p, gids, sizeof(int64_t) * nv_local, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(dc.p, coords, sizeof(double) * nv_local * 3, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_gids_to_keys, nv_local, dg.p, nv_local, n_global, keys.p, vals.p, derr.p);
+    if (fetch(ctx, derr.p)) NOSH_THROW(NOSH_EMESH, "Illegal mesh: a local vertex has a global id outside [0, %lld)", (long long)n_global);
+    sort_pairs_u32(ctx, tmp, keys, vals, nv_local);
+    LAUNCH(ctx, k_check_unique_sorted, nv_local, keys.p, nv_local, derr.p);
+    if (fetch(ctx, derr.p)) NOSH_THROW(NOSH_EMESH, "Illegal mesh: a global vertex id appears twice in the local vertex list");
+  }
+  DBuf<int32_t> cl, cellsG;
+  cl.alloc(ncells * nvc);
+  cellsG.alloc(ncells * nvc);
+  if (ncells) {
+    CUDA_CHECK(cudaMemcpyAsync(cl.p, cells, sizeof(int32_t) * ncells * nvc, cudaMemcpyHostToDevice, ctx->stream));
+    DBuf<unsigned long long> vfirst;
+    vfirst.alloc(1);
+    CUDA_CHECK(cudaMemsetAsync(vfirst.p, 0xFF, sizeof(unsigned long long), ctx->stream));
+    if (dim == 3)
+      LAUNCH(ctx, (k_validate_cells<4>), ncells, cl.p, ncells, nv_local, derr.p, vfirst.p);
+    else
+      LAUNCH(ctx, (k_validate_cells<3>), ncells, cl.p, ncells, nv_local, derr.p, vfirst.p);
+    const int e = fetch(ctx, derr.p);
+    if (e) {
+      const unsigned long long c = fetch(ctx, vfirst.p);
+      if (e == 2)
+        NOSH_THROW(NOSH_EMESH, "Illegal mesh: cell %llu references a vertex outside the local list [0, %lld)", c,
+                   (long long)nv_local);
+      NOSH_THROW(NOSH_EMESH, "Illegal mesh: cell %llu references the same vertex twice", c);
+    }
+    LAUNCH(ctx, k_cells_to_global, ncells * nvc, cl.p, dg.p, ncells * nvc, cellsG.p);
+  }
+  cl.release();
+  LocalCoords lc{keys.p, vals.p, nv_local, dc.p};
+  if (dim == 3)
+    build_from_cells<4, 6>(ctx, cellsG, ncells, nullptr, nullptr, &lc);
+  else
+    build_from_cells<3, 3>(ctx, cellsG, ncells, nullptr, nullptr, &lc);
 }
 
 void mesh_tetgrid(Ctx *ctx, int nx, int ny, int nz, const double lo[3], const double hi[3],

@@ -13,7 +13,7 @@ Environment:
                       host: torch gloo process group + nosh_ctx_comm_init_host (set-up through the caller's
                       communicator, no NCCL anywhere; ranks may share a GPU)
   NOSH_TEST_N         grid size (default 20)
-  NOSH_TEST_SECTIONS  comma list of core,amg,gmres,cont,tiny (default: all)
+  NOSH_TEST_SECTIONS  comma list of core,local,amg,gmres,cont,tiny (default: all)
 """
 import os
 import sys
@@ -41,7 +41,7 @@ def main():
     world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ["LOCAL_RANK"])
     mode = os.environ.get("NOSH_TEST_COMM", "nccl")
-    sections = set(os.environ.get("NOSH_TEST_SECTIONS", "core,amg,gmres,cont,tiny").split(","))
+    sections = set(os.environ.get("NOSH_TEST_SECTIONS", "core,local,amg,gmres,cont,tiny").split(","))
     dev = local % torch.cuda.device_count()
     torch.cuda.set_device(dev)
     if mode == "host":
@@ -189,6 +189,40 @@ def main():
         assert np.array_equal(psis[sl], psi)
         summary["newton"] = [int(v) for v in lin]
         log("Newton %s == oracle, bits == one GPU" % list(lin))
+
+    if "local" in sections:
+        # ---- partitioned ingestion (MOAB's READ_PART, src/mesh_reader.cpp:32-35): every rank passes only the
+        # cells touching its owned vertex range + their vertices; identical to uploading the global mesh
+        cg = new_ctx()
+        mg = cg.mesh_set(coords, cells)
+        cl = new_ctx()
+        b0, e0, _ = nosh_b200.partition_range(N, world, rank, group)
+        gids_l, coords_l, cells_l = nosh_b200.Context.local_part(coords, cells, b0, e0)
+        perm = np.random.default_rng(rank).permutation(gids_l.size)       # any order of the local vertex list
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(perm.size)
+        ml = cl.mesh_set_local(N, gids_l[perm], coords_l[perm], inv[cells_l].astype(np.int32))
+        assert gids_l.size < N                                         # really only a part
+        for f in ("n_global", "owned_begin", "n_owned", "n_ghost", "n_cells", "n_edges", "n_blocks", "n_stored"):
+            assert getattr(mg, f) == getattr(ml, f) == getattr(mi, f), f
+        assert np.array_equal(cg.local_gids(), cl.local_gids()) and np.array_equal(cg.coords(), cl.coords())
+        assert np.array_equal(cg.control_volumes(), cl.control_volumes())
+        outs = []
+        for c in (cg, cl):
+            fields(c)
+            c.keo_fill(par)
+            outs.append((c.block_csr(), c.compute_f(par, x[sl].copy())))
+        for a_, b_ in zip(outs[0][0], outs[1][0]):
+            assert np.array_equal(a_, b_)
+        assert np.array_equal(outs[0][1], outs[1][1])
+        with np.testing.assert_raises(RuntimeError):                     # a global id outside [0, N)
+            bad = new_ctx()
+            g2 = gids_l.copy()
+            g2[0] = N + 5
+            bad.mesh_set_local(N, g2, coords_l, cells_l)
+        cg.close()
+        cl.close()
+        log("partitioned ingestion (mesh_set_local) == global upload, bit for bit")
 
     if "amg" in sections:
         # ---- preconditioned MINRES: every rank applies the AMG V-cycle of ITS diagonal block of the

@@ -567,3 +567,36 @@ def test_sell_sigma_on_a_mesh_with_varying_valence(nb, orc):
     ctx.mesh_tetgrid(40)
     assert ctx.stat("sell.sigma") == 0.0 and ctx.stat("sell.stored_over_blocks") < 1.05
     ctx.close()
+
+
+def test_mesh_set_local_and_connectivity_validation(nb, orc):
+    """nosh_mesh_set_local with the whole mesh as one part (vertex list in random order) is nosh_mesh_set; bad
+    connectivity is rejected with NOSH_EMESH instead of indexing out of bounds on the device."""
+    coords, cells = orc.meshgen.tetgrid(8)
+    N = coords.shape[0]
+    a = nb.Context()
+    ma = a.mesh_set(coords, cells)
+    perm = np.random.default_rng(3).permutation(N)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(N)
+    b = nb.Context()
+    mb = b.mesh_set_local(N, perm, coords[perm], inv[cells].astype(np.int32))
+    for f in ("n_global", "n_owned", "n_cells", "n_edges", "n_blocks"):
+        assert getattr(ma, f) == getattr(mb, f)
+    assert np.array_equal(a.control_volumes(), b.control_volumes())
+    ea, eb = a.edges(), b.edges()
+    for u, v in zip(ea, eb):
+        assert np.array_equal(u, v)
+    for bad_cells, what in ((np.where(cells == cells[5, 2], N + 3, cells), "outside"),
+                            (np.where(cells == cells[5, 2], -1, cells), "outside"),
+                            (np.vstack([cells, cells[:1, [0, 0, 1, 2]]]), "twice")):
+        c = nb.Context()
+        with pytest.raises(RuntimeError, match=what):
+            c.mesh_set(coords, bad_cells.astype(np.int32))
+        c.close()
+    c = nb.Context()
+    with pytest.raises(RuntimeError, match="twice"):
+        c.mesh_set_local(N, np.zeros(N, np.int64), coords, cells)
+    c.close()
+    a.close()
+    b.close()

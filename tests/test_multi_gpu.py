@@ -44,13 +44,13 @@ def test_partitioned_parity_and_bit_identity(world):
 def test_host_communicator_one_rank_per_gpu(world):
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
-    _run(world, {"NOSH_TEST_COMM": "host", "NOSH_TEST_SECTIONS": "core,cont"}, 29631 + world)
+    _run(world, {"NOSH_TEST_COMM": "host", "NOSH_TEST_SECTIONS": "core,local,cont"}, 29631 + world)
 
 
 @pytest.mark.parametrize("world", [2, 3])
 def test_shared_gpu_ranks_host_communicator(world):
     """Runs on ONE GPU: `world` processes share it (and any further GPUs round-robin)."""
     out = _run(world, {"NOSH_TEST_COMM": "host", "NOSH_TEST_N": "12",
-                       "NOSH_TEST_SECTIONS": os.environ.get("NOSH_SHARED_SECTIONS", "core,cont,tiny")},
+                       "NOSH_TEST_SECTIONS": os.environ.get("NOSH_SHARED_SECTIONS", "core,local,cont,tiny")},
                29651 + world)
     assert "p2p=1" in out
