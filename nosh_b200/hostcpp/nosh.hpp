@@ -20,6 +20,7 @@
 //  * the Thyra InArgs/OutArgs protocol is reduced to plain structs with the same members
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -55,25 +56,36 @@ struct param_list {
 };
 
 // ---------------------------------------------------------------------------------------
+// The communicator the reference's mesh carries (Teuchos::Comm<int>, src/mesh_reader.cpp:53-57; the tests run
+// under mpiexec -n 2 / -n 7, test/CMakeLists.txt:18-23): rank, size and an all-gather of host records -- with MPI,
+//   [](void *u, const void *s, void *r, int64_t n) { return MPI_Allgather(s, n, MPI_BYTE, r, n, MPI_BYTE, *(MPI_Comm *)u); }
+// One rank (the default) needs no callback.  The device data path never goes through it (include/nosh_b200.h).
+struct comm {
+  int rank = 0, size = 1;
+  nosh_allgather_fn allgather = nullptr;
+  void *user = nullptr;
+};
+
 class mesh {
 public:
-  // general mesh from arrays (coords: n x 3, cells: nc x (dim+1), 0-based)
-  mesh(int dim, const std::vector<double> &coords, const std::vector<int> &cells, int device = 0) {
-    create(device);
-    check(ctx_, nosh_mesh_set(ctx_, dim, (int64_t)coords.size() / 3, coords.data(),
-                              (int64_t)cells.size() / (dim + 1), cells.data()));
+  // general mesh from arrays (coords: n x 3, cells: nc x (dim+1), 0-based, GLOBAL numbering on every rank).
+  // Several ranks: every rank keeps and uploads only its part (nosh_mesh_set_local, the READ_PART analogue).
+  mesh(int dim, const std::vector<double> &coords, const std::vector<int> &cells, int device = 0,
+       const comm &c = comm()) {
+    create(device, c);
+    set_from_global(dim, coords, cells);
     finish();
   }
   // synthetic structured tetrahedral grid
-  mesh(int nx, int ny, int nz, double jitter = 0.2, uint64_t seed = 1234, int device = 0) {
-    create(device);
+  mesh(int nx, int ny, int nz, double jitter = 0.2, uint64_t seed = 1234, int device = 0, const comm &c = comm()) {
+    create(device, c);
     const double lo[3] = {-5, -5, -5}, hi[3] = {5, 5, 5};
     check(ctx_, nosh_mesh_tetgrid(ctx_, nx, ny, nz, lo, hi, jitter, seed));
     finish();
   }
   // nosh::read(file) (src/mesh_reader.cpp:19-162): mesh + vertex tags from a legacy VTK file (MOAB's
   // .h5m / Exodus need libraries that are not available: std::runtime_error with the conversion hint)
-  explicit mesh(const std::string &file_name, int device = 0) {
+  explicit mesh(const std::string &file_name, int device = 0, const comm &c = comm()) {
     nosh_meshfile *f = nullptr;
     const nosh_status st = nosh_meshfile_read(file_name.c_str(), &f);
     if (st != NOSH_OK) throw std::runtime_error(std::string("nosh::read: ") + nosh_meshfile_last_error());
@@ -93,32 +105,53 @@ public:
       tags_[name] = {ncomp, std::move(v)};
     }
     nosh_meshfile_free(f);
-    create(device);
-    check(ctx_, nosh_mesh_set(ctx_, dim, nv, file_coords_.data(), nc, file_cells_.data()));
+    create(device, c);
+    set_from_global(dim, file_coords_, file_cells_);
     finish();
   }
-  // vertex tags of the file (src/mesh.cpp:249-446).  One rank: owned == all vertices.
+  // vertex tags of the file (src/mesh.cpp:249-446) on the OWNED vertices of this rank (the file holds them in
+  // global numbering; every rank reads the whole file -- legacy VTK has no partition information)
   std::shared_ptr<Tpetra::Vector<double, int, int>> get_vector(const std::string &tag) const {
     const auto &t = tag_at(tag, 1);
     auto v = std::make_shared<Tpetra::Vector<double, int, int>>(map_);
-    std::copy(t.begin(), t.end(), v->getDataNonConst());
+    const size_t b = (size_t)info_.owned_begin, n = (size_t)info_.n_owned;
+    std::copy(t.begin() + b, t.begin() + b + n, v->getDataNonConst());
     return v;
   }
   std::shared_ptr<Tpetra::Vector<double, int, int>> get_complex_vector(const std::string &tag) const {
     const auto &t = tag_at(tag, 2);  // (re, im) per vertex = the interleaved layout of complex_map
     auto v = std::make_shared<Tpetra::Vector<double, int, int>>(complex_map_);
-    std::copy(t.begin(), t.end(), v->getDataNonConst());
+    const size_t b = 2 * (size_t)info_.owned_begin, n = 2 * (size_t)info_.n_owned;
+    std::copy(t.begin() + b, t.begin() + b + n, v->getDataNonConst());
     return v;
   }
   std::shared_ptr<Tpetra::MultiVector<double, int, int>> get_multi_vector(const std::string &tag) const {
     const auto &t = tag_at(tag, 3);  // file: (x,y,z) per vertex; MultiVector: one column per component
     auto v = std::make_shared<Tpetra::MultiVector<double, int, int>>(map_, 3);
-    const size_t n = t.size() / 3;
+    const size_t b = (size_t)info_.owned_begin, n = (size_t)info_.n_owned;
     for (size_t k = 0; k < n; k++)
-      for (int c = 0; c < 3; c++) v->getDataNonConst(c)[k] = t[3 * k + c];
+      for (int c = 0; c < 3; c++) v->getDataNonConst(c)[k] = t[3 * (b + k) + c];
     return v;
   }
   const std::vector<double> &tag_data(const std::string &tag) const { return tags_.at(tag).second; }
+  // a vertex tag in LOCAL numbering (owned vertices first, then ghosts): what the field set-up calls of the C ABI take
+  std::vector<double> tag_local(const std::string &tag, int ncomp) const {
+    const auto &t = tag_at(tag, ncomp);
+    const auto &g = local_gids();
+    std::vector<double> out(g.size() * (size_t)ncomp);
+    for (size_t k = 0; k < g.size(); k++)
+      for (int c = 0; c < ncomp; c++) out[k * ncomp + c] = t[(size_t)g[k] * ncomp + c];
+    return out;
+  }
+  // global (0-based) ids of the local vertices: owned first, then ghosts
+  const std::vector<int64_t> &local_gids() const {
+    if (gids_.empty() && info_.n_owned + info_.n_ghost > 0) {
+      gids_.resize((size_t)(info_.n_owned + info_.n_ghost));
+      check(ctx_, nosh_mesh_local_gids(ctx_, gids_.data()));
+    }
+    return gids_;
+  }
+  const comm &get_comm() const { return comm_; }
   // mesh::write (src/mesh.cpp:249-263), the outNNNN dumps of continuation_data_saver.hpp:24-50: the mesh of
   // the file with `psi` replaced by the given state
   void write(const std::string &file_name, const Tpetra::Vector<double, int, int> *psi = nullptr) const {
@@ -164,7 +197,48 @@ public:
   mutable const void *bound_thickness = nullptr, *bound_mvp = nullptr, *bound_potential = nullptr;
 
 private:
-  void create(int device) { if (nosh_ctx_create(device, nullptr, &ctx_) != NOSH_OK) throw std::runtime_error("nosh_ctx_create failed: no CUDA device (there is no CPU fallback)"); }
+  void create(int device, const comm &c) {
+    comm_ = c;
+    if (nosh_ctx_create(device, nullptr, &ctx_) != NOSH_OK)
+      throw std::runtime_error("nosh_ctx_create failed: no CUDA device (there is no CPU fallback)");
+    if (c.size > 1) check(ctx_, nosh_ctx_comm_init_host(ctx_, c.rank, c.size, c.allgather, c.user));
+  }
+  // one rank: upload everything; several ranks: keep the cells touching my vertex range and their vertices
+  template <class Int>
+  void set_from_global(int dim, const std::vector<double> &coords, const std::vector<Int> &cells) {
+    const int nvc = dim + 1;
+    const int64_t nv = (int64_t)coords.size() / 3, nc = (int64_t)cells.size() / nvc;
+    if (comm_.size == 1) {
+      std::vector<int32_t> c32(cells.begin(), cells.end());
+      check(ctx_, nosh_mesh_set(ctx_, dim, nv, coords.data(), nc, c32.data()));
+      return;
+    }
+    int64_t b = 0, e = 0, g = 0, group = 65536;
+    if (const char *env = std::getenv("NOSH_B200_GROUP")) group = std::atoll(env);
+    if (nosh_partition_range(nv, comm_.size, comm_.rank, group, &b, &e, &g) != NOSH_OK)
+      throw std::logic_error("nosh_partition_range failed");
+    std::vector<int64_t> lid((size_t)nv, -1), gids;
+    std::vector<int32_t> lc;
+    for (int64_t c = 0; c < nc; c++) {
+      bool mine = false;
+      for (int k = 0; k < nvc; k++) mine = mine || ((int64_t)cells[c * nvc + k] >= b && (int64_t)cells[c * nvc + k] < e);
+      if (!mine) continue;
+      for (int k = 0; k < nvc; k++) {
+        const int64_t v = cells[c * nvc + k];
+        if (v < 0 || v >= nv) throw std::runtime_error("Illegal mesh: vertex index outside [0, n)");
+        if (lid[v] < 0) {
+          lid[v] = (int64_t)gids.size();
+          gids.push_back(v);
+        }
+        lc.push_back((int32_t)lid[v]);
+      }
+    }
+    std::vector<double> lx(gids.size() * 3);
+    for (size_t k = 0; k < gids.size(); k++)
+      for (int d = 0; d < 3; d++) lx[3 * k + d] = coords[3 * (size_t)gids[k] + d];
+    check(ctx_, nosh_mesh_set_local(ctx_, dim, nv, (int64_t)gids.size(), gids.data(), lx.data(), (int64_t)lc.size() / nvc,
+                                    lc.data()));
+  }
   void finish() {
     check(ctx_, nosh_mesh_info(ctx_, &info_));
     map_ = std::make_shared<Tpetra::Map<int, int>>(info_.n_owned, info_.n_global, 1 + (int)info_.owned_begin);
@@ -182,13 +256,17 @@ private:
   std::vector<int32_t> file_cells_;
   std::map<std::string, std::pair<int, std::vector<double>>> tags_;
   nosh_ctx *ctx_ = nullptr;
+  comm comm_;
+  mutable std::vector<int64_t> gids_;
   nosh_mesh_info_t info_;
   std::shared_ptr<const Tpetra::Map<int, int>> map_, complex_map_;
   mutable std::shared_ptr<const Tpetra::Vector<double, int, int>> cv_;
 };
 
 // src/mesh_reader.hpp: std::shared_ptr<nosh::mesh> read(const std::string & file_name)
-inline std::shared_ptr<nosh::mesh> read(const std::string &file_name) { return std::make_shared<nosh::mesh>(file_name); }
+inline std::shared_ptr<nosh::mesh> read(const std::string &file_name, const comm &c = comm()) {
+  return std::make_shared<nosh::mesh>(file_name, 0, c);
+}
 
 // ---------------------------------------------------------------------------------------
 namespace scalar_field {
@@ -219,10 +297,13 @@ private:
   std::string name_;
   double init_;
 };
-// src/scalar_field_explicit_values.hpp, values given directly (local numbering)
+// src/scalar_field_explicit_values.hpp: by tag name like the reference, or values given directly (local numbering)
 class explicit_values : public base {
 public:
   explicit_values(const nosh::mesh &, std::vector<double> values) : v_(std::move(values)) {}
+  // the reference's constructor (src/scalar_field_explicit_values.hpp:20-23): the values are the vertex tag
+  // `field_name` of the mesh file
+  explicit_values(const nosh::mesh &m, const std::string &field_name) : v_(m.tag_local(field_name, 1)) {}
   const std::map<std::string, double> get_scalar_parameters() const override { return {{"beta", 1.0}}; }
   void bind_as_thickness(const mesh &m) const override { check(m.ctx(), nosh_set_thickness(m.ctx(), v_.data(), 0.0)); }
   void bind_as_potential(const mesh &m) const override { check(m.ctx(), nosh_set_potential_values(m.ctx(), v_.data())); }
@@ -240,11 +321,15 @@ public:
   virtual const std::map<std::string, double> get_scalar_parameters() const = 0;
   virtual void bind(const mesh &m) const = 0;
 };
-// src/vector_field_explicit_values.hpp: explicit_values(mesh, field_name, mu); the nodal
-// values (mesh tag "A" in the reference) are passed directly, n x 3
+// src/vector_field_explicit_values.hpp: explicit_values(mesh, field_name, mu) reads the vertex tag (mesh tag "A"
+// in the reference); the overload with a vector takes the nodal values directly, n_local x 3
 class explicit_values : public base {
 public:
   explicit_values(const nosh::mesh &, std::vector<double> A, double mu) : A_(std::move(A)), mu_(mu) {}
+  // the reference's constructor (src/vector_field_explicit_values.hpp:17-21): the nodal values are the vertex tag
+  // `field_name` of the mesh file
+  explicit_values(const nosh::mesh &m, const std::string &field_name, double mu)
+      : A_(m.tag_local(field_name, 3)), mu_(mu) {}
   void set_parameters(const std::map<std::string, double> &p) override { mu_ = p.at("mu"); }
   const std::map<std::string, double> get_scalar_parameters() const override { return {{"mu", mu_}}; }
   void bind(const mesh &m) const override { check(m.ctx(), nosh_set_mvp_explicit(m.ctx(), A_.data())); }

@@ -4,9 +4,15 @@
 // arithmetic operation below the class interface runs in the sm_100a kernels.
 // Catch is not available: REQUIRE/Approx are restated in a few lines (Approx = relative
 // 1.2e-5 like Catch's default, tightened where noted).
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 
 #include "nosh.hpp"
@@ -254,7 +260,27 @@ static void run_io(const Fixture &fx, double a_inf_x, double a_inf_y) {
   REQUIRE_THROWS_AS(nosh::read("/tmp/pacman.h5m"), std::runtime_error);
   // the file-read mesh drives the same operators: test/keo.cpp's quadratic form again
   auto thickness = std::make_shared<nosh::scalar_field::constant>(*mesh, 1.0);
-  auto mvp = std::make_shared<nosh::vector_field::explicit_values>(*mesh, mesh->tag_data("A"), 1.0e-2);
+  // the reference's constructors take the TAG NAME (src/vector_field_explicit_values.hpp:17-21,
+  // src/scalar_field_explicit_values.hpp:20-23)
+  auto mvp = std::make_shared<nosh::vector_field::explicit_values>(*mesh, "A", 1.0e-2);
+  auto vtag = std::make_shared<nosh::scalar_field::explicit_values>(*mesh, "V");
+  REQUIRE_THROWS_AS(nosh::vector_field::explicit_values(*mesh, "no such tag", 1.0), std::runtime_error);
+  {
+    // F(psi) with the potential taken from the file's "V" tag == the golden value (V = -1 everywhere)
+    auto psi0 = mesh->get_complex_vector("psi");
+    nosh::model_evaluator::nls model(mesh, mvp, vtag, 1.0, thickness, psi0, "mu");
+    auto in = model.createInArgs();
+    in.set_x(psi0);
+    auto names = model.get_p_names(0);
+    std::vector<double> p;
+    for (const auto &nm : *names) p.push_back(nm == "g" ? 1.0 : (nm == "mu" ? 0.01 : 1.0));
+    in.set_p(0, p);
+    auto out = model.createOutArgs();
+    auto f = std::make_shared<Tpetra::Vector<double, int, int>>(mesh->complex_map());
+    out.set_f(f);
+    model.evalModel(in, out);
+    REQUIRE_APPROX(f->norm1(), fx.f1, 1e-8);
+  }
   nosh::parameter_matrix::keo keo(mesh, thickness, mvp);
   keo.set_parameters({{"mu", 1.0e-2}}, {});
   Tpetra::Vector<double, int, int> one(mesh->complex_map()), Kone(mesh->complex_map());
@@ -272,7 +298,157 @@ static void run_io(const Fixture &fx, double a_inf_x, double a_inf_y) {
   REQUIRE_APPROX(1.0 + worst, 1.0, 1e-15);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The reference runs every test under mpiexec -n 2 and -n 7 (test/CMakeLists.txt:18-23).  Here: the process forks
+// into P ranks BEFORE any CUDA call; their communicator is an all-gather over a shared-memory region (what
+// MPI_Allgather would be), handed to nosh::mesh as nosh::comm.  The ranks share the GPU; everything below the
+// class interface -- partitioned mesh, peer-memory halo exchange, reductions -- runs in the sm_100a kernels.
+// ---------------------------------------------------------------------------------------------------------
+struct Shm {
+  std::atomic<int> count, sense;
+  int P;
+  size_t cap;
+  char *buf() { return reinterpret_cast<char *>(this + 1); }
+};
+struct RankComm {
+  Shm *shm;
+  int rank, local_sense = 0;
+  void barrier() {
+    local_sense ^= 1;
+    if (shm->count.fetch_add(1) == shm->P - 1) {
+      shm->count.store(0);
+      shm->sense.store(local_sense);
+    } else {
+      while (shm->sense.load() != local_sense) usleep(50);
+    }
+  }
+};
+static int shm_allgather(void *user, const void *send, void *recv, int64_t n) {
+  RankComm *c = static_cast<RankComm *>(user);
+  if ((size_t)n > c->shm->cap) return 1;
+  std::memcpy(c->shm->buf() + (size_t)c->rank * c->shm->cap, send, (size_t)n);
+  c->barrier();
+  for (int r = 0; r < c->shm->P; r++) std::memcpy((char *)recv + (size_t)r * n, c->shm->buf() + (size_t)r * c->shm->cap, (size_t)n);
+  c->barrier();
+  return 0;
+}
+static double allsum(RankComm &c, double v) {
+  std::vector<double> all(c.shm->P);
+  shm_allgather(&c, &v, all.data(), sizeof(double));
+  double s = 0.0;
+  for (double a : all) s += a;
+  return s;
+}
+
+static int rank_main(RankComm &rc, int P) {
+  setenv("NOSH_B200_GROUP", "512", 1);  // 8 x 8 x 20 = 1280 vertices -> 3 groups of 512: every rank owns rows
+  nosh::comm c;
+  c.rank = rc.rank;
+  c.size = P;
+  c.allgather = shm_allgather;
+  c.user = &rc;
+  const double mu = 0.3;
+  // the same problem on P ranks and, in the same process, on one rank
+  auto build = [&](const nosh::comm &cm) { return std::make_shared<nosh::mesh>(8, 8, 20, 0.2, 1234, 0, cm); };
+  auto mesh = build(c);
+  auto one = build(nosh::comm());
+  const size_t No = mesh->info().n_owned, b = mesh->info().owned_begin, N = one->info().n_owned;
+  REQUIRE_APPROX((double)mesh->map()->getGlobalNumElements(), (double)N, 0.0);
+  REQUIRE_APPROX(allsum(rc, (double)No), (double)N, 0.0);
+  REQUIRE_APPROX(allsum(rc, mesh->control_volumes()->norm1()), one->control_volumes()->norm1(), 1e-13);
+  auto run_model = [&](const std::shared_ptr<nosh::mesh> &m, size_t off, size_t n, std::vector<double> &F, std::vector<double> &Jx,
+                       int &its) {
+    auto mvp = std::make_shared<nosh::vector_field::constantCurl>(m, std::vector<double>{0.0, 0.0, 1.0});
+    auto thickness = std::make_shared<nosh::scalar_field::constant>(*m, 1.0);
+    auto sp = std::make_shared<nosh::scalar_field::constant>(*m, -1.0);
+    auto psi = std::make_shared<Tpetra::Vector<double, int, int>>(m->complex_map());
+    Tpetra::Vector<double, int, int> x(m->complex_map()), y(m->complex_map()), sol(m->complex_map());
+    for (size_t k = 0; k < n; k++) {  // values keyed on the GLOBAL vertex id
+      const double g = (double)(off + k);
+      (*psi)[2 * k] = std::cos(0.37 * g);
+      (*psi)[2 * k + 1] = 0.5 * std::sin(0.11 * g);
+      x[2 * k] = std::sin(0.05 * g) + 0.2;
+      x[2 * k + 1] = std::cos(0.23 * g);
+    }
+    nosh::model_evaluator::nls model(m, mvp, sp, 1.0, thickness, psi, "mu");
+    auto in = model.createInArgs();
+    in.set_x(psi);
+    in.set_p(0, {1.0, mu, 0.0});  // g, mu, theta (name sorted)
+    auto out = model.createOutArgs();
+    auto f = std::make_shared<Tpetra::Vector<double, int, int>>(m->complex_map());
+    auto jac = model.create_W_op();
+    out.set_f(f);
+    out.set_W_op(jac);
+    model.evalModel(in, out);
+    jac->apply(x, y);
+    auto solver = model.get_W_factory();
+    solver->solver_type = "MINRES";
+    solver->convergence_tolerance = 1e-10;
+    solver->maximum_iterations = 2000;
+    auto st = solver->solve(*jac, x, sol);
+    its = st.converged ? st.iterations : -1;
+    F.assign(f->getData(), f->getData() + 2 * n);
+    Jx.assign(y.getData(), y.getData() + 2 * n);
+  };
+  std::vector<double> Fp, Jp, F1, J1;
+  int itp = 0, it1 = 0;
+  run_model(mesh, b, No, Fp, Jp, itp);
+  run_model(one, 0, N, F1, J1, it1);
+  // partition independence: the owned slice equals the one-rank result bit for bit, same MINRES iteration count
+  g_checks += 3;
+  if (std::memcmp(Fp.data(), F1.data() + 2 * b, sizeof(double) * 2 * No) != 0) { std::printf("FAIL rank %d: F differs from the one-rank run\n", rc.rank); g_fail++; }
+  if (std::memcmp(Jp.data(), J1.data() + 2 * b, sizeof(double) * 2 * No) != 0) { std::printf("FAIL rank %d: J x differs from the one-rank run\n", rc.rank); g_fail++; }
+  if (itp != it1 || itp <= 0) { std::printf("FAIL rank %d: MINRES %d iterations vs %d on one rank\n", rc.rank, itp, it1); g_fail++; }
+  std::printf("rank %d of %d: %zu owned vertices, MINRES %d iterations == one rank, %d checks, %d failures\n", rc.rank, P, No, itp,
+              g_checks, g_fail);
+  return g_fail ? 1 : 0;
+}
+
+static int run_ranks(int P) {
+  const size_t cap = 1 << 22;
+  void *mem = mmap(nullptr, sizeof(Shm) + cap * P, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+  if (mem == MAP_FAILED) return 1;
+  Shm *shm = new (mem) Shm;
+  shm->count.store(0);
+  shm->sense.store(0);
+  shm->P = P;
+  shm->cap = cap;
+  std::vector<pid_t> kids;
+  for (int r = 0; r < P; r++) {
+    const pid_t pid = fork();  // before any CUDA call of this process
+    if (pid == 0) {
+      RankComm rc{shm, r};
+      int rcode = 2;
+      try {
+        rcode = rank_main(rc, P);
+      } catch (const std::exception &e) {
+        std::printf("FAIL rank %d: uncaught exception: %s\n", r, e.what());
+      }
+      std::fflush(stdout);
+      _exit(rcode);
+    }
+    kids.push_back(pid);
+  }
+  int bad = 0;
+  for (pid_t k : kids) {
+    int st = 0;
+    waitpid(k, &st, 0);
+    if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) bad++;
+  }
+  munmap(mem, sizeof(Shm) + cap * P);
+  return bad;
+}
+
 int main() {
+  std::fflush(stdout);
+  for (int P : {2, 3}) {
+    const int bad = run_ranks(P);
+    g_checks++;
+    if (bad) {
+      std::printf("FAIL %d of %d ranks failed\n", bad, P);
+      g_fail++;
+    }
+  }
   try {
     run(rectanglesmall());
     run(cubesmall());
