@@ -453,6 +453,51 @@ NOSH_API nosh_status nosh_meshfile_write(const char *path, int32_t dim, int64_t 
  * Morton curve through the bounding box. */
 NOSH_API nosh_status nosh_morton_order(int64_t n_vertices, const double *coords /* n x 3 */, int64_t *perm);
 
+/* ---- generic finite-volume matrix / operator ("next" row f4): nosh::fvm_matrix::fill (src/fvm_matrix.hpp:44-70)
+ * and nosh::fvm_operator::apply (src/fvm_operator.hpp:45-94) for REAL scalar problems on the mesh's vertex graph
+ * (src/mesh.cpp build_graph), enough for examples/poisson and examples/bratu.  The reference assembles from
+ * user-defined virtual cores generated by nfc; a device cannot call host virtuals per edge, so:
+ *   - edge_lhs == NULL: the built-in edge core of  integrate(-n_dot_grad(u), dS):
+ *       covolume/length * edge_coeff[e] * [[1,-1],[-1,1]]   (edge_coeff == NULL: 1)
+ *   - edge_lhs != NULL: arbitrary cores, evaluated once on the host: E x 4 doubles (lhs00, lhs01, lhs10, lhs11 of
+ *       matrix_core_edge::eval, vertex 0 = the edge's first vertex in nosh_mesh_get_edges) and edge_rhs E x 2
+ *   - vertex_lhs / vertex_rhs: n_owned doubles each, what matrix_core_vertex::eval returns (already times the
+ *       control volume) -- boundary cores are added into the same arrays by the caller
+ *   - dirichlet_mask (n_owned int32, non-zero = Dirichlet vertex) + dirichlet_values: rows replaced by unit rows,
+ *       right-hand side = value; columns are NOT eliminated (as the reference, :208-250)
+ * All arrays are HOST arrays (or NULL).  rhs (or NULL): n_owned doubles out, host or device.
+ * Vectors of the apply / solve calls: n_owned doubles, host or device.  One rank only. */
+typedef enum { NOSH_FVM_VERTEX_NONE = 0,
+               NOSH_FVM_VERTEX_EXP = 1,            /* y_k -= alpha c_k exp(x_k)          (bratu.py: F)        */
+               NOSH_FVM_VERTEX_EXP_LINEARIZED = 2  /* y_k -= alpha c_k exp(u0_k) x_k     (bratu.py: Jacobian) */
+} nosh_fvm_vertex_core;
+typedef enum { NOSH_FVM_DIRICHLET_NONE = 0,
+               NOSH_FVM_DIRICHLET_IDENTITY = 1, /* y_k = x_k            (lambda u, x: u(x))      */
+               NOSH_FVM_DIRICHLET_ZERO = 2,     /* y_k = 0              (lambda x, u: 0.0)       */
+               NOSH_FVM_DIRICHLET_VALUE = 3     /* y_k = x_k - value_k  (residual of u = g)      */
+} nosh_fvm_dirichlet_kind;
+/* the mesh's "boundary" subdomain (src/mesh.cpp:76-131): flags[k] = 1 for owned vertices on the skin */
+NOSH_API nosh_status nosh_mesh_boundary_vertices(nosh_ctx *ctx, int32_t *flags /* host, n_owned */);
+NOSH_API nosh_status nosh_fvm_matrix_fill(nosh_ctx *ctx, const double *edge_coeff, const double *edge_lhs,
+                                          const double *edge_rhs, const double *vertex_lhs, const double *vertex_rhs,
+                                          const int32_t *dirichlet_mask, const double *dirichlet_values, double *rhs);
+NOSH_API nosh_status nosh_fvm_matrix_apply(nosh_ctx *ctx, const double *x, double *y);
+/* entry-wise access for parity: CSR of the n_owned x n_owned real matrix (rowptr n_owned+1, cols/vals n_blocks) */
+NOSH_API nosh_status nosh_fvm_get_csr(nosh_ctx *ctx, int64_t *rowptr, int32_t *cols, double *vals);
+/* fvm_operator::apply: y = [A x] + vertex core, Dirichlet rows last.  with_matrix = 0 drops the matrix term
+ * (bratu.py: dFdp = -integrate(exp(u), dV) is NOSH_FVM_VERTEX_EXP with alpha = 1 and no matrix).  The matrix is the
+ * one of the last nosh_fvm_matrix_fill (fill it WITHOUT Dirichlet rows for an operator: they are applied here). */
+NOSH_API nosh_status nosh_fvm_operator_apply(nosh_ctx *ctx, int with_matrix, nosh_fvm_vertex_core vertex_core, double alpha,
+                                             const double *u0, const int32_t *dirichlet_mask,
+                                             nosh_fvm_dirichlet_kind dirichlet_kind, const double *dirichlet_values,
+                                             const double *x, double *y);
+/* Belos "Pseudo Block CG" on the filled matrix (examples/poisson/poisson.cpp:58-66), ||r|| / ||r0|| <= tol.
+ * x0 = the Dirichlet lift of the fill (g on the Dirichlet vertices, 0 elsewhere) instead of poisson.cpp:28's 0:
+ * the reference eliminates Dirichlet ROWS only, so its matrix is not symmetric; from the lift CG runs on the
+ * symmetric interior block (from 0 plain CG does not converge -- the reference leans on its MueLu preconditioner). */
+NOSH_API nosh_status nosh_fvm_cg(nosh_ctx *ctx, const double *b, double *x, double tol, int maxit,
+                                 nosh_krylov_result *res);
+
 /* ---- measurement helpers: device-resident scratch vectors so that benchmarks can
  * time kernels with inputs already in HBM.  slot in [0,8). Returns a device pointer to
  * 2*(n_owned+n_ghost) doubles owned by the ctx. */

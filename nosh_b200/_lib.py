@@ -20,6 +20,8 @@ OP_JACOBIAN, OP_KEO, OP_KEOREG = 0, 1, 2
 PREC_NONE, PREC_KEOREG_AMG = 0, 1
 SOLVER_MINRES, SOLVER_CG, SOLVER_GMRES = 0, 1, 2
 AMG_REUSE_NONE, AMG_REUSE_FULL = 0, 1
+FVM_VERTEX_NONE, FVM_VERTEX_EXP, FVM_VERTEX_EXP_LINEARIZED = 0, 1, 2
+FVM_DIRICHLET_NONE, FVM_DIRICHLET_IDENTITY, FVM_DIRICHLET_ZERO, FVM_DIRICHLET_VALUE = 0, 1, 2, 3
 AMG_MAX_LEVELS = 16
 
 
@@ -178,6 +180,12 @@ def lib():
         "nosh_meshfile_get_field": (C.c_int, [vp, C.c_char_p, C.POINTER(i32), vp]),
         "nosh_meshfile_write": (C.c_int, [C.c_char_p, i32, i64, vp, i64, vp, i32, cpp, vp, vp, i32]),
         "nosh_morton_order": (C.c_int, [i64, vp, vp]),
+        "nosh_mesh_boundary_vertices": (C.c_int, [vp, vp]),
+        "nosh_fvm_matrix_fill": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "nosh_fvm_matrix_apply": (C.c_int, [vp, vp, vp]),
+        "nosh_fvm_get_csr": (C.c_int, [vp, vp, vp, vp]),
+        "nosh_fvm_operator_apply": (C.c_int, [vp, C.c_int, C.c_int, dbl, vp, vp, C.c_int, vp, vp, vp]),
+        "nosh_fvm_cg": (C.c_int, [vp, vp, vp, dbl, C.c_int, C.POINTER(KrylovResult)]),
         "nosh_scratch_vector": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
         "nosh_ctx_set_tuning": (C.c_int, [vp, C.c_char_p, C.c_int]),
         "nosh_launch_count": (i64, [vp]),

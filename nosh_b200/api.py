@@ -559,6 +559,51 @@ class Context:
             for s in steps:
                 f.write("%d,%.15e,%.15e,%.15e\n" % (s.step, s.param, s.gibbs_energy, s.norm))
 
+    # ---- generic FVM matrix / operator (row f4) --------------------------------------------
+    def boundary_vertices(self):
+        f = np.empty(self.n_owned, np.int32)
+        self._ck(self.L.nosh_mesh_boundary_vertices(self.h, _ptr(f)))
+        return f
+
+    def fvm_matrix_fill(self, edge_coeff=None, edge_lhs=None, edge_rhs=None, vertex_lhs=None, vertex_rhs=None,
+                        dirichlet_mask=None, dirichlet_values=None):
+        """fvm_matrix::fill; returns the right-hand side."""
+        f64 = lambda a: None if a is None else np.ascontiguousarray(a, np.float64)  # noqa: E731
+        ec, el, er, vl, vr, dv = map(f64, (edge_coeff, edge_lhs, edge_rhs, vertex_lhs, vertex_rhs, dirichlet_values))
+        dm = None if dirichlet_mask is None else np.ascontiguousarray(dirichlet_mask, np.int32)
+        rhs = np.empty(self.n_owned)
+        self._ck(self.L.nosh_fvm_matrix_fill(self.h, _ptr(ec), _ptr(el), _ptr(er), _ptr(vl), _ptr(vr), _ptr(dm), _ptr(dv),
+                                             _ptr(rhs)))
+        return rhs
+
+    def fvm_matrix_apply(self, x, y=None):
+        y = self._out_like(x) if y is None else y
+        self._ck(self.L.nosh_fvm_matrix_apply(self.h, _ptr(x), _ptr(y)))
+        return y
+
+    def fvm_csr(self):
+        mi = self._info
+        rp = np.empty(mi.n_owned + 1, np.int64)
+        cols = np.empty(mi.n_blocks, np.int32)
+        vals = np.empty(mi.n_blocks)
+        self._ck(self.L.nosh_fvm_get_csr(self.h, _ptr(rp), _ptr(cols), _ptr(vals)))
+        return rp, cols, vals
+
+    def fvm_operator_apply(self, x, y=None, with_matrix=True, vertex_core=0, alpha=0.0, u0=None, dirichlet_mask=None,
+                           dirichlet_kind=0, dirichlet_values=None):
+        y = self._out_like(x) if y is None else y
+        dm = None if dirichlet_mask is None else np.ascontiguousarray(dirichlet_mask, np.int32)
+        dv = None if dirichlet_values is None else np.ascontiguousarray(dirichlet_values, np.float64)
+        self._ck(self.L.nosh_fvm_operator_apply(self.h, int(bool(with_matrix)), int(vertex_core), float(alpha), _ptr(u0),
+                                                _ptr(dm), int(dirichlet_kind), _ptr(dv), _ptr(x), _ptr(y)))
+        return y
+
+    def fvm_cg(self, b, x=None, tol=1e-10, maxit=1000):
+        x = self._out_like(b) if x is None else x
+        res = KrylovResult()
+        self._ck(self.L.nosh_fvm_cg(self.h, _ptr(b), _ptr(x), float(tol), int(maxit), C.byref(res)))
+        return x, res
+
     # ---- measurement ------------------------------------------------------------------
     def scratch_vector(self, slot):
         p = C.c_void_p()

@@ -5,6 +5,7 @@
 #include "amg.h"
 #include "apply.cuh"
 #include "comm.h"
+#include "fvm.h"
 #include "keo.h"
 #include "krylov.h"
 #include "mesh.h"
@@ -99,6 +100,10 @@ __global__ void k_gather_vals(const int32_t *pos, const double2 *val, int64_t n,
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) out[i] = val[pos[i]];
 }
+__global__ void k_gather_real(const int32_t *pos, const double *val, int64_t n, double *out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = val[pos[i]];
+}
 __global__ void k_widen(const int32_t *in, int64_t n, int64_t *out) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[i];
@@ -112,6 +117,7 @@ void after_mesh(Ctx *ctx) {
   ctx->thick_set = false;
   ctx->mvp_kind = MVP_NONE;
   ctx->alpha_ok = ctx->keo_filled = ctx->dkeo_filled = ctx->jac_ok = ctx->keoreg_ok = false;
+  ctx->fvm_filled = false;
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 
@@ -880,6 +886,145 @@ nosh_status nosh_scratch_vector(nosh_ctx *ctx, int slot, double **dev_ptr) {
     CUDA_CHECK(cudaMemsetAsync(ctx->scratch[slot].p, 0, sizeof(double2) * n, ctx->stream));
   }
   *dev_ptr = (double *)ctx->scratch[slot].p;
+  API_END(ctx)
+}
+
+// ---- generic FVM cores (fvm.cu) ----------------------------------------------------------------------
+namespace {
+// real vectors of n_owned doubles: host pointers are staged through the ctx's (complex-sized) staging buffers
+const double *real_in(Ctx *ctx, const double *p, DBuf<double2> &buf) {
+  if (!p) NOSH_THROW(NOSH_EINVAL, "NULL vector");
+  if (is_device_ptr(p)) return p;
+  buf.ensure(ctx->Nl > 0 ? ctx->Nl : 1);
+  CUDA_CHECK(cudaMemcpyAsync(buf.p, p, sizeof(double) * ctx->No, cudaMemcpyHostToDevice, ctx->stream));
+  return (const double *)buf.p;
+}
+struct RealOut {
+  double *dev, *user;
+  bool host;
+};
+RealOut real_out(Ctx *ctx, double *p, DBuf<double2> &buf) {
+  if (!p) NOSH_THROW(NOSH_EINVAL, "NULL vector");
+  RealOut o{p, p, !is_device_ptr(p)};
+  if (o.host) {
+    buf.ensure(ctx->Nl > 0 ? ctx->Nl : 1);
+    o.dev = (double *)buf.p;
+  }
+  return o;
+}
+void real_finish(Ctx *ctx, const RealOut &o) {
+  if (o.host) {
+    CUDA_CHECK(cudaMemcpyAsync(o.user, o.dev, sizeof(double) * ctx->No, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+}
+}  // namespace
+
+nosh_status nosh_mesh_boundary_vertices(nosh_ctx *ctx, int32_t *flags) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  if (!flags) NOSH_THROW(NOSH_EINVAL, "NULL flags");
+  DBuf<int32_t> f;
+  f.alloc(ctx->No);
+  fvm_boundary_vertices(ctx, f.p);
+  d2h(ctx, flags, f.p, ctx->No);
+  API_END(ctx)
+}
+
+nosh_status nosh_fvm_matrix_fill(nosh_ctx *ctx, const double *edge_coeff, const double *edge_lhs, const double *edge_rhs,
+                                 const double *vertex_lhs, const double *vertex_rhs, const int32_t *dirichlet_mask,
+                                 const double *dirichlet_values, double *rhs) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  fvm_matrix_fill(ctx, edge_coeff, edge_lhs, edge_rhs, vertex_lhs, vertex_rhs, dirichlet_mask, dirichlet_values);
+  if (rhs && ctx->No > 0) {
+    CUDA_CHECK(cudaMemcpyAsync(rhs, ctx->fvm_rhs.p, sizeof(double) * ctx->No,
+                               is_device_ptr(rhs) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+  API_END(ctx)
+}
+
+nosh_status nosh_fvm_matrix_apply(nosh_ctx *ctx, const double *x, double *y) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  const double *xd = real_in(ctx, x, ctx->stage_x);
+  RealOut o = real_out(ctx, y, ctx->stage_y);
+  fvm_apply_dev(ctx, true, NOSH_FVM_VERTEX_NONE, 0.0, nullptr, nullptr, NOSH_FVM_DIRICHLET_NONE, nullptr, xd, o.dev);
+  real_finish(ctx, o);
+  API_END(ctx)
+}
+
+nosh_status nosh_fvm_get_csr(nosh_ctx *ctx, int64_t *rowptr, int32_t *cols, double *vals) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  if (vals && !ctx->fvm_filled) NOSH_THROW(NOSH_ESTATE, "FVM matrix not filled");
+  if (rowptr) {
+    DBuf<int64_t> w;
+    w.alloc(ctx->No + 1);
+    k_widen<<<(unsigned)cdiv(ctx->No + 1, 256), 256, 0, ctx->stream>>>(ctx->rowptr.p, ctx->No + 1, w.p);
+    ctx->launches++;
+    d2h(ctx, rowptr, w.p, ctx->No + 1);
+  }
+  if (cols) {  // local column ids -> global (one rank: identical)
+    d2h(ctx, cols, ctx->csr_col.p, ctx->nb);
+  }
+  if (vals) {
+    DBuf<double> g;
+    g.alloc(ctx->nb);
+    k_gather_real<<<(unsigned)cdiv(ctx->nb, 256), 256, 0, ctx->stream>>>(ctx->csr_pos.p, ctx->fvm_val.p, ctx->nb, g.p);
+    ctx->launches++;
+    d2h(ctx, vals, g.p, ctx->nb);
+  }
+  API_END(ctx)
+}
+
+nosh_status nosh_fvm_operator_apply(nosh_ctx *ctx, int with_matrix, nosh_fvm_vertex_core vertex_core, double alpha,
+                                    const double *u0, const int32_t *dirichlet_mask, nosh_fvm_dirichlet_kind dirichlet_kind,
+                                    const double *dirichlet_values, const double *x, double *y) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  if (vertex_core == NOSH_FVM_VERTEX_EXP_LINEARIZED && !u0) NOSH_THROW(NOSH_EINVAL, "the linearised core needs u0");
+  if (dirichlet_kind != NOSH_FVM_DIRICHLET_NONE && !dirichlet_mask) NOSH_THROW(NOSH_EINVAL, "Dirichlet kind without a mask");
+  if (dirichlet_kind == NOSH_FVM_DIRICHLET_VALUE && !dirichlet_values) NOSH_THROW(NOSH_EINVAL, "Dirichlet values missing");
+  const int64_t No = ctx->No > 0 ? ctx->No : 1;
+  DBuf<int32_t> dm;
+  DBuf<double> dv, du0;
+  const double *u0d = nullptr;
+  if (u0) {
+    if (is_device_ptr(u0)) {
+      u0d = u0;
+    } else {
+      du0.alloc(No);
+      CUDA_CHECK(cudaMemcpyAsync(du0.p, u0, sizeof(double) * ctx->No, cudaMemcpyHostToDevice, ctx->stream));
+      u0d = du0.p;
+    }
+  }
+  if (dirichlet_mask) {
+    dm.alloc(No);
+    CUDA_CHECK(cudaMemcpyAsync(dm.p, dirichlet_mask, sizeof(int32_t) * ctx->No, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (dirichlet_values) {
+    dv.alloc(No);
+    CUDA_CHECK(cudaMemcpyAsync(dv.p, dirichlet_values, sizeof(double) * ctx->No, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  const double *xd = real_in(ctx, x, ctx->stage_x);
+  RealOut o = real_out(ctx, y, ctx->stage_y);
+  fvm_apply_dev(ctx, with_matrix != 0, vertex_core, alpha, u0d, dirichlet_mask ? dm.p : nullptr, dirichlet_kind,
+                dirichlet_values ? dv.p : nullptr, xd, o.dev);
+  real_finish(ctx, o);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // dm / dv / du0 go out of scope
+  API_END(ctx)
+}
+
+nosh_status nosh_fvm_cg(nosh_ctx *ctx, const double *b, double *x, double tol, int maxit, nosh_krylov_result *res) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  if (maxit < 0) NOSH_THROW(NOSH_EINVAL, "maxit < 0");
+  const double *bd = real_in(ctx, b, ctx->stage_x);
+  RealOut o = real_out(ctx, x, ctx->stage_y);
+  fvm_cg_dev(ctx, bd, o.dev, tol, maxit, res);
+  real_finish(ctx, o);
   API_END(ctx)
 }
 

@@ -206,6 +206,10 @@ struct Ctx {
   DBuf<int32_t> diag_slot;          // No storage positions
   DBuf<double2> Kval, dKval;        // nstored
   DBuf<double> Kdiag;               // No: sum of alpha over incident edges
+  // ---- generic FVM matrix (fvm.cu): one double per storage slot of the same graph ----
+  DBuf<double> fvm_val, fvm_rhs, fvm_dval;
+  DBuf<int32_t> fvm_mask;
+  bool fvm_filled = false;
   // ---- fields ----
   DBuf<double> thick;               // Nl
   bool thick_set = false;

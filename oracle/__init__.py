@@ -8,3 +8,4 @@ from .oracle import OracleProblem, build_library, lib, num_threads, set_dot_part
 from . import meshgen  # noqa: F401
 from . import continuation  # noqa: F401
 from . import gmres  # noqa: F401
+from . import fvm  # noqa: F401

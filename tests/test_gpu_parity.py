@@ -600,3 +600,91 @@ def test_mesh_set_local_and_connectivity_validation(nb, orc):
     c.close()
     a.close()
     b.close()
+
+
+# ---- row f4: generic real-valued FVM matrix / operator (examples/poisson, examples/bratu) ------------------------
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("kind", ["kuhn", "five", "tri"])
+def test_fvm_matrix_fill_apply_and_poisson(nb, orc, layout, kind):
+    from oracle import fvm
+    if kind == "kuhn":
+        coords, cells = orc.meshgen.tetgrid(9, jitter=0.15)
+    elif kind == "five":
+        coords, cells = orc.meshgen.tetgrid5(9)
+    else:
+        coords, cells = orc.meshgen.trigrid(17, 9)
+    P = orc.OracleProblem(coords, cells, ("constcurl", (0.0, 0.0, 1.0), None))
+    ctx = nb.Context(layout=layout)
+    ctx.mesh_set(coords, cells)
+    bnd = ctx.boundary_vertices()
+    assert np.array_equal(bnd, fvm.boundary_vertices(cells, P.N))
+    rng = np.random.default_rng(2)
+    # (1) built-in Laplace core with a per-edge coefficient, vertex cores
+    e_gpu, _, _ = ctx.edges()
+    assert np.array_equal(e_gpu, P.edges)
+    coeff = 0.5 + rng.random(P.E)
+    vl, vr = P.cv * rng.random(P.N), P.cv * rng.standard_normal(P.N)
+    rhs = ctx.fvm_matrix_fill(edge_coeff=coeff, vertex_lhs=vl, vertex_rhs=vr)
+    A, orhs = fvm.fill(P, edge_coeff=coeff, vertex_lhs=vl, vertex_rhs=vr)
+    rp, cols, vals = ctx.fvm_csr()
+    assert np.array_equal(rp, A.indptr) and np.array_equal(cols, A.indices)
+    assert relerr(vals, A.data) <= RTOL and relerr(rhs, orhs) <= RTOL
+    x = rng.standard_normal(P.N)
+    assert relerr(ctx.fvm_matrix_apply(x), A @ x) <= RTOL
+    # (2) arbitrary host-evaluated cores: 2x2 block + rhs pair per edge
+    el, er = rng.standard_normal((P.E, 4)), rng.standard_normal((P.E, 2))
+    rhs = ctx.fvm_matrix_fill(edge_lhs=el, edge_rhs=er)
+    A2, orhs2 = fvm.fill(P, edge_lhs=el, edge_rhs=er)
+    _, _, vals2 = ctx.fvm_csr()
+    assert relerr(vals2, A2.data) <= RTOL and relerr(rhs, orhs2) <= RTOL
+    # (3) examples/poisson: -Laplace(u) = sin(y), u = 0 / 1 on the two halves of the boundary, CG
+    g1 = (bnd == 1) & (coords[:, 1] >= 0)
+    dv = np.where(g1, 1.0, 0.0)
+    f = P.cv * np.sin(coords[:, 1])
+    b = ctx.fvm_matrix_fill(vertex_rhs=f, dirichlet_mask=bnd, dirichlet_values=dv)
+    A3, ob = fvm.fill(P, vertex_rhs=f, dirichlet_mask=bnd, dirichlet_values=dv)
+    _, _, vals3 = ctx.fvm_csr()
+    assert relerr(vals3, A3.data) <= RTOL and relerr(b, ob) <= RTOL
+    xo, ito, _ = fvm.cg(A3, ob, 1e-10, 3000, x0=np.where(bnd == 1, dv, 0.0))   # nosh_fvm_cg starts from the lift
+    xg, res = ctx.fvm_cg(b, tol=1e-10, maxit=3000)
+    assert res.converged == 1 and abs(res.iterations - ito) <= 1, (res.iterations, ito)
+    assert relerr(xg, xo) <= 1e-7
+    import scipy.sparse.linalg as spla
+    assert relerr(xg, spla.spsolve(A3.tocsc(), ob)) <= 1e-7
+    with pytest.raises(RuntimeError):
+        nb.Context().fvm_matrix_apply(x)            # no mesh
+    ctx.close()
+
+
+def test_fvm_operator_bratu(nb, orc):
+    """examples/bratu/bratu.py: F, Jacobian and dF/dp as fvm_operator applies with the Dirichlet override."""
+    from oracle import fvm
+    coords, cells = orc.meshgen.tetgrid(9, jitter=0.15)
+    P = orc.OracleProblem(coords, cells, ("constcurl", (0.0, 0.0, 1.0), None))
+    ctx = nb.Context()
+    ctx.mesh_set(coords, cells)
+    bnd = ctx.boundary_vertices()
+    ctx.fvm_matrix_fill()                           # NLaplace, no Dirichlet rows: the operator applies them
+    A, _ = fvm.fill(P)
+    rng = np.random.default_rng(3)
+    u, du = 0.2 * rng.standard_normal(P.N), rng.standard_normal(P.N)
+    alpha = 0.3
+    F = ctx.fvm_operator_apply(u, vertex_core=nb.FVM_VERTEX_EXP, alpha=alpha, dirichlet_mask=bnd,
+                               dirichlet_kind=nb.FVM_DIRICHLET_IDENTITY)
+    assert relerr(F, fvm.operator_apply(A, P.cv, u, 1, alpha, None, bnd, 1)) <= RTOL
+    J = ctx.fvm_operator_apply(du, vertex_core=nb.FVM_VERTEX_EXP_LINEARIZED, alpha=alpha, u0=u, dirichlet_mask=bnd,
+                               dirichlet_kind=nb.FVM_DIRICHLET_IDENTITY)
+    assert relerr(J, fvm.operator_apply(A, P.cv, du, 2, alpha, u, bnd, 1)) <= RTOL
+    dFdp = ctx.fvm_operator_apply(u, with_matrix=False, vertex_core=nb.FVM_VERTEX_EXP, alpha=1.0, dirichlet_mask=bnd,
+                                  dirichlet_kind=nb.FVM_DIRICHLET_ZERO)
+    assert relerr(dFdp, fvm.operator_apply(None, P.cv, u, 1, 1.0, None, bnd, 2)) <= RTOL
+    # the Jacobian is the derivative of F (central differences through the device operator)
+    eps = 1e-6
+    Fp = ctx.fvm_operator_apply(u + eps * du, vertex_core=nb.FVM_VERTEX_EXP, alpha=alpha, dirichlet_mask=bnd,
+                                dirichlet_kind=nb.FVM_DIRICHLET_IDENTITY)
+    Fm = ctx.fvm_operator_apply(u - eps * du, vertex_core=nb.FVM_VERTEX_EXP, alpha=alpha, dirichlet_mask=bnd,
+                                dirichlet_kind=nb.FVM_DIRICHLET_IDENTITY)
+    assert relerr((Fp - Fm) / (2 * eps), J) <= 1e-7
+    with pytest.raises(ValueError):
+        ctx.fvm_operator_apply(u, vertex_core=nb.FVM_VERTEX_EXP_LINEARIZED, alpha=1.0)   # u0 missing
+    ctx.close()
