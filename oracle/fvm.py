@@ -59,12 +59,14 @@ def fill(P, edge_coeff=None, edge_lhs=None, edge_rhs=None, vertex_lhs=None, vert
     if vertex_rhs is not None:
         rhs = rhs + np.asarray(vertex_rhs, np.float64)
     A = A.tocsr()
-    if dirichlet_mask is not None:
-        m = np.asarray(dirichlet_mask) != 0
-        keep = sp.diags((~m).astype(np.float64))
-        A = (keep @ A + sp.diags(m.astype(np.float64))).tocsr()
-        rhs = np.where(m, np.asarray(dirichlet_values, np.float64), rhs)
     A.sort_indices()
+    if dirichlet_mask is not None:
+        # getGlobalRowCopy / fill(vals, 0) / vals[diag] = 1 / replaceGlobalValues: the pattern stays (:226-243)
+        m = np.asarray(dirichlet_mask) != 0
+        row = np.repeat(np.arange(N), np.diff(A.indptr))
+        A.data[m[row]] = 0.0
+        A.data[m[row] & (A.indices == row)] = 1.0
+        rhs = np.where(m, np.asarray(dirichlet_values, np.float64), rhs)
     return A, rhs
 
 
