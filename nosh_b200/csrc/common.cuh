@@ -172,7 +172,7 @@ struct Ctx {
   int persistent_mgpu = 1;          // multi-GPU persistent loop over peer memory (env NOSH_B200_PERSISTENT_MGPU=0 /
                                     // tuning key "persistent_mgpu" select the multi-launch loop)
   int persist_grid_mgpu = 0;
-  int mgpu_fence = 1;               // measurement knob of k_minres_persistent_mgpu (krylov.cu)
+  int mgpu_fence = 2;               // k_minres_persistent_mgpu: who fences system-wide after the halo push (krylov.cu)
   int persist_grid = 0;             // co-resident CTAs of that kernel (occupancy x SMs), computed once
   int apply_variant = 0;            // measurement knob: which k_apply_sell variant the MINRES loop uses (apply.cu)
   int64_t group_vertices = 65536;

@@ -371,3 +371,75 @@ def test_newton_solver_choice(nb, orc):
     assert its[("gmres", nb.PREC_KEOREG_AMG)].sum() < its[("gmres", nb.PREC_NONE)].sum() / 2
     with pytest.raises(ValueError):
         ctx.set_linear_solver(7)
+
+
+def test_two_level_hierarchy_by_dense_linear_algebra(nb):
+    """An INDEPENDENT check of the device hierarchy (the other tests compare with oracle/amg.py, the builder's own
+    restatement of MueLu): on a 343-vertex mesh with two levels everything is re-derived here with dense numpy
+    from the published definitions only -- the matrix is read off the device by applying it to unit vectors, the
+    aggregates, the prolongator and the coarse operator come from the device accessors:
+      * the aggregates partition the vertices,
+      * P (I_c scaled) reproduces the damped-Jacobi-smoothed constants:  P w = (I - omega D^-1 A) 1  per dof,
+        w_a = sqrt(|aggregate a|), omega = (4/3) / lambda_max reported by the device,
+      * the coarse operator is the Galerkin product  A_c = P^T A P,
+      * one V-cycle is  pre-smoothing, exact coarse solve of the restricted residual, post-smoothing  with the
+        Chebyshev recurrence on S^-1 A, S = absolute row sums, spectrum [1/20, 1]."""
+    n = 7
+    ctx = nb.Context()
+    mi = ctx.mesh_tetgrid(n)
+    N = int(mi.n_owned)
+    ctx.set_thickness(None, 1.0)
+    ctx.set_potential_constant(-1.0)
+    ctx.set_mvp_constcurl((0.0, 0.0, 1.0))
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(2 * N) * 0.7
+    ctx.amg_set_options(degree=1, coarse_degree=2, coarse_max=64)
+    ctx.keoreg_rebuild(PARAMS, x)
+    # the regularised KEO as a dense matrix, column by column, from the device operator itself
+    eye = np.eye(2 * N)
+    A = np.array(ctx.keoreg_matrix_apply(eye)).T          # rows of the 2-D argument are the columns of the multi-vector
+    assert np.abs(A - A.T).max() <= 1e-12 * np.abs(A).max() and np.linalg.eigvalsh(A).min() > 0
+    b = rng.standard_normal(2 * N)
+    z = ctx.keoreg_apply(b)
+    info = ctx.amg_info()
+    assert info.levels == 2
+    nc = int(info.nodes[1])
+    agg = ctx.amg_aggregates(0)
+    assert agg.shape == (N,) and agg.min() == 0 and agg.max() == nc - 1
+    sizes = np.bincount(agg, minlength=nc)
+    assert sizes.min() >= 1 and sizes.sum() == N
+    P = block_csr_to_scipy(*ctx.amg_prolongator(0), ncols=nc).toarray()
+    Ac = block_csr_to_scipy(*ctx.amg_matrix(1), ncols=nc).toarray()
+    omega = (4.0 / 3.0) / info.lambda_max[0]
+    assert 0.5 < info.lambda_max[0] < 4.0
+    for c in (0, 1):                                      # the two dofs (re, im) of a vertex
+        onef = np.zeros(2 * N)
+        onef[c::2] = 1.0
+        w = np.zeros(2 * nc)
+        w[c::2] = np.sqrt(sizes)
+        assert relerr(P @ w, onef - omega * (A @ onef) / np.diag(A)) <= 1e-12
+    assert relerr(Ac, P.T @ A @ P) <= 1e-12
+    # the V-cycle, densely
+    sinv = 1.0 / np.abs(A).sum(axis=1)
+    theta, delta = 0.5 * (1.0 + 1.0 / 20.0), 0.5 * (1.0 - 1.0 / 20.0)
+    sigma = theta / delta
+
+    def cheb(M, si, rhs, x0, degree):
+        rho = 1.0 / sigma
+        r = rhs if x0 is None else rhs - M @ x0
+        d = (si * r) / theta
+        xx = d.copy() if x0 is None else x0 + d
+        for _ in range(1, degree):
+            rho_new = 1.0 / (2.0 * sigma - rho)
+            d = (rho_new * rho) * d + (2.0 * rho_new / delta) * (si * (rhs - M @ xx))
+            xx = xx + d
+            rho = rho_new
+        return xx
+    x1 = cheb(A, sinv, b, None, 1)
+    xc = np.linalg.solve(Ac, P.T @ (b - A @ x1))
+    zd = cheb(A, sinv, b, x1 + P @ xc, 1)
+    assert relerr(z, zd) <= 1e-11
+    # and it is a symmetric positive definite preconditioner
+    M = np.array(ctx.keoreg_apply(eye)).T
+    assert np.abs(M - M.T).max() <= 1e-11 * np.abs(M).max() and np.linalg.eigvalsh(0.5 * (M + M.T)).min() > 0
+    ctx.close()
