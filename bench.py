@@ -653,6 +653,7 @@ def run_b200(args):
                 if label == "amg":
                     ai = ctx.amg_info()
                     newton[label].update({"hierarchy_setup_seconds": float(ai.setup_seconds),
+                                          "hierarchy_setup_phases_s": {k[10:]: v for k, v in ctx.stats("amg.setup.").items()},
                                           "level_nodes": [int(ai.nodes[l]) for l in range(ai.levels)],
                                           "preconditioner": "one V-cycle of smoothed-aggregation AMG on the regularised "
                                                             "KEO, per rank (block-Jacobi over ranks)"})

@@ -124,6 +124,9 @@ NOSH_API nosh_status nosh_ctx_comm_init_host(nosh_ctx *ctx, int rank, int nranks
 /* set-up timings and counters by name ("setup.mesh_s", "setup.halo_s", "setup.p2p_s", "p2p", "sell_sigma", ...);
  * NOSH_EKEY if unknown */
 NOSH_API nosh_status nosh_ctx_get_stat(nosh_ctx *ctx, const char *key, double *value);
+/* all recorded stats as "key=value\n" lines ("amg.setup.<phase>" = seconds of every phase of the last hierarchy
+ * build, "sell.stored_over_blocks", ...); NUL terminated, truncated to cap bytes */
+NOSH_API nosh_status nosh_ctx_list_stats(nosh_ctx *ctx, char *buf, int64_t cap);
 
 /* ---- mesh (a1-a3).  Replaces nosh::read + mesh_tetra/mesh_tri ctor:
  * src/mesh_reader.cpp:19-162, src/mesh.cpp:18-51,629-691, src/mesh_tetra.cpp:14-35,

@@ -116,6 +116,7 @@ def lib():
         "nosh_ctx_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
         "nosh_ctx_comm_init_host": (C.c_int, [vp, C.c_int, C.c_int, ALLGATHER_FN, vp]),
         "nosh_ctx_get_stat": (C.c_int, [vp, C.c_char_p, C.POINTER(dbl)]),
+        "nosh_ctx_list_stats": (C.c_int, [vp, vp, i64]),
         "nosh_partition_range": (C.c_int, [i64, C.c_int, C.c_int, i64, C.POINTER(i64), C.POINTER(i64),
                                            C.POINTER(i64)]),
         "nosh_mesh_set": (C.c_int, [vp, C.c_int, i64, vp, i64, vp]),

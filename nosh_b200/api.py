@@ -201,6 +201,16 @@ class Context:
         self._ck(self.L.nosh_ctx_get_stat(self.h, key.encode(), C.byref(v)))
         return v.value
 
+    def stats(self, prefix=""):
+        buf = C.create_string_buffer(1 << 16)
+        self._ck(self.L.nosh_ctx_list_stats(self.h, buf, len(buf)))
+        out = {}
+        for ln in buf.value.decode().splitlines():
+            k, _, v = ln.partition("=")
+            if k.startswith(prefix):
+                out[k] = float(v)
+        return out
+
     def synchronize(self):
         self._ck(self.L.nosh_ctx_synchronize(self.h))
 

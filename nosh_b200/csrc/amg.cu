@@ -992,12 +992,16 @@ void build_hierarchy(Ctx *ctx) {
     return e && atoi(e) != 0;
   }();
   auto tlast = t0;
+  // phase times: always recorded (nosh_ctx_get_stat "amg.setup.<phase>" = seconds summed over the levels; a
+  // stream synchronisation per phase is noise against the set-up), printed with NOSH_B200_AMG_TIMING=1
+  for (auto it = ctx->stats.begin(); it != ctx->stats.end();)
+    it = it->first.rfind("amg.setup.", 0) == 0 ? ctx->stats.erase(it) : std::next(it);
   auto tick = [&](const char *what, int lev) {
-    if (!timing) return;
     cudaStreamSynchronize(ctx->stream);
     const auto now = std::chrono::steady_clock::now();
-    fprintf(stderr, "[amg setup] level %d %-22s %8.1f ms\n", lev, what,
-            1e3 * std::chrono::duration<double>(now - tlast).count());
+    const double sec = std::chrono::duration<double>(now - tlast).count();
+    ctx->stats[std::string("amg.setup.") + what] += sec;
+    if (timing) fprintf(stderr, "[amg setup] level %d %-22s %8.1f ms\n", lev, what, 1e3 * sec);
     tlast = now;
   };
   amg_free(ctx);
@@ -1019,6 +1023,31 @@ void build_hierarchy(Ctx *ctx) {
       cudaMemPoolTrimTo(pool, 0);
     }
   } pool_guard{pool, ctx->stream, &keep_none};
+  // Grow the pool ONCE, up front: the expand-sort-compress products of level 0 need ~200 B of temporaries per
+  // matrix block (keys, indices, 2x2 products, the sort's double buffers); growing the pool piecemeal, allocation
+  // by allocation, is what made the same set-up take 0.35 ... 2.7 s on different boxes (first-touch mapping of
+  // ~25 GB in thousands of driver calls).  One big allocation, freed straight back into the pool (release
+  // threshold = keep everything), maps the same memory in one step.
+  {
+    size_t free_b = 0, total_b = 0;
+    CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    size_t want = (size_t)ctx->nb * 200;
+    if (const char *e = getenv("NOSH_B200_AMG_PREGROW_MB")) want = (size_t)atoll(e) << 20;
+    want = std::min(want, free_b / 2);
+    if (want >= ((size_t)64 << 20)) {
+      const auto tg = std::chrono::steady_clock::now();
+      void *p = nullptr;
+      if (cudaMallocAsync(&p, want, ctx->stream) == cudaSuccess) {
+        cudaFreeAsync(p, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+      } else {
+        cudaGetLastError();
+      }
+      ctx->stats["amg.pool_pregrow_s"] = std::chrono::duration<double>(std::chrono::steady_clock::now() - tg).count();
+      ctx->stats["amg.pool_pregrow_bytes"] = (double)want;
+      tick("pool pre-grow", 0);
+    }
+  }
   Temp tmp;
   DBuf<double> scratch;
   const int64_t No = ctx->No;

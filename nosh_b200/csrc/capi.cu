@@ -257,6 +257,22 @@ nosh_status nosh_ctx_get_stat(nosh_ctx *ctx, const char *key, double *value) {
   API_END(ctx)
 }
 
+// all recorded stats as "key=value\n" lines (NUL terminated, truncated to cap)
+nosh_status nosh_ctx_list_stats(nosh_ctx *ctx, char *buf, int64_t cap) {
+  API_BEGIN(ctx)
+  if (!buf || cap < 1) NOSH_THROW(NOSH_EINVAL, "NULL buffer");
+  std::string out;
+  char line[256];
+  for (const auto &kv : ctx->stats) {
+    snprintf(line, sizeof(line), "%s=%.9g\n", kv.first.c_str(), kv.second);
+    out += line;
+  }
+  const size_t n = std::min<size_t>(out.size(), (size_t)cap - 1);
+  memcpy(buf, out.data(), n);
+  buf[n] = 0;
+  API_END(ctx)
+}
+
 nosh_status nosh_mesh_set(nosh_ctx *ctx, int dim, int64_t nv, const double *coords, int64_t nc,
                           const int32_t *cells) {
   API_BEGIN(ctx)

@@ -394,7 +394,7 @@ def test_two_level_hierarchy_by_dense_linear_algebra(nb):
     rng = np.random.default_rng(5)
     x = rng.standard_normal(2 * N) * 0.7
     ctx.amg_set_options(degree=1, coarse_degree=2, coarse_max=64)
-    ctx.keoreg_rebuild(PARAMS, x)
+    ctx.keoreg_rebuild(dict(PARAMS, theta=0.0), x)
     # the regularised KEO as a dense matrix, column by column, from the device operator itself
     eye = np.eye(2 * N)
     A = np.array(ctx.keoreg_matrix_apply(eye)).T          # rows of the 2-D argument are the columns of the multi-vector
