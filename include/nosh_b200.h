@@ -380,6 +380,14 @@ typedef struct {
   double norm;  /* sqrt(inner_product(psi, psi)) */
   double fnorm;
 } nosh_continuation_step;
+/* LOCA::Thyra::SaveDataStrategy::saveSolution(x, p) (src/continuation_data_saver.hpp:24-50: the outNNNN dumps) and
+ * observer::observeSolution (src/observer.cpp:134-159: the CSV row): called by both continuation drivers after every
+ * accepted step with the step index, the parameter value, the Gibbs energy and scaled norm of the CSV, and the
+ * solution -- this rank's owned entries, interleaved (re,im), in HOST memory valid during the call.  A non-zero
+ * return stops the continuation (the steps so far are returned).  NULL removes the observer. */
+typedef int (*nosh_step_observer_fn)(void *user, int step, double param, double gibbs_energy, double norm,
+                                     const double *psi_host, int64_t n_doubles);
+NOSH_API nosh_status nosh_ctx_set_step_observer(nosh_ctx *ctx, nosh_step_observer_fn fn, void *user);
 NOSH_API nosh_status nosh_continuation(nosh_ctx *ctx, int np, const char *const *names,
                                        const double *values, const char *pname, double dp, int nsteps,
                                        double *psi, double nl_tol, int nl_maxit, double lin_tol,

@@ -75,6 +75,11 @@ class NewtonResult(C.Structure):
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
 
 
+# nosh_step_observer_fn: int (*)(void *user, int step, double param, double gibbs, double norm, const double *psi, int64 n)
+STEP_OBSERVER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double),
+                               C.c_int64)
+
+
 def build(force=False):
     """Compile the library in-tree with nvcc for sm_100a (nosh_b200/csrc/Makefile)."""
     args = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
@@ -117,6 +122,7 @@ def lib():
         "nosh_ctx_comm_init_host": (C.c_int, [vp, C.c_int, C.c_int, ALLGATHER_FN, vp]),
         "nosh_ctx_get_stat": (C.c_int, [vp, C.c_char_p, C.POINTER(dbl)]),
         "nosh_ctx_list_stats": (C.c_int, [vp, vp, i64]),
+        "nosh_ctx_set_step_observer": (C.c_int, [vp, STEP_OBSERVER_FN, vp]),
         "nosh_partition_range": (C.c_int, [i64, C.c_int, C.c_int, i64, C.POINTER(i64), C.POINTER(i64),
                                            C.POINTER(i64)]),
         "nosh_mesh_set": (C.c_int, [vp, C.c_int, i64, vp, i64, vp]),

@@ -561,6 +561,26 @@ class Context:
                                                     _ptr(psi), steps, C.byref(nrec)))
         return [steps[i] for i in range(nrec.value)]
 
+    def set_step_observer(self, fn):
+        """fn(step, param, gibbs_energy, norm, psi) is called after every accepted continuation step with this rank's
+        owned part of the solution (a numpy copy); returning True stops the run.  The image of the reference's
+        observer (CSV row, src/observer.cpp:134-159) and continuation_data_saver (outNNNN dumps).  None removes it."""
+        if fn is None:
+            self._obs_cb = _lib.STEP_OBSERVER_FN(0)
+            self._ck(self.L.nosh_ctx_set_step_observer(self.h, self._obs_cb, None))
+            return
+
+        def _cb(user, step, param, energy, norm, psi, n):
+            try:
+                arr = np.ctypeslib.as_array(psi, shape=(int(n),)).copy() if n > 0 else np.zeros(0)
+                return 1 if fn(int(step), float(param), float(energy), float(norm), arr) else 0
+            except Exception:          # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._obs_cb = _lib.STEP_OBSERVER_FN(_cb)
+        self._ck(self.L.nosh_ctx_set_step_observer(self.h, self._obs_cb, None))
+
     @staticmethod
     def write_continuation_csv(path, steps, pname):
         """The CSV the reference's observer writes (src/observer.cpp:134-159, src/csv_writer.cpp)."""

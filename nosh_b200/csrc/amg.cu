@@ -1263,9 +1263,8 @@ void amg_ensure(Ctx *ctx) {
   build_hierarchy(ctx);
 }
 
-void amg_vcycle(Ctx *ctx, const double2 *b, double2 *x, const KrylovState *gate) {
+static void vcycle_launches(Ctx *ctx, const double2 *b, double2 *x, const KrylovState *gate) {
   Amg &H = *ctx->amg;
-  if (ctx->No == 0) return;
   if (ctx->nranks > 1 && H.levels.size() > 1) {
     // block-Jacobi over ranks: smooth on buffers whose ghost part is zero, then copy out
     AmgLevel &L = *H.levels[0];
@@ -1274,6 +1273,47 @@ void amg_vcycle(Ctx *ctx, const double2 *b, double2 *x, const KrylovState *gate)
   } else {
     vcycle_level(ctx, H, 0, b, x, gate);
   }
+}
+
+// The cycle is ~25 launches, most of them 5-90 us long: issued one by one the launch gaps cost ~0.35 ms of a 2.9 ms
+// preconditioned iteration (profiles/r1_launches_amg_minres_n200_iters10.csv: 2.5 ms of kernels).  All arguments
+// are fixed for given (b, x, gate) pointers -- the Krylov loops alternate between two pairs -- so every distinct
+// cycle is captured once into a CUDA graph and replayed (NOSH_B200_AMG_GRAPH=0 / tuning key "amg_graph" = 0:
+// plain launches).  The graphs die with the hierarchy (amg_free).
+void amg_vcycle(Ctx *ctx, const double2 *b, double2 *x, const KrylovState *gate) {
+  Amg &H = *ctx->amg;
+  if (ctx->No == 0) return;
+  if (!ctx->amg_graph) {
+    vcycle_launches(ctx, b, x, gate);
+    return;
+  }
+  for (auto &g : H.graphs)
+    if (g.b == b && g.x == x && g.gate == gate && g.degree == ctx->amg_degree && g.coarse_degree == ctx->amg_coarse_degree) {
+      CUDA_CHECK(cudaGraphLaunch(g.exec, ctx->stream));
+      ctx->launches += g.launches;
+      return;
+    }
+  if (H.graphs.size() >= 8) {  // more pointer pairs than any solver here uses: stop caching, launch directly
+    vcycle_launches(ctx, b, x, gate);
+    return;
+  }
+  const int64_t l0 = ctx->launches;
+  cudaGraph_t graph = nullptr;
+  CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+  try {
+    vcycle_launches(ctx, b, x, gate);
+  } catch (...) {
+    cudaStreamEndCapture(ctx->stream, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  CUDA_CHECK(cudaStreamEndCapture(ctx->stream, &graph));
+  VcycleGraph g{b, x, gate, ctx->amg_degree, ctx->amg_coarse_degree, nullptr, ctx->launches - l0};
+  const cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) NOSH_THROW(NOSH_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+  H.graphs.push_back(g);
+  CUDA_CHECK(cudaGraphLaunch(g.exec, ctx->stream));
 }
 
 }  // namespace nosh

@@ -37,12 +37,24 @@ struct AmgLevel {
   DBuf<double2> b, x, x2, d, r;
 };
 
+// one captured V-cycle: the ~25 launches of a cycle for fixed (b, x, gate) pointers as one CUDA graph
+struct VcycleGraph {
+  const double2 *b;
+  double2 *x;
+  const KrylovState *gate;
+  int degree, coarse_degree;
+  cudaGraphExec_t exec;
+  int64_t launches;
+};
+
 struct Amg {
   std::vector<AmgLevel *> levels;
   DBuf<double> coarse_inv;  // dense (2 n_last)^2, row-major
   int64_t n_coarse2 = 0;
   double setup_seconds = 0.0;
+  std::vector<VcycleGraph> graphs;
   ~Amg() {
+    for (auto &g : graphs) cudaGraphExecDestroy(g.exec);
     for (auto *l : levels) delete l;
   }
 };

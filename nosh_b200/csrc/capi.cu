@@ -163,6 +163,7 @@ nosh_status nosh_ctx_create(int device, void *stream, nosh_ctx **out) {
   if (const char *e = getenv("NOSH_B200_PERSISTENT_MINRES")) ctx->persistent_minres = atoi(e) != 0;
   if (const char *e = getenv("NOSH_B200_PERSISTENT_MGPU")) ctx->persistent_mgpu = atoi(e) != 0;
   if (const char *e = getenv("NOSH_B200_MGPU_FENCE")) ctx->mgpu_fence = atoi(e);
+  if (const char *e = getenv("NOSH_B200_AMG_GRAPH")) ctx->amg_graph = atoi(e) != 0;
   if (const char *e = getenv("NOSH_B200_SELL_SIGMA")) ctx->sell_sigma = atoi(e) < 0 ? -1 : (atoi(e) != 0);
   *out = ctx;
   return NOSH_OK;
@@ -1044,6 +1045,13 @@ nosh_status nosh_fvm_cg(nosh_ctx *ctx, const double *b, double *x, double tol, i
   API_END(ctx)
 }
 
+nosh_status nosh_ctx_set_step_observer(nosh_ctx *ctx, nosh_step_observer_fn fn, void *user) {
+  API_BEGIN(ctx)
+  ctx->step_observer = fn;
+  ctx->step_observer_user = user;
+  API_END(ctx)
+}
+
 nosh_status nosh_ctx_set_tuning(nosh_ctx *ctx, const char *key, int value) {
   API_BEGIN(ctx)
   if (!key) NOSH_THROW(NOSH_EINVAL, "NULL key");
@@ -1054,6 +1062,8 @@ nosh_status nosh_ctx_set_tuning(nosh_ctx *ctx, const char *key, int value) {
     ctx->persistent_minres = value != 0;
   } else if (strcmp(key, "persistent_mgpu") == 0) {
     ctx->persistent_mgpu = value != 0;
+  } else if (strcmp(key, "amg_graph") == 0) {
+    ctx->amg_graph = value != 0;
   } else if (strcmp(key, "mgpu_fence") == 0) {
     ctx->mgpu_fence = value;
   } else if (strcmp(key, "sell_sigma") == 0) {

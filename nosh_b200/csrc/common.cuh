@@ -161,6 +161,8 @@ struct Ctx {
   int rank = 0, nranks = 1;
   NcclApi *nccl = nullptr;
   void *comm = nullptr;  // ncclComm_t
+  int (*step_observer)(void *, int, double, double, double, const double *, int64_t) = nullptr;  // continuation drivers
+  void *step_observer_user = nullptr;
   HostAllgather host_ag = nullptr;  // set-up exchange through the caller's communicator (no NCCL in the library)
   void *host_ag_user = nullptr;
   std::map<std::string, double> stats;  // set-up timings etc. (nosh_ctx_get_stat)
@@ -244,6 +246,7 @@ struct Ctx {
   int amg_coarse_max = 512;   // nodes at which the hierarchy stops and a dense inverse is used
   int amg_max_levels = 10;
   int amg_reuse = 1;          // nosh_amg_reuse: 0 none, 1 full ("reuse: type" = "full", keo_regularized.cpp:300)
+  int amg_graph = 1;          // replay the V-cycle as a CUDA graph (amg.cu:amg_vcycle)
   bool amg_keep_l0 = false;   // keep the level-0 block CSR copy (parity accessors)
   int64_t keoreg_version = 0, amg_dinv_version = -1;
   int lin_solver = 0;         // nosh_linear_solver of the Newton / continuation drivers (default MINRES)

@@ -1337,6 +1337,16 @@ void newton_dev(Ctx *ctx, int np, const char *const *names, const double *values
   }
 }
 
+// observer::observeSolution / continuation_data_saver::saveSolution: hand the accepted step to the caller
+static bool observe_step(Ctx *ctx, int step, double param, double energy, double norm, const double2 *psi) {
+  if (!ctx->step_observer) return false;
+  std::vector<double> h(2 * (size_t)(ctx->No > 0 ? ctx->No : 1));
+  if (ctx->No)
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), psi, sizeof(double2) * ctx->No, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return ctx->step_observer(ctx->step_observer_user, step, param, energy, norm, h.data(), 2 * ctx->No) != 0;
+}
+
 // Natural-parameter continuation with a tangent predictor (LOCA "Natural" stepper + "Tangent"
 // predictor of examples/conf.xml:35-47, constant step; the arc-length variant needs bordered solves
 // and is a later row).  Step k: p_k = p_0 + k dp; for k > 0 the predictor solves J t = -dF/dp at the
@@ -1381,7 +1391,8 @@ void continuation_dev(Ctx *ctx, int np, const char *const *names, const double *
     st.gibbs_energy = weighted_sum_dev(ctx, 2, psi, psi) / volume;
     st.norm = sqrt(weighted_sum_dev(ctx, 1, psi, psi) / volume);
     if (out) out[k] = st;
-    if (!nr.converged) {
+    const bool stop = nr.converged && observe_step(ctx, k, st.param, st.gibbs_energy, st.norm, psi);
+    if (!nr.converged || stop) {
       for (int j = k + 1; j <= nsteps && out; j++) {
         memset(&out[j], 0, sizeof(st));
         out[j].step = -1;
@@ -1452,6 +1463,7 @@ void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *val
     st.gibbs_energy = weighted_sum_dev(ctx, 2, psi, psi) / volume;
     st.norm = sqrt(weighted_sum_dev(ctx, 1, psi, psi) / volume);
     if (out) out[k] = st;
+    return conv ? observe_step(ctx, k, st.param, st.gibbs_energy, st.norm, psi) : false;
   };
   // tangent at (psi, p): J t = -dF/dp; returns MINRES iterations, writes (XD, pdot) with the sign that
   // keeps <(XD,pdot)_new, (XD,pdot)_old> > 0 (first call: pdot has the sign of ds)
@@ -1478,9 +1490,9 @@ void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *val
   nosh_newton_result nr;
   newton_dev(ctx, np, names, vals.data(), psi, opt->nl_tol, opt->nl_maxit, opt->lin_tol, opt->lin_maxit, &nr, nullptr,
              nullptr);
-  record(0, nr.converged, nr.steps, nr.total_linear_iterations, 0, nr.fnorm, 0.0, 0.0);
+  bool stop = record(0, nr.converged, nr.steps, nr.total_linear_iterations, 0, nr.fnorm, 0.0, 0.0);
   done = 1;
-  if (nr.converged && opt->max_steps > 0) {
+  if (nr.converged && opt->max_steps > 0 && !stop) {
     double ds = opt->initial_step_size, pdot = 0.0;
     int pred_its = tangent(pdot, true, ds);
     ds = fabs(ds);
@@ -1536,8 +1548,9 @@ void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *val
       if (No) CUDA_CHECK(cudaMemcpyAsync(X0.p, psi, sizeof(double2) * No, cudaMemcpyDeviceToDevice, ctx->stream));
       const int pred_prev = pred_its;
       pred_its = tangent(pdot, false, 0.0);
-      record(k, 1, its, lin, pred_prev, nrm, ds_used, pdot);
+      stop = record(k, 1, its, lin, pred_prev, nrm, ds_used, pdot);
       done = k + 1;
+      if (stop) break;
       const double fac = (double)(opt->nl_maxit - its) / (double)(opt->nl_maxit - 1);
       ds *= 1.0 + opt->aggressiveness * fac * fac;
       if (ds > opt->max_step_size) ds = opt->max_step_size;

@@ -21,6 +21,8 @@
 #pragma once
 #include <algorithm>
 #include <cstdlib>
+#include <functional>
+#include <set>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -152,6 +154,48 @@ public:
     return gids_;
   }
   const comm &get_comm() const { return comm_; }
+
+  // ---- subdomains (src/mesh.cpp:142-196, src/subdomain.hpp): vertex sets selected by is_inside(x), restricted
+  // to the boundary skin for is_boundary_only subdomains; "everywhere" and "boundary" exist by default (:59-75)
+  struct subdomain_def {
+    std::string id;
+    bool is_boundary_only;
+    std::function<bool(const double *x)> is_inside;
+  };
+  void mark_subdomains(const std::vector<subdomain_def> &subdomains) const {
+    ensure_vertex_data();
+    for (const auto &sd : subdomains) {
+      std::vector<int32_t> flags((size_t)info_.n_owned, 0);
+      for (int64_t k = 0; k < info_.n_owned; k++)
+        if ((!sd.is_boundary_only || boundary_[k]) && sd.is_inside(&coords_[3 * (size_t)k])) flags[k] = 1;
+      subdomains_[sd.id] = std::move(flags);
+    }
+  }
+  const std::vector<int32_t> &get_vertices(const std::string &subdomain_id) const {
+    ensure_vertex_data();
+    auto it = subdomains_.find(subdomain_id);
+    if (it == subdomains_.end())  // src/mesh.cpp:199-210
+      throw std::logic_error("Subdomain \"" + subdomain_id + "\" not found. Did you call mark_subdomains({...}) on the mesh?");
+    return it->second;
+  }
+  const std::vector<double> &local_coords() const {
+    ensure_vertex_data();
+    return coords_;
+  }
+  // edge list in local vertex ids with length and covolume (src/mesh.hpp: get_edge_data / my_edges)
+  struct edge_arrays {
+    std::vector<int32_t> vertices;  // E x 2
+    std::vector<double> length, covolume;
+  };
+  const edge_arrays &edge_data() const {
+    if (edges_.length.empty() && info_.n_edges > 0) {
+      edges_.vertices.resize(2 * (size_t)info_.n_edges);
+      edges_.length.resize((size_t)info_.n_edges);
+      edges_.covolume.resize((size_t)info_.n_edges);
+      check(ctx_, nosh_mesh_get_edges(ctx_, edges_.vertices.data(), edges_.length.data(), edges_.covolume.data()));
+    }
+    return edges_;
+  }
   // mesh::write (src/mesh.cpp:249-263), the outNNNN dumps of continuation_data_saver.hpp:24-50: the mesh of
   // the file with `psi` replaced by the given state
   void write(const std::string &file_name, const Tpetra::Vector<double, int, int> *psi = nullptr) const {
@@ -255,6 +299,19 @@ private:
   std::vector<double> file_coords_;
   std::vector<int32_t> file_cells_;
   std::map<std::string, std::pair<int, std::vector<double>>> tags_;
+  void ensure_vertex_data() const {
+    if (!coords_.empty() || info_.n_owned + info_.n_ghost == 0) return;
+    coords_.resize(3 * (size_t)(info_.n_owned + info_.n_ghost));
+    check(ctx_, nosh_mesh_get_coords(ctx_, coords_.data()));
+    boundary_.assign((size_t)info_.n_owned, 0);
+    if (comm_.size == 1) check(ctx_, nosh_mesh_boundary_vertices(ctx_, boundary_.data()));
+    subdomains_["everywhere"] = std::vector<int32_t>((size_t)info_.n_owned, 1);
+    subdomains_["boundary"] = boundary_;
+  }
+  mutable std::vector<double> coords_;
+  mutable std::vector<int32_t> boundary_;
+  mutable std::map<std::string, std::vector<int32_t>> subdomains_;
+  mutable edge_arrays edges_;
   nosh_ctx *ctx_ = nullptr;
   comm comm_;
   mutable std::vector<int64_t> gids_;
@@ -581,6 +638,149 @@ public:
     st.achieved_tol = r.relres;
     return st;
   }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Generic finite-volume matrix (src/fvm_matrix.hpp, src/matrix_core_{edge,vertex,boundary,dirichlet}.hpp).  The
+// reference's cores are virtual eval(moab::EntityHandle) objects generated by nfc; MOAB handles do not exist here,
+// so eval receives what the generated bodies look up through the handle (edge index, end points, length,
+// covolume / vertex index, coordinates, control volume).  fill() evaluates every core ONCE on the host into
+// per-edge 2x2 blocks and per-vertex pairs and hands them to the device (nosh_fvm_matrix_fill: slot scatter, no
+// atomics); apply() is the device SpMV.  One rank.
+// ---------------------------------------------------------------------------------------------
+struct edge_ref {
+  int64_t index;
+  int32_t v0, v1;            // local vertex ids, gid(v0) < gid(v1)
+  const double *x0, *x1;     // coordinates
+  double length, covolume;   // mesh->get_edge_data()[k]
+};
+struct vertex_ref {
+  int64_t index;             // local (owned) vertex id
+  const double *x;
+  double control_volume;
+};
+struct matrix_core_edge_data {
+  double lhs[2][2];
+  double rhs[2];
+};
+class matrix_core_edge {
+public:
+  explicit matrix_core_edge(std::set<std::string> _subdomain_ids = {"everywhere"}) : subdomain_ids(std::move(_subdomain_ids)) {}
+  virtual ~matrix_core_edge() = default;
+  virtual matrix_core_edge_data eval(const edge_ref &edge) const = 0;
+  const std::set<std::string> subdomain_ids;
+};
+struct vertex_data {
+  double lhs, rhs;
+};
+class matrix_core_vertex {
+public:
+  explicit matrix_core_vertex(std::set<std::string> _subdomain_ids = {"everywhere"}) : subdomain_ids(std::move(_subdomain_ids)) {}
+  virtual ~matrix_core_vertex() = default;
+  virtual vertex_data eval(const vertex_ref &vertex) const = 0;
+  const std::set<std::string> subdomain_ids;
+};
+using matrix_core_boundary = matrix_core_vertex;  // same shape (src/matrix_core_boundary.hpp)
+class matrix_core_dirichlet {
+public:
+  explicit matrix_core_dirichlet(std::set<std::string> _subdomain_ids) : subdomain_ids(std::move(_subdomain_ids)) {}
+  virtual ~matrix_core_dirichlet() = default;
+  virtual double eval(const vertex_ref &vertex) const = 0;
+  const std::set<std::string> subdomain_ids;
+};
+
+class fvm_matrix : public Tpetra::Operator<double, int, int> {
+public:
+  fvm_matrix(const std::shared_ptr<const nosh::mesh> &_mesh, std::vector<std::shared_ptr<const matrix_core_edge>> matrix_core_edges,
+             std::vector<std::shared_ptr<const matrix_core_vertex>> matrix_core_vertexs,
+             std::vector<std::shared_ptr<const matrix_core_boundary>> matrix_core_boundarys,
+             std::vector<std::shared_ptr<const matrix_core_dirichlet>> dbcs)
+      : mesh(_mesh), matrix_core_edges_(std::move(matrix_core_edges)), matrix_core_vertexs_(std::move(matrix_core_vertexs)),
+        matrix_core_boundarys_(std::move(matrix_core_boundarys)), dbcs_(std::move(dbcs)) {}
+
+  // src/fvm_matrix.hpp:44-70: zero, edge / vertex / boundary contributions, Dirichlet rows; rhs optional
+  void fill(const std::shared_ptr<Tpetra::Vector<double, int, int>> &rhs = nullptr) {
+    const auto &ed = mesh->edge_data();
+    const auto &xc = mesh->local_coords();
+    const int64_t E = mesh->info().n_edges, N = mesh->info().n_owned;
+    auto cv = mesh->control_volumes();
+    std::vector<double> elhs(4 * (size_t)E, 0.0), erhs(2 * (size_t)E, 0.0), vlhs((size_t)N, 0.0), vrhs((size_t)N, 0.0), dval((size_t)N, 0.0);
+    std::vector<int32_t> dmask((size_t)N, 0);
+    for (const auto &core : matrix_core_edges_)
+      for (const auto &sd : core->subdomain_ids) {
+        const auto &in = mesh->get_vertices(sd);
+        for (int64_t k = 0; k < E; k++) {
+          const int32_t v0 = ed.vertices[2 * k], v1 = ed.vertices[2 * k + 1];
+          const bool in0 = v0 < N && in[v0], in1 = v1 < N && in[v1];
+          if (!in0 && !in1) continue;
+          const auto d = core->eval({k, v0, v1, &xc[3 * (size_t)v0], &xc[3 * (size_t)v1], ed.length[k], ed.covolume[k]});
+          // interior edges of the subdomain contribute both rows, half edges the row of the vertex inside (:96-146)
+          if (in0) {
+            elhs[4 * k] += d.lhs[0][0];
+            elhs[4 * k + 1] += d.lhs[0][1];
+            erhs[2 * k] += d.rhs[0];
+          }
+          if (in1) {
+            elhs[4 * k + 2] += d.lhs[1][0];
+            elhs[4 * k + 3] += d.lhs[1][1];
+            erhs[2 * k + 1] += d.rhs[1];
+          }
+        }
+      }
+    auto vertex_loop = [&](const std::vector<std::shared_ptr<const matrix_core_vertex>> &cores) {
+      for (const auto &core : cores)
+        for (const auto &sd : core->subdomain_ids) {
+          const auto &in = mesh->get_vertices(sd);
+          for (int64_t k = 0; k < N; k++)
+            if (in[k]) {
+              const auto d = core->eval({k, &xc[3 * (size_t)k], (*cv)[k]});
+              vlhs[k] += d.lhs;
+              vrhs[k] += d.rhs;
+            }
+        }
+    };
+    vertex_loop(matrix_core_vertexs_);
+    vertex_loop(matrix_core_boundarys_);
+    for (const auto &bc : dbcs_)
+      for (const auto &sd : bc->subdomain_ids) {
+        const auto &in = mesh->get_vertices(sd);
+        for (int64_t k = 0; k < N; k++)
+          if (in[k]) {
+            dmask[k] = 1;
+            dval[k] = bc->eval({k, &xc[3 * (size_t)k], (*cv)[k]});
+          }
+      }
+    const bool any_d = !dbcs_.empty();
+    check(mesh->ctx(), nosh_fvm_matrix_fill(mesh->ctx(), nullptr, elhs.data(), erhs.data(), vlhs.data(), vrhs.data(),
+                                            any_d ? dmask.data() : nullptr, any_d ? dval.data() : nullptr,
+                                            rhs ? rhs->getDataNonConst() : nullptr));
+  }
+  void apply(const Tpetra::MultiVector<double, int, int> &X, Tpetra::MultiVector<double, int, int> &Y,
+             Teuchos::ETransp mode = Teuchos::NO_TRANS, double alpha = 1.0, double beta = 0.0) const override {
+    if (mode != Teuchos::NO_TRANS || alpha != 1.0 || beta != 0.0) throw std::logic_error("fvm_matrix::apply: only y = A x");
+    for (size_t j = 0; j < X.getNumVectors(); j++)
+      check(mesh->ctx(), nosh_fvm_matrix_apply(mesh->ctx(), X.getData(j), Y.getDataNonConst(j)));
+  }
+  Teuchos::RCP<const Tpetra::Map<int, int>> getDomainMap() const override { return mesh->map(); }
+  Teuchos::RCP<const Tpetra::Map<int, int>> getRangeMap() const override { return mesh->map(); }
+  // mikado::linear_solve(A, b, x, {"package": "Belos", "method": "Pseudo Block CG"}) of examples/poisson/poisson.cpp
+  linear_solve_status solve_cg(const Tpetra::Vector<double, int, int> &b, Tpetra::Vector<double, int, int> &x, double tol = 1e-10,
+                               int maxit = 1000) const {
+    nosh_krylov_result r;
+    check(mesh->ctx(), nosh_fvm_cg(mesh->ctx(), b.getData(), x.getDataNonConst(), tol, maxit, &r));
+    linear_solve_status st;
+    st.iterations = r.iterations;
+    st.converged = r.converged != 0;
+    st.achieved_tol = r.relres;
+    return st;
+  }
+  const std::shared_ptr<const nosh::mesh> mesh;
+
+private:
+  const std::vector<std::shared_ptr<const matrix_core_edge>> matrix_core_edges_;
+  const std::vector<std::shared_ptr<const matrix_core_vertex>> matrix_core_vertexs_;
+  const std::vector<std::shared_ptr<const matrix_core_boundary>> matrix_core_boundarys_;
+  const std::vector<std::shared_ptr<const matrix_core_dirichlet>> dbcs_;
 };
 
 namespace model_evaluator {

@@ -439,6 +439,79 @@ static int run_ranks(int P) {
   return bad;
 }
 
+// ---- examples/poisson (poisson.py / poisson.cpp): -Laplace(u) = sin(y), u = 0 on the boundary with y < 0, u = 1
+// on the rest of the boundary, assembled from nfc-style cores through nosh::fvm_matrix and solved with CG ----
+namespace poisson {
+struct laplace_core : public nosh::matrix_core_edge {  // integrate(-n_dot_grad(u), dS): nfc's generated edge core
+  nosh::matrix_core_edge_data eval(const nosh::edge_ref &e) const override {
+    const double alpha = e.covolume / e.length;
+    return {{{alpha, -alpha}, {-alpha, alpha}}, {0.0, 0.0}};
+  }
+};
+struct source_core : public nosh::matrix_core_vertex {  // - integrate(sin(x[1]), dV): affine part, sign flipped to the rhs
+  nosh::vertex_data eval(const nosh::vertex_ref &v) const override { return {0.0, v.control_volume * std::sin(v.x[1])}; }
+};
+struct bc : public nosh::matrix_core_dirichlet {
+  bc(const std::string &sd, double value) : nosh::matrix_core_dirichlet({sd}), value_(value) {}
+  double eval(const nosh::vertex_ref &) const override { return value_; }
+  double value_;
+};
+}  // namespace poisson
+
+static void run_poisson() {
+  auto mesh = std::make_shared<nosh::mesh>(9, 9, 9, 0.15);
+  mesh->mark_subdomains({{"gamma0", true, [](const double *x) { return x[1] < 0; }},
+                         {"gamma1", true, [](const double *x) { return x[1] >= 0; }}});
+  REQUIRE_THROWS_AS(mesh->get_vertices("gamma2"), std::logic_error);
+  const auto &bnd = mesh->get_vertices("boundary");
+  const auto &g0 = mesh->get_vertices("gamma0"), &g1 = mesh->get_vertices("gamma1");
+  int nb = 0, n0 = 0, n1 = 0;
+  for (size_t k = 0; k < bnd.size(); k++) {
+    nb += bnd[k];
+    n0 += g0[k];
+    n1 += g1[k];
+  }
+  REQUIRE_APPROX((double)nb, 9.0 * 9 * 9 - 7.0 * 7 * 7, 0.0);  // the skin of a 9^3 grid
+  REQUIRE_APPROX((double)(n0 + n1), (double)nb, 0.0);
+  nosh::fvm_matrix A(mesh, {std::make_shared<poisson::laplace_core>()}, {std::make_shared<poisson::source_core>()}, {},
+                     {std::make_shared<poisson::bc>("gamma0", 0.0), std::make_shared<poisson::bc>("gamma1", 1.0)});
+  auto rhs = std::make_shared<Tpetra::Vector<double, int, int>>(mesh->map());
+  A.fill(rhs);
+  Tpetra::Vector<double, int, int> x(mesh->map()), Ax(mesh->map());
+  const auto st = A.solve_cg(*rhs, x, 1e-11, 2000);
+  g_checks++;
+  if (!st.converged) { std::printf("FAIL poisson: CG did not converge (%d its, %.2e)\n", st.iterations, st.achieved_tol); g_fail++; }
+  A.apply(x, Ax);
+  double r2 = 0.0, b2 = 0.0, worst_bc = 0.0;
+  for (size_t k = 0; k < bnd.size(); k++) {
+    r2 += (Ax[k] - (*rhs)[k]) * (Ax[k] - (*rhs)[k]);
+    b2 += (*rhs)[k] * (*rhs)[k];
+    if (g0[k]) worst_bc = std::fmax(worst_bc, std::fabs(x[k]));
+    if (g1[k]) worst_bc = std::fmax(worst_bc, std::fabs(x[k] - 1.0));
+  }
+  REQUIRE_APPROX(1.0 + std::sqrt(r2 / b2), 1.0, 1e-9);
+  REQUIRE_APPROX(1.0 + worst_bc, 1.0, 1e-14);
+  // the device's built-in Laplace core gives the same system as the host-evaluated one
+  std::vector<double> vr(bnd.size()), dv(bnd.size()), rhs2(bnd.size()), x2(bnd.size());
+  auto cv = mesh->control_volumes();
+  const auto &xc = mesh->local_coords();
+  for (size_t k = 0; k < bnd.size(); k++) {
+    vr[k] = (*cv)[k] * std::sin(xc[3 * k + 1]);
+    dv[k] = g1[k] ? 1.0 : 0.0;
+  }
+  nosh_krylov_result kr;
+  nosh::check(mesh->ctx(), nosh_fvm_matrix_fill(mesh->ctx(), nullptr, nullptr, nullptr, nullptr, vr.data(), bnd.data(), dv.data(), rhs2.data()));
+  nosh::check(mesh->ctx(), nosh_fvm_cg(mesh->ctx(), rhs2.data(), x2.data(), 1e-11, 2000, &kr));
+  double worst = 0.0, scale = 0.0;
+  for (size_t k = 0; k < bnd.size(); k++) {
+    worst = std::fmax(worst, std::fabs(x2[k] - x[k]));
+    scale = std::fmax(scale, std::fabs(x[k]));
+  }
+  REQUIRE_APPROX(1.0 + worst / scale, 1.0, 1e-9);
+  REQUIRE_APPROX((double)kr.iterations, (double)st.iterations, 0.0);
+  std::printf("poisson: %d CG iterations, max |u| = %.3f, done\n", st.iterations, scale);
+}
+
 int main() {
   std::fflush(stdout);
   for (int P : {2, 3}) {
@@ -454,6 +527,7 @@ int main() {
     run(cubesmall());
     run_io(rectanglesmall(), 0.25, 2.5);
     run_io(cubesmall(), 0.25, 0.25);
+    run_poisson();
   } catch (const std::exception &e) {
     std::printf("FAIL uncaught exception: %s\n", e.what());
     return 2;

@@ -27,7 +27,27 @@ def test_reference_arm_runs_on_the_cpu_and_prints_one_json_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["value"] == d["value"] and "sample" in cb
     assert cb["cores"] == len(os.sched_getaffinity(0))
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and "l2" in d["config"]
+    assert d["steps"] == 1 and d["steps_requested"] == 1
+
+
+def test_reference_arm_on_the_gpu_box_ran_the_b200_arms_mesh():
+    """like for like: the committed reference-arm line (16 host cores of the GPU box) and the committed B200 line
+    carry the same config object"""
+    ref = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_reference_arm_n200_gpubox.json")))
+    gpu = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_default_1gpu_v2.json")))
+    assert ref["impl"] == "reference" and ref["config"] == gpu["config"]
+    assert ref["cpu_baseline"]["cores"] >= 8 and ref["value"] > 0
+    assert gpu["e2e"]["value"] / ref["value"] > 50
+
+
+def test_multi_gpu_lines_carry_the_parity_object():
+    for name, n in (("r2_bench_weak_2gpu_persistent.json", 2), ("r2_bench_weak_8gpu_persistent.json", 8)):
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        pr = d["parity"]
+        assert d["n_gpus"] == n and pr["ok"] is True and pr["ok_all_ranks"] is True and pr["bits_equal_one_gpu"] is True
+        assert pr["peer_memory"] is True and max(pr["f_relerr"], pr["jx_relerr"], pr["dfdmu_relerr"]) <= 1e-12
+        assert d["gpu_launches"] <= 10 * d["steps"]            # one cooperative launch per MINRES solve and rank
 
 
 def test_rank_other_than_zero_of_the_reference_arm_does_no_work():
@@ -38,13 +58,18 @@ def test_rank_other_than_zero_of_the_reference_arm_does_no_work():
 
 
 def test_committed_b200_line_has_every_contract_key():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_default_1gpu_v5.json")))
-    for k in BASE_KEYS + ["roofline", "cpu_baseline", "gpu_launches", "clocks"]:
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_default_1gpu_v2.json")))
+    for k in BASE_KEYS + ["roofline", "cpu_baseline", "gpu_launches", "clocks", "parity"]:
         assert k in d, k
+    # the parity gate ran before anything was timed: entry-wise KEO / F / J x / dF/dmu at 1.0M vertices <= 1e-12
+    pr = d["parity"]
+    assert pr["ok"] is True and max(pr["keo_entries_relerr"], pr["f_relerr"], pr["jx_relerr"], pr["dfdmu_relerr"]) <= 1e-12
+    assert pr["keo_entries_compared"] > 10_000_000 and pr["minres_count_ok"] is True
+    assert set(d["config"]) == {"workload", "l2"}         # the reference arm prints the same config object
     assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["data"] == "synthetic" and d["dtype"] == "f64"
     assert "workload" in d["config"] and "model" not in d["config"]
     rf = d["roofline"]
-    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "ms_per_launch_batches"):
         assert k in rf, k
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
     assert 0.7 <= rf["frac"] <= 1.1                      # BASELINE.json's target is >= 70 % of the HBM roofline

@@ -688,3 +688,35 @@ def test_fvm_operator_bratu(nb, orc):
     with pytest.raises(ValueError):
         ctx.fvm_operator_apply(u, vertex_core=nb.FVM_VERTEX_EXP_LINEARIZED, alpha=1.0)   # u0 missing
     ctx.close()
+
+
+def test_continuation_step_observer_writes_the_out_files(nb, orc, tmp_path):
+    """continuation_data_saver::saveSolution (outNNNN dumps) and observer::observeSolution (CSV row) as a step
+    observer of both continuation drivers; a True return stops the run."""
+    coords, cells = orc.meshgen.tetgrid(8)
+    ctx, P, psi = make_pair(nb, orc, coords, cells, 1, group=512)
+    rows, files = [], []
+
+    def observer(step, param, energy, norm, x):
+        path = str(tmp_path / ("out%04d.vtk" % step))
+        nb.write_mesh(path, coords, cells, {"psi": x.reshape(-1, 2)}, binary=True)
+        files.append(path)
+        rows.append((step, param, energy, norm))
+        return False
+    ctx.set_step_observer(observer)
+    xg = psi.copy()
+    steps = ctx.continuation({"g": 1.0, "mu": 0.0}, "mu", 0.05, 3, xg)
+    assert [r[0] for r in rows] == [0, 1, 2, 3] and len(steps) == 4
+    for s, r in zip(steps, rows):
+        assert (s.param, s.gibbs_energy, s.norm) == r[1:]
+    _, _, tags = nb.read_mesh(files[-1])
+    assert np.array_equal(tags["psi"].reshape(-1), xg)            # the last dump is the returned solution
+    # arc-length driver, stopped by the observer after its second accepted step
+    rows.clear()
+    ctx.set_step_observer(lambda step, *a: (rows.append(step) or step >= 2))
+    al = ctx.continuation_arclength({"g": 1.0, "mu": 0.0}, "mu", psi.copy(), initial_step_size=0.05, max_step_size=0.1,
+                                    max_steps=6)
+    assert rows == [0, 1, 2] and len(al) == 3
+    ctx.set_step_observer(None)
+    assert len(ctx.continuation({"g": 1.0, "mu": 0.0}, "mu", 0.05, 1, psi.copy())) == 2 and rows == [0, 1, 2]
+    ctx.close()
