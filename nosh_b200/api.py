@@ -206,7 +206,7 @@ class Context:
         self._ck(self.L.nosh_ctx_list_stats(self.h, buf, len(buf)))
         out = {}
         for ln in buf.value.decode().splitlines():
-            k, _, v = ln.partition("=")
+            k, _, v = ln.rpartition("=")
             if k.startswith(prefix):
                 out[k] = float(v)
         return out

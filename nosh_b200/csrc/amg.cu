@@ -367,10 +367,12 @@ __global__ void k_mm_count(Csr A, Csr B, int64_t *cnt) {
     }
   cnt[i] = c;
 }
-__global__ void k_mm_expand(Csr A, Csr B, const int64_t *off, uint64_t *keys, uint32_t *idx, B22 *vals) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= A.n) return;
-  int64_t t = off[i];
+// rows [r0, r1) of the product (one panel): positions are relative to off[r0]
+__global__ void k_mm_expand(Csr A, Csr B, const int64_t *off, int64_t r0, int64_t r1, uint64_t *keys, uint32_t *idx,
+                            B22 *vals) {
+  const int64_t i = r0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= r1) return;
+  int64_t t = off[i] - off[r0];
   for (int p = A.rowptr[i]; p < A.rowptr[i + 1]; p++) {
     const int k = A.col[p];
     const B22 a = A.val[p];
@@ -387,10 +389,11 @@ __global__ void k_atb_count(Csr A, Csr B, int64_t *cnt) {
   if (i > A.n) return;
   cnt[i] = i < A.n ? (int64_t)(A.rowptr[i + 1] - A.rowptr[i]) * (B.rowptr[i + 1] - B.rowptr[i]) : 0;
 }
-__global__ void k_atb_expand(Csr A, Csr B, const int64_t *off, uint64_t *keys, uint32_t *idx, B22 *vals) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= A.n) return;
-  int64_t t = off[i];
+__global__ void k_atb_expand(Csr A, Csr B, const int64_t *off, int64_t r0, int64_t r1, uint64_t *keys, uint32_t *idx,
+                             B22 *vals) {
+  const int64_t i = r0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= r1) return;
+  int64_t t = off[i] - off[r0];
   for (int p = A.rowptr[i]; p < A.rowptr[i + 1]; p++) {
     const B22 a = A.val[p];
     const uint64_t hi = (uint64_t)(uint32_t)A.col[p] << 32;
@@ -432,42 +435,114 @@ struct CsrOut {
   Csr view() const { return Csr{n, rowptr.p, col.p, val.p}; }
 };
 
-// expand (already counted) -> sort -> compress
-template <typename ExpandFn>
-void esc_finish(Ctx *ctx, Temp &tmp, TBuf<int64_t> &cnt, int64_t nrows_in, int64_t nrows_out, ExpandFn expand,
-                CsrOut &C) {
-  TBuf<int64_t> off;
-  off.alloc(nrows_in + 1);
-  exclusive_scan_i64(ctx, tmp, cnt.p, off.p, nrows_in + 1);
-  const int64_t total = fetch(ctx, off.p + nrows_in);
-  check_count(total, "a sparse product");
-  TBuf<uint64_t> keys;
-  TBuf<uint32_t> idx;
-  TBuf<B22> vals;
-  keys.alloc(total);
-  idx.alloc(total);
-  vals.alloc(total);
-  expand(off.p, keys.p, idx.p, vals.p);
-  off.release();
-  cnt.release();
+// second-level merge of the panels of A^T B: the compressed entries of all panels, concatenated, as "products"
+__global__ void k_merge_keys(const uint64_t *ukeys, int64_t n, uint64_t *keys, uint32_t *idx) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys[i] = ukeys[i];
+    idx[i] = (uint32_t)i;
+  }
+}
+__global__ void k_panel_cols(const uint64_t *ukeys, int64_t n, int32_t *col) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) col[i] = (int32_t)(ukeys[i] & 0xFFFFFFFFull);
+}
+
+// sort `total` (key, index) pairs and sum the products of every unique key in emission order:
+// out: nuniq, ukeys (nuniq), usum (nuniq)
+void sort_compress(Ctx *ctx, Temp &tmp, TBuf<uint64_t> &keys, TBuf<uint32_t> &idx, const B22 *vals, int64_t total,
+                   int64_t &nuniq, TBuf<uint64_t> &ukeys, TBuf<B22> &usum) {
   sort_pairs_u64(ctx, tmp, keys, idx, total);
-  TBuf<int32_t> head, excl;
+  TBuf<int32_t> head, excl, start, ucol;
   head.alloc(total + 1);
   excl.alloc(total + 1);
   ALAUNCH(ctx, k_head_flags, total + 1, keys.p, total, head.p);
   exclusive_scan_i32(ctx, tmp, head.p, excl.p, total + 1);
-  const int64_t nuniq = fetch(ctx, excl.p + total);
-  TBuf<uint64_t> ukeys;
-  TBuf<int32_t> start;
+  nuniq = fetch(ctx, excl.p + total);
   ukeys.alloc(nuniq);
   start.alloc(nuniq + 1);
+  ucol.alloc(nuniq);
+  usum.alloc(nuniq);
   ALAUNCH(ctx, k_unique_starts, total + 1, keys.p, head.p, excl.p, total, nuniq, ukeys.p, start.p);
+  ALAUNCH(ctx, k_segment_sum, nuniq, ukeys.p, start.p, idx.p, vals, nuniq, ucol.p, usum.p);
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+// Expand (already counted) -> sort -> compress, in ROW PANELS of at most ~panel_products products each: the
+// temporaries of one panel (44 B per product + the sort's double buffers) are reused by the next, so a product
+// with 460M terms (A P on 8M vertices) maps ~4 GB of pool memory instead of ~29 GB -- first-touch mapping of the
+// temporaries was what made the set-up take 0.35 ... 2.7 s depending on the box.  rows_disjoint: every output row
+// is produced by one panel only (C = A B): the panels' results are simply concatenated, bit-identical to one
+// panel.  Otherwise (C = A^T B) the compressed panels are merged by one more, small, sort-compress pass.
+template <typename ExpandFn>
+void esc_finish(Ctx *ctx, Temp &tmp, TBuf<int64_t> &cnt, int64_t nrows_in, int64_t nrows_out, bool rows_disjoint,
+                ExpandFn expand, CsrOut &C) {
+  TBuf<int64_t> off;
+  off.alloc(nrows_in + 1);
+  exclusive_scan_i64(ctx, tmp, cnt.p, off.p, nrows_in + 1);
+  cnt.release();
+  const int64_t total = fetch(ctx, off.p + nrows_in);
+  const int64_t budget = ctx->amg_panel_products > 0 ? ctx->amg_panel_products : ((int64_t)64 << 20);
+  const int64_t npanels = std::max<int64_t>(1, std::min<int64_t>(cdiv(total, budget), nrows_in > 0 ? nrows_in : 1));
+  std::vector<TBuf<uint64_t>> pk(npanels);
+  std::vector<TBuf<B22>> pv(npanels);
+  std::vector<int64_t> pn(npanels, 0);
+  int64_t nsum = 0;
+  for (int64_t q = 0; q < npanels; q++) {
+    const int64_t r0 = nrows_in * q / npanels, r1 = nrows_in * (q + 1) / npanels;
+    const int64_t ptotal = fetch(ctx, off.p + r1) - fetch(ctx, off.p + r0);
+    check_count(ptotal, "a panel of a sparse product");
+    if (ptotal == 0) continue;
+    TBuf<uint64_t> keys;
+    TBuf<uint32_t> idx;
+    TBuf<B22> vals;
+    keys.alloc(ptotal);
+    idx.alloc(ptotal);
+    vals.alloc(ptotal);
+    expand(off.p, r0, r1, keys.p, idx.p, vals.p);
+    sort_compress(ctx, tmp, keys, idx, vals.p, ptotal, pn[q], pk[q], pv[q]);
+    nsum += pn[q];
+  }
+  off.release();
+  check_count(nsum, "a sparse product");
+  // concatenate the panels (row-ordered for rows_disjoint)
+  TBuf<uint64_t> ukeys;
+  TBuf<B22> uval;
+  int64_t nuniq = nsum;
+  if (npanels == 1) {
+    ukeys.swap(pk[0]);
+    uval.swap(pv[0]);
+  } else {
+    ukeys.alloc(nsum);
+    uval.alloc(nsum);
+    int64_t at = 0;
+    for (int64_t q = 0; q < npanels; q++) {
+      if (!pn[q]) continue;
+      CUDA_CHECK(cudaMemcpyAsync(ukeys.p + at, pk[q].p, sizeof(uint64_t) * pn[q], cudaMemcpyDeviceToDevice, ctx->stream));
+      CUDA_CHECK(cudaMemcpyAsync(uval.p + at, pv[q].p, sizeof(B22) * pn[q], cudaMemcpyDeviceToDevice, ctx->stream));
+      at += pn[q];
+      pk[q].release();
+      pv[q].release();
+    }
+    if (!rows_disjoint) {
+      TBuf<uint64_t> keys, mk;
+      TBuf<uint32_t> idx;
+      TBuf<B22> mv;
+      keys.alloc(nsum);
+      idx.alloc(nsum);
+      ALAUNCH(ctx, k_merge_keys, nsum, ukeys.p, nsum, keys.p, idx.p);
+      sort_compress(ctx, tmp, keys, idx, uval.p, nsum, nuniq, mk, mv);
+      ukeys.swap(mk);
+      uval.swap(mv);
+    }
+  }
   C.n = nrows_out;
   C.nnz = nuniq;
   C.col.alloc(nuniq);
   C.val.alloc(nuniq);
   C.rowptr.alloc(nrows_out + 1);
-  ALAUNCH(ctx, k_segment_sum, nuniq, ukeys.p, start.p, idx.p, vals.p, nuniq, C.col.p, C.val.p);
+  ALAUNCH(ctx, k_panel_cols, nuniq, ukeys.p, nuniq, C.col.p);
+  if (nuniq) CUDA_CHECK(cudaMemcpyAsync(C.val.p, uval.p, sizeof(B22) * nuniq, cudaMemcpyDeviceToDevice, ctx->stream));
   ALAUNCH(ctx, k_rowptr_from_keys, nrows_out + 1, ukeys.p, nuniq, nrows_out, C.rowptr.p);
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
@@ -476,9 +551,9 @@ void spgemm(Ctx *ctx, Temp &tmp, const Csr &A, const Csr &B, CsrOut &C) {
   TBuf<int64_t> cnt;
   cnt.alloc(A.n + 1);
   ALAUNCH(ctx, k_mm_count, A.n + 1, A, B, cnt.p);
-  esc_finish(ctx, tmp, cnt, A.n, A.n,
-             [&](const int64_t *off, uint64_t *keys, uint32_t *idx, B22 *vals) {
-               ALAUNCH(ctx, k_mm_expand, A.n, A, B, off, keys, idx, vals);
+  esc_finish(ctx, tmp, cnt, A.n, A.n, true,
+             [&](const int64_t *off, int64_t r0, int64_t r1, uint64_t *keys, uint32_t *idx, B22 *vals) {
+               ALAUNCH(ctx, k_mm_expand, r1 - r0, A, B, off, r0, r1, keys, idx, vals);
              },
              C);
 }
@@ -486,9 +561,9 @@ void spgemm_atb(Ctx *ctx, Temp &tmp, const Csr &A, const Csr &B, int64_t ncols_a
   TBuf<int64_t> cnt;
   cnt.alloc(A.n + 1);
   ALAUNCH(ctx, k_atb_count, A.n + 1, A, B, cnt.p);
-  esc_finish(ctx, tmp, cnt, A.n, ncols_a,
-             [&](const int64_t *off, uint64_t *keys, uint32_t *idx, B22 *vals) {
-               ALAUNCH(ctx, k_atb_expand, A.n, A, B, off, keys, idx, vals);
+  esc_finish(ctx, tmp, cnt, A.n, ncols_a, false,
+             [&](const int64_t *off, int64_t r0, int64_t r1, uint64_t *keys, uint32_t *idx, B22 *vals) {
+               ALAUNCH(ctx, k_atb_expand, r1 - r0, A, B, off, r0, r1, keys, idx, vals);
              },
              C);
 }
@@ -1023,15 +1098,16 @@ void build_hierarchy(Ctx *ctx) {
       cudaMemPoolTrimTo(pool, 0);
     }
   } pool_guard{pool, ctx->stream, &keep_none};
-  // Grow the pool ONCE, up front: the expand-sort-compress products of level 0 need ~200 B of temporaries per
-  // matrix block (keys, indices, 2x2 products, the sort's double buffers); growing the pool piecemeal, allocation
-  // by allocation, is what made the same set-up take 0.35 ... 2.7 s on different boxes (first-touch mapping of
-  // ~25 GB in thousands of driver calls).  One big allocation, freed straight back into the pool (release
-  // threshold = keep everything), maps the same memory in one step.
+  // Grow the pool ONCE, up front, to what one panel of the expand-sort-compress products plus the compressed
+  // results need (esc_finish).  First-touch mapping of pool memory costs 6 ... 45 ms per GB depending on the box
+  // (measured: 23.8 GB in 0.13 s on one box, 1.06 s on another), which is what made the un-panelled set-up
+  // (~29 GB of temporaries for A P on 8M vertices) take 0.35 ... 2.7 s.  One allocation, freed straight back into
+  // the pool (release threshold = keep everything), maps the memory in one step.
   {
     size_t free_b = 0, total_b = 0;
     CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    size_t want = (size_t)ctx->nb * 200;
+    // one panel of the expand-sort-compress products (64M products x ~80 B) + the compressed results
+    size_t want = std::min<size_t>((size_t)ctx->nb * 200, ((size_t)6 << 30) + (size_t)ctx->nb * 40);
     if (const char *e = getenv("NOSH_B200_AMG_PREGROW_MB")) want = (size_t)atoll(e) << 20;
     want = std::min(want, free_b / 2);
     if (want >= ((size_t)64 << 20)) {

@@ -164,6 +164,8 @@ nosh_status nosh_ctx_create(int device, void *stream, nosh_ctx **out) {
   if (const char *e = getenv("NOSH_B200_PERSISTENT_MGPU")) ctx->persistent_mgpu = atoi(e) != 0;
   if (const char *e = getenv("NOSH_B200_MGPU_FENCE")) ctx->mgpu_fence = atoi(e);
   if (const char *e = getenv("NOSH_B200_AMG_GRAPH")) ctx->amg_graph = atoi(e) != 0;
+  if (const char *e = getenv("NOSH_B200_AMG_PANEL_PRODUCTS"))
+    if (atoll(e) > 0) ctx->amg_panel_products = atoll(e);
   if (const char *e = getenv("NOSH_B200_SELL_SIGMA")) ctx->sell_sigma = atoi(e) < 0 ? -1 : (atoi(e) != 0);
   *out = ctx;
   return NOSH_OK;
@@ -1062,6 +1064,10 @@ nosh_status nosh_ctx_set_tuning(nosh_ctx *ctx, const char *key, int value) {
     ctx->persistent_minres = value != 0;
   } else if (strcmp(key, "persistent_mgpu") == 0) {
     ctx->persistent_mgpu = value != 0;
+  } else if (strcmp(key, "amg_panel_products") == 0) {
+    if (value < 1) NOSH_THROW(NOSH_EINVAL, "amg_panel_products must be positive");
+    ctx->amg_panel_products = value;
+    ctx->amg_valid = false;
   } else if (strcmp(key, "amg_graph") == 0) {
     ctx->amg_graph = value != 0;
   } else if (strcmp(key, "mgpu_fence") == 0) {

@@ -443,3 +443,29 @@ def test_two_level_hierarchy_by_dense_linear_algebra(nb):
     M = np.array(ctx.keoreg_apply(eye)).T
     assert np.abs(M - M.T).max() <= 1e-11 * np.abs(M).max() and np.linalg.eigvalsh(0.5 * (M + M.T)).min() > 0
     ctx.close()
+
+
+def test_row_panelled_setup_products_give_the_same_hierarchy(nb, orc):
+    """The set-up's sparse products run in row panels (bounded temporaries).  C = A B panels are concatenated --
+    identical bits; C = A^T B panels are merged by one more sort-compress pass -- same entries to rounding."""
+    out = {}
+    for panel in (1 << 26, 3000):                       # one panel / dozens of panels
+        ctx, P, Pm, H, x, params = setup_pair(nb, orc, n=12, coarse_max=40)
+        ctx.set_tuning("amg_panel_products", panel)
+        ctx.keoreg_rebuild(params, x)
+        ctx.amg_setup()
+        info = ctx.amg_info()
+        b = orc.meshgen.random_state(P.N, 3)
+        out[panel] = (int(info.levels), [ctx.amg_aggregates(l) for l in range(info.levels - 1)],
+                      [ctx.amg_prolongator(l) for l in range(info.levels - 1)],
+                      [ctx.amg_matrix(l) for l in range(1, info.levels)], ctx.keoreg_apply(b))
+        ctx.close()
+    a, c = out[1 << 26], out[3000]
+    assert a[0] == c[0] >= 3
+    for u, v in zip(a[1], c[1]):
+        assert np.array_equal(u, v)
+    assert np.array_equal(a[2][0][0], c[2][0][0]) and np.array_equal(a[2][0][1], c[2][0][1])
+    assert np.array_equal(a[2][0][2], c[2][0][2])                # P of level 0: rows are disjoint between panels
+    for (rp1, c1, v1), (rp2, c2, v2) in zip(a[3], c[3]):
+        assert np.array_equal(rp1, rp2) and np.array_equal(c1, c2) and relerr(v2, v1) <= 1e-13
+    assert relerr(c[4], a[4]) <= 1e-12
