@@ -482,7 +482,7 @@ void esc_finish(Ctx *ctx, Temp &tmp, TBuf<int64_t> &cnt, int64_t nrows_in, int64
   exclusive_scan_i64(ctx, tmp, cnt.p, off.p, nrows_in + 1);
   cnt.release();
   const int64_t total = fetch(ctx, off.p + nrows_in);
-  const int64_t budget = ctx->amg_panel_products > 0 ? ctx->amg_panel_products : ((int64_t)64 << 20);
+  const int64_t budget = ctx->amg_panel_products > 0 ? ctx->amg_panel_products : ((int64_t)32 << 20);
   const int64_t npanels = std::max<int64_t>(1, std::min<int64_t>(cdiv(total, budget), nrows_in > 0 ? nrows_in : 1));
   std::vector<TBuf<uint64_t>> pk(npanels);
   std::vector<TBuf<B22>> pv(npanels);
@@ -1106,8 +1106,8 @@ void build_hierarchy(Ctx *ctx) {
   {
     size_t free_b = 0, total_b = 0;
     CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    // one panel of the expand-sort-compress products (64M products x ~80 B) + the compressed results
-    size_t want = std::min<size_t>((size_t)ctx->nb * 200, ((size_t)6 << 30) + (size_t)ctx->nb * 40);
+    // one panel of the expand-sort-compress products (32M products x ~80 B) + the compressed results
+    size_t want = std::min<size_t>((size_t)ctx->nb * 200, ((size_t)3 << 30) + (size_t)ctx->nb * 40);
     if (const char *e = getenv("NOSH_B200_AMG_PREGROW_MB")) want = (size_t)atoll(e) << 20;
     want = std::min(want, free_b / 2);
     if (want >= ((size_t)64 << 20)) {

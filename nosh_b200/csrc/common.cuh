@@ -246,7 +246,7 @@ struct Ctx {
   int amg_coarse_max = 512;   // nodes at which the hierarchy stops and a dense inverse is used
   int amg_max_levels = 10;
   int amg_reuse = 1;          // nosh_amg_reuse: 0 none, 1 full ("reuse: type" = "full", keo_regularized.cpp:300)
-  int64_t amg_panel_products = (int64_t)64 << 20;  // products per row panel of the set-up's sparse products (amg.cu)
+  int64_t amg_panel_products = (int64_t)32 << 20;  // products per row panel of the set-up's sparse products (amg.cu)
   int amg_graph = 1;          // replay the V-cycle as a CUDA graph (amg.cu:amg_vcycle)
   bool amg_keep_l0 = false;   // keep the level-0 block CSR copy (parity accessors)
   int64_t keoreg_version = 0, amg_dinv_version = -1;
