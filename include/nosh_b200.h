@@ -101,6 +101,15 @@ NOSH_API const char *nosh_last_error(const nosh_ctx *ctx);
 NOSH_API nosh_status nosh_ctx_set_layout(nosh_ctx *ctx, nosh_layout layout);
 NOSH_API nosh_status nosh_ctx_set_group_vertices(nosh_ctx *ctx, int64_t group_vertices);
 NOSH_API nosh_status nosh_ctx_synchronize(nosh_ctx *ctx);
+/* Pipelined host I/O (optional).  nosh_prefetch starts the host-to-device copy of a HOST state vector (n_owned
+ * complex entries; pinned memory for a truly asynchronous copy) on the ctx's copy stream and returns; the next
+ * call that is given the same host pointer waits for that copy instead of making its own -- issue it before a
+ * long call (a Krylov solve) and the next step's inputs travel while that solve runs.  With async output enabled,
+ * calls whose result vector is in host memory enqueue the device-to-host copy on the copy stream and return
+ * without waiting for it: the data is valid after nosh_ctx_synchronize (scalar results -- iteration counts,
+ * norms -- are always returned synchronously).  Default: off, every call returns with its result in host memory. */
+NOSH_API nosh_status nosh_prefetch(nosh_ctx *ctx, const double *host_vector);
+NOSH_API nosh_status nosh_ctx_set_async_output(nosh_ctx *ctx, int enabled);
 
 /* ---- multi-GPU (one process per GPU).  Replaces Teuchos::MpiComm / Tpetra
  * Import / reduceAll (src/mesh_reader.cpp:53-57; Tpetra, not in tree). ---------- */

@@ -117,6 +117,8 @@ def lib():
         "nosh_ctx_set_layout": (C.c_int, [vp, C.c_int]),
         "nosh_ctx_set_group_vertices": (C.c_int, [vp, i64]),
         "nosh_ctx_synchronize": (C.c_int, [vp]),
+        "nosh_prefetch": (C.c_int, [vp, vp]),
+        "nosh_ctx_set_async_output": (C.c_int, [vp, C.c_int]),
         "nosh_comm_unique_id": (C.c_int, [vp]),
         "nosh_ctx_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
         "nosh_ctx_comm_init_host": (C.c_int, [vp, C.c_int, C.c_int, ALLGATHER_FN, vp]),

@@ -201,6 +201,14 @@ class Context:
         self._ck(self.L.nosh_ctx_get_stat(self.h, key.encode(), C.byref(v)))
         return v.value
 
+    def prefetch(self, host_vector):
+        """start the H2D copy of a host state vector now; the next call given the same array waits for it"""
+        self._ck(self.L.nosh_prefetch(self.h, _ptr(host_vector)))
+
+    def set_async_output(self, enabled):
+        """results in host memory are copied back on the copy stream; valid after synchronize()"""
+        self._ck(self.L.nosh_ctx_set_async_output(self.h, int(bool(enabled))))
+
     def stats(self, prefix=""):
         buf = C.create_string_buffer(1 << 16)
         self._ck(self.L.nosh_ctx_list_stats(self.h, buf, len(buf)))

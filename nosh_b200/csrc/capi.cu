@@ -55,10 +55,25 @@ void require_mesh(Ctx *ctx) {
 // the landing buffer (krylov.cu:apply_halo_dev), so a device vector of the caller is used in place.
 bool ghost_room(const Ctx *ctx) { return ctx->nranks > 1 && !ctx->p2p.ok; }
 
+void ensure_copy_stream(Ctx *ctx) {
+  if (ctx->copy_stream) return;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
+  for (auto &pf : ctx->prefetch) CUDA_CHECK(cudaEventCreateWithFlags(&pf.ready, cudaEventDisableTiming));
+  for (auto &e : ctx->out_done) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+}
+
 double2 *stage_in(Ctx *ctx, const double *p, DBuf<double2> &buf, bool need_ghost_room) {
   if (!p && ctx->No > 0) NOSH_THROW(NOSH_EINVAL, "NULL vector");
   const bool dev = p && is_device_ptr(p);
   if (dev && !need_ghost_room) return (double2 *)p;
+  if (!dev && ctx->copy_stream)
+    for (auto &pf : ctx->prefetch)
+      if (pf.valid && pf.host == p) {  // already on its way (nosh_prefetch): wait for it instead of copying
+        pf.valid = false;
+        CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, pf.ready, 0));
+        return pf.dev.p;
+      }
   buf.ensure(ctx->Nl > 0 ? ctx->Nl : 1);
   if (ctx->No > 0)
     CUDA_CHECK(cudaMemcpyAsync(buf.p, p, sizeof(double2) * ctx->No, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
@@ -69,15 +84,27 @@ struct OutVec {
   double2 *dev;
   double *user;
   bool host;
+  int slot;
 };
 OutVec stage_out(Ctx *ctx, double *p, DBuf<double2> &buf) {
   if (!p && ctx->No > 0) NOSH_THROW(NOSH_EINVAL, "NULL vector");
   OutVec o;
   o.user = p;
   o.host = !p || !is_device_ptr(p);
+  o.slot = 0;
   if (o.host) {
-    buf.ensure(ctx->Nl > 0 ? ctx->Nl : 1);
-    o.dev = buf.p;
+    DBuf<double2> *b = &buf;
+    if (ctx->async_output && &buf == &ctx->stage_y) {
+      // the previous result may still be travelling to the host from the other buffer: alternate, and do not
+      // overwrite a buffer before its own copy has finished
+      ensure_copy_stream(ctx);
+      o.slot = ctx->out_flip;
+      ctx->out_flip ^= 1;
+      if (o.slot == 1) b = &ctx->stage_y2;
+      CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->out_done[o.slot], 0));
+    }
+    b->ensure(ctx->Nl > 0 ? ctx->Nl : 1);
+    o.dev = b->p;
   } else {
     o.dev = (double2 *)p;
   }
@@ -85,6 +112,14 @@ OutVec stage_out(Ctx *ctx, double *p, DBuf<double2> &buf) {
 }
 void finish_out(Ctx *ctx, const OutVec &o) {
   if (o.host && ctx->No > 0) {
+    if (ctx->async_output && ctx->copy_stream) {
+      // pipelined: the D2H rides on the copy stream behind the producing work; nosh_ctx_synchronize completes it
+      CUDA_CHECK(cudaEventRecord(ctx->ev_order, ctx->stream));
+      CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_order, 0));
+      CUDA_CHECK(cudaMemcpyAsync(o.user, o.dev, sizeof(double2) * ctx->No, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      CUDA_CHECK(cudaEventRecord(ctx->out_done[o.slot], ctx->copy_stream));
+      return;
+    }
     CUDA_CHECK(cudaMemcpyAsync(o.user, o.dev, sizeof(double2) * ctx->No, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   }
@@ -179,6 +214,13 @@ void nosh_ctx_destroy(nosh_ctx *ctx) {
   amg_free(ctx);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaEventDestroy(ctx->ev_order);
+    for (auto &pf : ctx->prefetch) cudaEventDestroy(pf.ready);
+    for (auto &e : ctx->out_done) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   cudaStream_t s = ctx->own_stream ? ctx->stream : nullptr;
   delete ctx;
   if (s) cudaStreamDestroy(s);
@@ -205,6 +247,39 @@ nosh_status nosh_ctx_set_group_vertices(nosh_ctx *ctx, int64_t g) {
 nosh_status nosh_ctx_synchronize(nosh_ctx *ctx) {
   API_BEGIN(ctx)
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->copy_stream) CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
+  API_END(ctx)
+}
+
+nosh_status nosh_prefetch(nosh_ctx *ctx, const double *host_vector) {
+  API_BEGIN(ctx)
+  require_mesh(ctx);
+  if (!host_vector) NOSH_THROW(NOSH_EINVAL, "NULL vector");
+  if (is_device_ptr(host_vector) || ctx->No == 0) return NOSH_OK;  // nothing to stage
+  ensure_copy_stream(ctx);
+  Ctx::Prefetch *slot = nullptr;
+  for (auto &pf : ctx->prefetch)
+    if (pf.valid && pf.host == host_vector) slot = &pf;  // refresh an entry that was never consumed
+  if (!slot) {
+    slot = &ctx->prefetch[ctx->prefetch_next];
+    ctx->prefetch_next = (ctx->prefetch_next + 1) % 4;
+  }
+  slot->dev.ensure(ctx->Nl > 0 ? ctx->Nl : 1);
+  // the buffer's last consumer was enqueued on the compute stream before this call: stay behind it
+  CUDA_CHECK(cudaEventRecord(ctx->ev_order, ctx->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_order, 0));
+  CUDA_CHECK(cudaMemcpyAsync(slot->dev.p, host_vector, sizeof(double2) * ctx->No, cudaMemcpyHostToDevice, ctx->copy_stream));
+  CUDA_CHECK(cudaEventRecord(slot->ready, ctx->copy_stream));
+  slot->host = host_vector;
+  slot->valid = true;
+  API_END(ctx)
+}
+
+nosh_status nosh_ctx_set_async_output(nosh_ctx *ctx, int enabled) {
+  API_BEGIN(ctx)
+  if (!enabled && ctx->copy_stream) CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
+  ctx->async_output = enabled != 0;
+  if (enabled) ensure_copy_stream(ctx);
   API_END(ctx)
 }
 

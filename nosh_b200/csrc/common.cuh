@@ -257,6 +257,20 @@ struct Ctx {
   DBuf<double2> work[14];
   DBuf<double2> scratch[8];
   DBuf<double2> stage_x, stage_y;   // host staging
+  // pipelined host I/O (capi.cu: nosh_prefetch / nosh_ctx_set_async_output): copies on their own stream
+  cudaStream_t copy_stream = nullptr;
+  struct Prefetch {
+    const double *host = nullptr;
+    DBuf<double2> dev;
+    cudaEvent_t ready = nullptr;
+    bool valid = false;
+  } prefetch[4];
+  int prefetch_next = 0;
+  cudaEvent_t ev_order = nullptr;   // orders the copy stream behind the compute stream
+  int async_output = 0;
+  DBuf<double2> stage_y2;           // second output staging buffer (async output alternates)
+  cudaEvent_t out_done[2] = {nullptr, nullptr};
+  int out_flip = 0;
   DBuf<double2> gmres_basis;        // (restart+1) x Nl Arnoldi vectors, allocated by the first nosh_gmres
   // ---- reductions ----
   DBuf<double> partials;            // 2 x n_chunks

@@ -720,3 +720,38 @@ def test_continuation_step_observer_writes_the_out_files(nb, orc, tmp_path):
     ctx.set_step_observer(None)
     assert len(ctx.continuation({"g": 1.0, "mu": 0.0}, "mu", 0.05, 1, psi.copy())) == 2 and rows == [0, 1, 2]
     ctx.close()
+
+
+def test_prefetch_and_async_output_give_the_same_bits(nb, orc):
+    """Pipelined host I/O: nosh_prefetch + asynchronous D2H produce exactly what the blocking calls produce."""
+    import torch
+    coords, cells = orc.meshgen.tetgrid(16)
+    ctx, P, psi = make_pair(nb, orc, coords, cells, 1)
+    par = {"g": 1.0, "mu": 0.3}
+    xs = [torch.from_numpy(orc.meshgen.random_state(P.N, 20 + k)).pin_memory() for k in range(3)]
+    bs = [torch.from_numpy(orc.meshgen.random_state(P.N, 30 + k)).pin_memory() for k in range(3)]
+    ref = []
+    for x, b in zip(xs, bs):
+        ctx.jac_rebuild(par, x.numpy())
+        sol, r = ctx.minres(b.numpy(), tol=1e-10, maxit=500)
+        ref.append((sol.copy(), r.iterations, ctx.compute_f(par, x.numpy()).copy()))
+    outs = [torch.empty_like(b).pin_memory() for b in bs]
+    fs = [torch.empty_like(b).pin_memory() for b in bs]
+    ctx.set_async_output(True)
+    ctx.prefetch(xs[0].numpy())
+    ctx.prefetch(bs[0].numpy())
+    its = []
+    for k in range(3):
+        ctx.jac_rebuild(par, xs[k].numpy())
+        if k + 1 < 3:
+            ctx.prefetch(xs[k + 1].numpy())
+            ctx.prefetch(bs[k + 1].numpy())
+        _, r = ctx.minres(bs[k].numpy(), outs[k].numpy(), tol=1e-10, maxit=500)
+        its.append(r.iterations)
+        ctx.compute_f(par, xs[k].numpy(), fs[k].numpy())      # not prefetched any more: plain staging, async result
+    ctx.synchronize()
+    ctx.set_async_output(False)
+    for k in range(3):
+        assert its[k] == ref[k][1]
+        assert np.array_equal(outs[k].numpy(), ref[k][0]) and np.array_equal(fs[k].numpy(), ref[k][2])
+    ctx.close()
