@@ -335,6 +335,7 @@ void gmres_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, doub
     if (No) GLAUNCH(ctx, k_scale_add, g1, 256, bscale, b, W, W, No);
     beta = norm2_of(W);
   }
+  if (p2p_check_error(ctx)) NOSH_THROW(NOSH_ECOMM, "peer-memory exchange timed out (a rank is not responding)");
   if (res) {
     res->iterations = iters;
     res->converged = converged;

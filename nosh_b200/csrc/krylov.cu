@@ -1244,6 +1244,7 @@ void cg_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, double2
     }
   }
   poll_done(ctx, &hs);
+  if (p2p_check_error(ctx)) NOSH_THROW(NOSH_ECOMM, "peer-memory reduction timed out (a rank is not responding)");
   if (res) {
     res->iterations = hs.iter;
     res->converged = hs.converged;

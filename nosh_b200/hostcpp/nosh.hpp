@@ -471,11 +471,50 @@ public:
   Teuchos::RCP<const Tpetra::Map<int, int>> getRangeMap() const override { return mesh_->complex_map(); }
   const std::shared_ptr<const nosh::mesh> &get_mesh() const { return mesh_; }
 
+  // ---- Tpetra::CrsMatrix row access (the reference's keo IS a CrsMatrix, src/parameter_matrix_keo.hpp:37).  The
+  // device stores complex blocks; a local row of the real 2N x 2N matrix is unfolded from them: block K_ij = a + ib
+  // contributes [a, -b] to row 2i and [b, a] to row 2i+1 at columns 2j, 2j+1 (src/parameter_matrix_keo.cpp:150-166).
+  // Column indices are LOCAL (owned vertices first, then ghosts); values are fetched from the device once per fill.
+  size_t getNodeNumRows() const { return 2 * (size_t)mesh_->info().n_owned; }
+  size_t getNumEntriesInLocalRow(int row) const {
+    fetch_blocks();
+    const int64_t i = row / 2;
+    return 2 * (size_t)(rowptr_[i + 1] - rowptr_[i]);
+  }
+  void getLocalRowCopy(int row, std::vector<int> &cols, std::vector<double> &vals, size_t &num) const {
+    fetch_blocks();
+    const int64_t i = row / 2;
+    const bool imag_row = row & 1;
+    num = 2 * (size_t)(rowptr_[i + 1] - rowptr_[i]);
+    cols.resize(num);
+    vals.resize(num);
+    size_t k = 0;
+    for (int64_t p = rowptr_[i]; p < rowptr_[i + 1]; p++, k += 2) {
+      const double a = bvals_[2 * p], b = bvals_[2 * p + 1];
+      cols[k] = 2 * bcols_[p];
+      cols[k + 1] = 2 * bcols_[p] + 1;
+      vals[k] = imag_row ? b : a;
+      vals[k + 1] = imag_row ? a : -b;
+    }
+  }
+
 protected:
+  void invalidate_rows() { rowptr_.clear(); }
+  void fetch_blocks() const {
+    if (!rowptr_.empty()) return;
+    const auto &mi = mesh_->info();
+    rowptr_.resize((size_t)mi.n_owned + 1);
+    bcols_.resize((size_t)mi.n_blocks);
+    bvals_.resize(2 * (size_t)mi.n_blocks);
+    check(mesh_->ctx(), nosh_get_block_csr(mesh_->ctx(), id_, rowptr_.data(), bcols_.data(), bvals_.data()));
+  }
   const std::shared_ptr<const nosh::mesh> mesh_;
   const std::shared_ptr<const nosh::scalar_field::base> thickness_;
   const std::shared_ptr<nosh::vector_field::base> mvp_;
   nosh_matrix_id id_;
+  mutable std::vector<int64_t> rowptr_;
+  mutable std::vector<int32_t> bcols_;
+  mutable std::vector<double> bvals_;
 };
 
 // src/parameter_matrix_keo.hpp:37-60
@@ -492,6 +531,7 @@ protected:
     mvp_->set_parameters(p);  // src/parameter_matrix_keo.cpp:88
     param_list pl(p);
     check(mesh_->ctx(), nosh_keo_fill(mesh_->ctx(), pl.size(), pl.names.data(), pl.values.data()));
+    invalidate_rows();
   }
 };
 
@@ -509,6 +549,7 @@ protected:
     mvp_->set_parameters(p);
     param_list pl(p);
     check(mesh_->ctx(), nosh_dkeo_fill(mesh_->ctx(), pl.size(), pl.names.data(), pl.values.data(), param_name_.c_str()));
+    invalidate_rows();
   }
   const std::string param_name_;
 };

@@ -8,6 +8,7 @@
 #include <sys/wait.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -107,6 +108,49 @@ static void run(const Fixture &fx) {
     keo.apply(w, Ku);
     REQUIRE_APPROX(std::fabs(u.dot(Ku)), 0.0, 0.0);  // Hermitian: e_r^T K e_i = 0
     REQUIRE_THROWS_AS(keo.set_parameters({{"nu", mu}}, {}), std::out_of_range);
+    // CrsMatrix row access: rows of the real matrix unfolded from the device's complex blocks.  y = K u recomputed
+    // from getLocalRowCopy equals apply(); on rectanglesmall the entries are the 8x8 matrix printed in
+    // test/keo.cpp:121-130 (diagonal 5.05; -4.99844 -+0.124987 on the long edges; -0.0499844 +-0.00124987 on the
+    // short ones; -2.0e-16 on the diagonal edge)
+    keo.set_parameters({{"mu", mu}}, {});
+    Tpetra::Vector<double, int, int> uu(map), Kuu(map);
+    for (size_t k = 0; k < map->getNodeNumElements(); k++) uu.replaceLocalValue(k, std::sin(1.0 + 0.7 * (double)k));
+    keo.apply(uu, Kuu);
+    double worst = 0.0, scale = 0.0, dmin = 1e300, dmax = 0.0;
+    std::vector<double> mags;
+    for (size_t r = 0; r < keo.getNodeNumRows(); r++) {
+      std::vector<int> cols;
+      std::vector<double> vals;
+      size_t num = 0;
+      keo.getLocalRowCopy((int)r, cols, vals, num);
+      REQUIRE_APPROX((double)num, (double)keo.getNumEntriesInLocalRow((int)r), 0.0);
+      double acc = 0.0;
+      for (size_t k = 0; k < num; k++) {
+        acc += vals[k] * uu[cols[k]];
+        if ((size_t)cols[k] == r) {
+          dmin = std::fmin(dmin, vals[k]);
+          dmax = std::fmax(dmax, vals[k]);
+        } else if (vals[k] != 0.0) {
+          mags.push_back(std::fabs(vals[k]));
+        }
+      }
+      worst = std::fmax(worst, std::fabs(acc - Kuu[r]));
+      scale = std::fmax(scale, std::fabs(Kuu[r]));
+    }
+    REQUIRE_APPROX(1.0 + worst / scale, 1.0, 1e-13);
+    if (fx.name == "rectanglesmall") {
+      REQUIRE_APPROX(dmin, 5.05, 1e-12);
+      REQUIRE_APPROX(dmax, 5.05, 1e-12);
+      std::sort(mags.begin(), mags.end());
+      REQUIRE_APPROX(mags.back(), 4.99844, 1e-5);             // |Re| on the long edges
+      int n_small = 0, n_mid = 0;
+      for (double m : mags) {
+        n_small += std::fabs(m - 0.00124987) < 1e-7;
+        n_mid += std::fabs(m - 0.124987) < 1e-6;
+      }
+      REQUIRE_APPROX((double)n_small, 8.0, 0.0);
+      REQUIRE_APPROX((double)n_mid, 8.0, 0.0);
+    }
   }
 
   nosh::model_evaluator::nls model(mesh, mvp, sp, 1.0, thickness, psi, "mu");
