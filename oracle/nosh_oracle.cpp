@@ -581,12 +581,22 @@ ORC_API int orc_keoreg_add_diag(int64_t nv, const int64_t *rowptr, const int32_t
 // Rows are statically partitioned over `nthreads` (one MPI rank per core with
 // Tpetra's serial node).
 // -----------------------------------------------------------------------------
+// g_row_reverse: sum every row right to left instead of left to right -- a rounding-level perturbation of the
+// operator apply (what a different column order in Tpetra's local graph, or the GPU's fused-multiply-add complex
+// arithmetic, amounts to), used to measure how sensitive the Krylov iteration counts are to it
+// (tests/golden/make_counts_golden.py).
+static int g_row_reverse = 0;
+ORC_API void orc_set_row_reverse(int on) { g_row_reverse = on != 0; }
 ORC_API void orc_csr_apply(int64_t nrows, const int64_t *rowptr, const int32_t *cols,
                            const double *vals, const double *x, double *y, int nthreads) {
+  const int rev = g_row_reverse;
 #pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
   for (int64_t i = 0; i < nrows; i++) {
     double s = 0.0;
-    for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++) s += vals[j] * x[cols[j]];
+    if (rev)
+      for (int64_t j = rowptr[i + 1] - 1; j >= rowptr[i]; j--) s += vals[j] * x[cols[j]];
+    else
+      for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++) s += vals[j] * x[cols[j]];
     y[i] = s;
   }
 }

@@ -85,6 +85,8 @@ def lib():
         L.orc_num_threads.restype = C.c_int
         L.orc_set_dot_parts.restype = None
         L.orc_set_dot_parts.argtypes = [C.c_int]
+        L.orc_set_row_reverse.restype = None
+        L.orc_set_row_reverse.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -97,6 +99,12 @@ def set_dot_parts(parts):
     """Split every dot product of the Krylov solvers into `parts` contiguous partial sums (the image of
     `parts` MPI ranks), independently of the number of threads; 0 = one part per thread (default)."""
     lib().orc_set_dot_parts(int(parts))
+
+
+def set_row_reverse(on):
+    """Sum every row of the sparse matrix-vector products right to left: a rounding-level perturbation of the
+    operator apply, to measure the sensitivity of iteration counts to it."""
+    lib().orc_set_row_reverse(int(bool(on)))
 
 
 def _ptr(a):
