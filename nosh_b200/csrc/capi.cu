@@ -198,6 +198,7 @@ nosh_status nosh_ctx_create(int device, void *stream, nosh_ctx **out) {
   if (const char *e = getenv("NOSH_B200_PERSISTENT_MINRES")) ctx->persistent_minres = atoi(e) != 0;
   if (const char *e = getenv("NOSH_B200_PERSISTENT_MGPU")) ctx->persistent_mgpu = atoi(e) != 0;
   if (const char *e = getenv("NOSH_B200_MGPU_FENCE")) ctx->mgpu_fence = atoi(e);
+  if (const char *e = getenv("NOSH_B200_MGPU_LEAN")) ctx->mgpu_lean = atoi(e) != 0;
   if (const char *e = getenv("NOSH_B200_AMG_GRAPH")) ctx->amg_graph = atoi(e) != 0;
   if (const char *e = getenv("NOSH_B200_AMG_PANEL_PRODUCTS"))
     if (atoll(e) > 0) ctx->amg_panel_products = atoll(e);
@@ -1145,6 +1146,8 @@ nosh_status nosh_ctx_set_tuning(nosh_ctx *ctx, const char *key, int value) {
     ctx->amg_valid = false;
   } else if (strcmp(key, "amg_graph") == 0) {
     ctx->amg_graph = value != 0;
+  } else if (strcmp(key, "mgpu_lean") == 0) {
+    ctx->mgpu_lean = value != 0;
   } else if (strcmp(key, "mgpu_fence") == 0) {
     ctx->mgpu_fence = value;
   } else if (strcmp(key, "sell_sigma") == 0) {

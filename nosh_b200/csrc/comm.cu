@@ -266,6 +266,31 @@ void halo_setup(Ctx *ctx) {
   if (ctx->n_send)
     CUDA_CHECK(cudaMemcpyAsync(ctx->send_idx.p, sidx.data(), sizeof(int32_t) * ctx->n_send, cudaMemcpyHostToDevice,
                                ctx->stream));
+  // the same list sorted by the 512-row chunk of the source vertex (stable), for kernels that push a chunk's
+  // boundary entries right after computing them (k_minres_persistent_mgpu, LEAN schedule)
+  {
+    const int64_t nch = cdiv(ctx->No, CHUNK);
+    std::vector<int32_t> cptr(nch + 1, 0), csrc(ctx->n_send > 0 ? ctx->n_send : 1), crank(csrc.size()), coff(csrc.size());
+    for (int64_t e = 0; e < ctx->n_send; e++) cptr[sidx[e] / CHUNK + 1]++;
+    for (int64_t c = 0; c < nch; c++) cptr[c + 1] += cptr[c];
+    std::vector<int32_t> fill(cptr.begin(), cptr.end() - 1);
+    for (int r = 0; r < P; r++)
+      for (int64_t e = ctx->send_off[r]; e < ctx->send_off[r + 1]; e++) {
+        const int32_t at = fill[sidx[e] / CHUNK]++;
+        csrc[at] = sidx[e];
+        crank[at] = r;
+        coff[at] = (int32_t)(e - ctx->send_off[r]);
+      }
+    ctx->csend_ptr.alloc(nch + 1);
+    ctx->csend_src.alloc(csrc.size());
+    ctx->csend_rank.alloc(csrc.size());
+    ctx->csend_off.alloc(csrc.size());
+    CUDA_CHECK(cudaMemcpyAsync(ctx->csend_ptr.p, cptr.data(), sizeof(int32_t) * (nch + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->csend_src.p, csrc.data(), sizeof(int32_t) * csrc.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->csend_rank.p, crank.data(), sizeof(int32_t) * csrc.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->csend_off.p, coff.data(), sizeof(int32_t) * csrc.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
   // interior / boundary chunk lists for the overlapped apply
   const int64_t nch = cdiv(ctx->No, CHUNK);
   if (nch > 0) {

@@ -174,6 +174,8 @@ struct Ctx {
   int persistent_mgpu = 1;          // multi-GPU persistent loop over peer memory (env NOSH_B200_PERSISTENT_MGPU=0 /
                                     // tuning key "persistent_mgpu" select the multi-launch loop)
   int persist_grid_mgpu = 0;
+  int mgpu_lean = 0;                // k_minres_persistent_mgpu: 1 = the two-grid-syncs-per-iteration schedule (krylov.cu;
+                                    // bit-identical, measured SLOWER: 1377 vs 1441 it/s on 2 B200), 0 = six syncs
   int mgpu_fence = 2;               // k_minres_persistent_mgpu: who fences system-wide after the halo push (krylov.cu)
   int persist_grid = 0;             // co-resident CTAs of that kernel (occupancy x SMs), computed once
   int apply_variant = 0;            // measurement knob: which k_apply_sell variant the MINRES loop uses (apply.cu)
@@ -290,6 +292,7 @@ struct Ctx {
   P2P p2p;
   // chunks (512 rows) whose rows reference no ghost column can be applied before the halo lands
   DBuf<int32_t> chunks_int, chunks_bnd;
+  DBuf<int32_t> csend_ptr, csend_src, csend_rank, csend_off;  // send list sorted by source chunk (comm.cu)
   DBuf<int32_t> chunks_all;         // interior chunks first, boundary chunks last (one launch, the last CTAs wait)
   int64_t n_chunks_int = 0, n_chunks_bnd = 0;
 };

@@ -478,6 +478,12 @@ struct PersistMgpuArgs {
   int64_t n_send;
   PushView push0, push1;  // targets when r_{h+1} lives in R0 / R1
   int fence_mode;
+  // LEAN schedule: the send list sorted by source chunk, so that the CTA that has just written a chunk of
+  // r_{h+1} pushes that chunk's boundary entries itself (no grid sync between phase B and the push)
+  const int32_t *csend_ptr;   // n_chunks + 1
+  const int32_t *csend_src;   // owned vertex
+  const int32_t *csend_rank;  // destination rank
+  const int32_t *csend_off;   // position in that rank's ghost block
 };
 
 __device__ __forceinline__ void persist_exchange(const PersistMgpuArgs &M, unsigned long long epoch) {
@@ -506,7 +512,16 @@ __device__ __forceinline__ void persist_exchange(const PersistMgpuArgs &M, unsig
   __threadfence_system();
 }
 
-template <int EPI>
+// LEAN (tuning key "mgpu_lean" = 1; NOT the default -- measured slower on 2 B200: 1377 vs 1441 MINRES it/s, twice):
+// two grid syncs per iteration instead of six.  After a phase only the chunk partials have to be
+// complete before CTA 0 may publish (one grid sync); CTA 0 then sums its rank's groups itself and stores them into
+// every rank's slot, and EVERY CTA waits for the ranks' flags on its own (local memory) instead of meeting at a
+// second grid-wide barrier; the halo entries of a chunk are pushed by the CTA that has just computed them.  Same
+// partials, same group sums (same lane runs, same xor tree), same level 3 => same bits as the other schedules
+// (mgpu_worker.py runs it).  Why it loses is not resolved: hiding the send-list latency and batching CTA 0's loads
+// changed nothing; the suspects left are 296 CTAs polling the flags next to the one CTA that works, and the
+// system-scope acquire fences in every CTA (the six-sync schedule fences system-wide in CTA 0 only).
+template <int EPI, bool LEAN>
 __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent_mgpu(const PersistMgpuArgs M) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
@@ -556,6 +571,72 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent_mgpu(const Persi
     }
     __syncthreads();
     return t;
+  };
+  // LEAN, CTA 0 only: level 2 of my groups straight into every rank's slot (own included), then the flags
+  auto publish = [&](unsigned long long ep) {
+    const P2PView &q = M.q;
+    const int slot = (int)(ep & 1ull);
+    const int per = (P.cpg + 31) / 32;
+    // four groups per warp and pass: their partials are loaded before any of them is reduced (the loads of one
+    // group alone are a chain of L2 latencies; CTA 0 is the only one working here)
+    for (int64_t g0 = (tid >> 5) * 4; g0 < M.n_groups_local; g0 += (CHUNK / 32) * 4) {
+      double s[4] = {0.0, 0.0, 0.0, 0.0};
+      if (per <= 8) {
+        double v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int t = 0; t < 8; t++) {
+            const int k = lane * per + t;
+            const int64_t at = (g0 + u) * P.cpg + k;
+            v[u][t] = (t < per && g0 + u < M.n_groups_local && k < P.cpg && at < P.n_chunks) ? __ldcg(P.partials + at) : 0.0;
+          }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+          for (int t = 0; t < 8; t++)
+            if (t < per) s[u] += v[u][t];
+      } else {
+        for (int u = 0; u < 4; u++)
+          for (int t = 0; t < per; t++) {
+            const int k = lane * per + t;
+            const int64_t at = (g0 + u) * P.cpg + k;
+            if (g0 + u < M.n_groups_local && k < P.cpg && at < P.n_chunks) s[u] += __ldcg(P.partials + at);
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const double t = warp_sum(s[u]);  // xor butterfly: every lane holds the sum
+        if (g0 + u < M.n_groups_local && lane < q.P) q.red[lane][slot * MAX_GROUPS + (int)(M.group_begin + g0 + u)] = t;
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < q.P) *((volatile unsigned long long *)&q.flags[tid][q.me]) = ep;
+  };
+  // LEAN, every CTA: wait until all ranks' sums (and, behind them, their halo pushes) have landed here.  Only
+  // CTA 0 watches the clock: on a time-out it raises the error flag and releases the other CTAs itself.
+  auto wait_all = [&](unsigned long long ep) {
+    const P2PView &q = M.q;
+    if (tid < q.P) {
+      volatile unsigned long long *mine = (volatile unsigned long long *)&q.flags[q.me][tid];
+      if (blockIdx.x == 0) {
+        const long long t0 = clock64();
+        while (*mine < ep) {
+          if (clock64() - t0 > q.timeout) {
+            *q.err = 1;
+            __threadfence();
+            *mine = ep;
+            break;
+          }
+        }
+      } else {
+        while (*mine < ep) {
+        }
+      }
+      __threadfence_system();  // acquire: the observers fence, the CTA barrier extends it to the other threads
+    }
+    __syncthreads();
   };
   for (int h = 1; h <= P.maxit; h++) {
     if (s_st.done) break;
@@ -608,12 +689,17 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent_mgpu(const Persi
       }
     }
     grid.sync();
-    level2();
-    grid.sync();
     epoch++;
-    if (blockIdx.x == 0) persist_exchange(M, epoch);
-    grid.sync();
-    if (__ldcg(M.q.err)) break;  // a peer timed out: every CTA sees the flag after the sync and leaves
+    if (LEAN) {
+      if (blockIdx.x == 0) publish(epoch);
+      wait_all(epoch);
+    } else {
+      level2();
+      grid.sync();
+      if (blockIdx.x == 0) persist_exchange(M, epoch);
+      grid.sync();
+    }
+    if (__ldcg(M.q.err)) break;  // a peer timed out: every CTA sees the flag after the wait and leaves
     {
       const double total = level3(epoch);
       if (tid == 0) {
@@ -627,6 +713,12 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent_mgpu(const Persi
       const double f = s_st.f_r2;
       for (int64_t chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
         const int64_t i = chunk * CHUNK + tid;
+        // LEAN: this chunk's range of the send list, loaded now so that its latency hides behind the row work
+        int e0 = 0, e1 = 0;
+        if (LEAN) {
+          e0 = __ldg(M.csend_ptr + chunk);
+          e1 = __ldg(M.csend_ptr + chunk + 1);
+        }
         double c = 0.0;
         if (i < P.A.No) {
           const double2 r = sub_scaled(P.Pv[i], f, rcur[i]);
@@ -646,9 +738,14 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent_mgpu(const Persi
           P.partials[chunk] = s;
         }
         __syncthreads();
+        if (LEAN) {  // this chunk's boundary entries of r_{h+1} (written above, visible after the barrier) go out now
+          for (int e = e0 + tid; e < e1; e += CHUNK)
+            push.dst[__ldg(M.csend_rank + e)][__ldg(M.csend_off + e)] = rprev[__ldg(M.csend_src + e)];
+        }
       }
     }
     grid.sync();
+    if (!LEAN) {
     level2();
     // halo push of r_{h+1}: my boundary entries into the neighbours' ghost segments over NVLink
     {
@@ -666,10 +763,16 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent_mgpu(const Persi
       if (M.fence_mode == 0 || (M.fence_mode == 1 && pushed)) __threadfence_system();
     }
     grid.sync();
+    }
     epoch++;
-    if (blockIdx.x == 0) persist_exchange(M, epoch);
-    grid.sync();
-    if (__ldcg(M.q.err)) break;  // a peer timed out: every CTA sees the flag after the sync and leaves
+    if (LEAN) {
+      if (blockIdx.x == 0) publish(epoch);  // CTA 0's system fence in there also covers the pushes (cumulativity)
+      wait_all(epoch);
+    } else {
+      if (blockIdx.x == 0) persist_exchange(M, epoch);
+      grid.sync();
+    }
+    if (__ldcg(M.q.err)) break;  // a peer timed out: every CTA sees the flag after the wait and leaves
     {
       const double total = level3(epoch);
       if (tid == 0) {
@@ -1030,7 +1133,7 @@ multi_launch:
     if (ctx->persist_grid_mgpu == 0) {
       int coop = 0, per_sm = 0, sms = 0;
       CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minres_persistent_mgpu<EPI_DIAG>, CHUNK, 0));
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minres_persistent_mgpu<EPI_DIAG, true>, CHUNK, 0));
       CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
       ctx->persist_grid_mgpu = (coop && per_sm > 0) ? per_sm * sms : -1;
     }
@@ -1061,14 +1164,21 @@ multi_launch:
       MA.send_idx = ctx->send_idx.p;
       MA.n_send = ctx->n_send;
       MA.fence_mode = ctx->mgpu_fence;
+      MA.csend_ptr = ctx->csend_ptr.p;
+      MA.csend_src = ctx->csend_src.p;
+      MA.csend_rank = ctx->csend_rank.p;
+      MA.csend_off = ctx->csend_off.p;
       for (int r = 0; r < ctx->nranks; r++) {
         MA.push0.dst[r] = ctx->p2p.R[0][r] + ctx->p2p.ghost_base[r];
         MA.push1.dst[r] = ctx->p2p.R[1][r] + ctx->p2p.ghost_base[r];
         MA.push0.off[r] = MA.push1.off[r] = ctx->send_off[r];
       }
       MA.push0.off[ctx->nranks] = MA.push1.off[ctx->nranks] = ctx->send_off[ctx->nranks];
-      const void *fn = epi == EPI_DIAG ? (const void *)k_minres_persistent_mgpu<EPI_DIAG>
-                                       : (const void *)k_minres_persistent_mgpu<EPI_NONE>;
+      const bool lean = ctx->mgpu_lean && ctx->csend_ptr.p;
+      const void *fn = epi == EPI_DIAG ? (lean ? (const void *)k_minres_persistent_mgpu<EPI_DIAG, true>
+                                               : (const void *)k_minres_persistent_mgpu<EPI_DIAG, false>)
+                                       : (lean ? (const void *)k_minres_persistent_mgpu<EPI_NONE, true>
+                                               : (const void *)k_minres_persistent_mgpu<EPI_NONE, false>);
       const unsigned pgrid = (unsigned)std::min<int64_t>(ctx->persist_grid_mgpu, ctx->n_chunks);
       void *kargs[] = {&MA};
       CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(pgrid), dim3(CHUNK), kargs, 0, ctx->stream));

@@ -144,8 +144,9 @@ def main():
         assert single.dot(x, y) == d
         xs, rs, hs = single.minres(b, tol=1e-10, maxit=3000, history=True)
         launches = {}
-        for persistent in (1, 0):
+        for persistent, lean in ((1, 0), (1, 1), (0, 0)):      # lean: the two-grid-syncs schedule of the persistent kernel
             ctx.set_tuning("persistent_mgpu", persistent)
+            ctx.set_tuning("mgpu_lean", lean)
             l0 = ctx.launch_count()
             xg, res, hg = ctx.minres(b[sl].copy(), tol=1e-10, maxit=3000, history=True)
             launches[persistent] = ctx.launch_count() - l0
@@ -162,6 +163,7 @@ def main():
             xk, rk = ctx.minres(b[sl].copy(), tol=1e-8, maxit=3000, op=nosh_b200.OP_KEO)
             xsk, rsk = single.minres(b, tol=1e-8, maxit=3000, op=nosh_b200.OP_KEO)
             assert rk.iterations == rsk.iterations and np.array_equal(xsk[sl], xk)
+        ctx.set_tuning("mgpu_lean", 0)
         if p2p:
             assert launches[1] <= 10 < launches[0], launches   # one cooperative launch per solve and rank
         summary["minres"] = ito
