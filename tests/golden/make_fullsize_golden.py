@@ -53,6 +53,21 @@ for name, s in (("one", one), ("er", er), ("ei", ei), ("x", x)):
     out["jac_%s" % name] = float(s @ P.jac_apply(s))
 P.dkeo_fill(mu, 0.0, "mu")
 out["dfdmu_norm2"] = float(np.linalg.norm(P.compute_dfdp(x, False, np.zeros(N))))
+# entry-level evidence at full size: the values of K x, F(x), J y and dF/dmu at 4096 strided vertices (both
+# components) -- each depends on the ~15 matrix blocks of its row, so a single wrong entry anywhere in those rows
+# shows up here, which the norms above would average away
+stride = max(1, N // 4096)
+rows = np.arange(0, N, stride)[:4096]
+idx = np.stack([2 * rows, 2 * rows + 1], 1).ravel()
+y = meshgen.random_state(N, 43)
+jy = P.jac_apply(y)
+dfdmu = P.compute_dfdp(x, False, np.zeros(N))
+out["sample_rows"] = {"stride": int(stride), "count": int(rows.size),
+                      "Kx": [float(v) for v in kx[idx]], "Kx_max": float(np.abs(kx).max()),
+                      "Fx": [float(v) for v in Fx[idx]], "Fx_max": float(np.abs(Fx).max()),
+                      "Jy": [float(v) for v in jy[idx]], "Jy_max": float(np.abs(jy).max()),
+                      "dFdmu": [float(v) for v in dfdmu[idx]], "dFdmu_max": float(np.abs(dfdmu).max()),
+                      "note": "x = random_state(N, 42) (also the state J is built at), y = random_state(N, 43)"}
 out["seconds"] = time.time() - t0
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fullsize_n%d.json" % n)
 json.dump(out, open(path, "w"), indent=1)

@@ -35,7 +35,7 @@ def test_reference_arm_on_the_gpu_box_ran_the_b200_arms_mesh():
     """like for like: the committed reference-arm line (16 host cores of the GPU box) and the committed B200 line
     carry the same config object"""
     ref = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_reference_arm_n200_gpubox.json")))
-    gpu = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_default_1gpu_v2.json")))
+    gpu = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_default_1gpu_v3.json")))
     assert ref["impl"] == "reference" and ref["config"] == gpu["config"]
     assert ref["cpu_baseline"]["cores"] >= 8 and ref["value"] > 0
     assert gpu["e2e"]["value"] / ref["value"] > 50
@@ -58,7 +58,7 @@ def test_rank_other_than_zero_of_the_reference_arm_does_no_work():
 
 
 def test_committed_b200_line_has_every_contract_key():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_default_1gpu_v2.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_default_1gpu_v3.json")))
     for k in BASE_KEYS + ["roofline", "cpu_baseline", "gpu_launches", "clocks", "parity"]:
         assert k in d, k
     # the parity gate ran before anything was timed: entry-wise KEO / F / J x / dF/dmu at 1.0M vertices <= 1e-12
