@@ -393,7 +393,8 @@ typedef struct {
  * observer::observeSolution (src/observer.cpp:134-159: the CSV row): called by both continuation drivers after every
  * accepted step with the step index, the parameter value, the Gibbs energy and scaled norm of the CSV, and the
  * solution -- this rank's owned entries, interleaved (re,im), in HOST memory valid during the call.  A non-zero
- * return stops the continuation (the steps so far are returned).  NULL removes the observer. */
+ * return stops the continuation (the steps so far are returned; with several ranks every rank's observer is
+ * called and all must return the same decision).  NULL removes the observer. */
 typedef int (*nosh_step_observer_fn)(void *user, int step, double param, double gibbs_energy, double norm,
                                      const double *psi_host, int64_t n_doubles);
 NOSH_API nosh_status nosh_ctx_set_step_observer(nosh_ctx *ctx, nosh_step_observer_fn fn, void *user);
