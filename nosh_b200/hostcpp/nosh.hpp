@@ -20,6 +20,8 @@
 //  * the Thyra InArgs/OutArgs protocol is reduced to plain structs with the same members
 #pragma once
 #include <algorithm>
+#include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <functional>
 #include <set>
@@ -896,6 +898,20 @@ public:
   }
   const std::shared_ptr<const nosh::mesh> mesh() const { return mesh_; }
 
+  // model_evaluator::base scalars (src/model_evaluator_base.hpp:50-60, src/model_evaluator_nls.cpp:699-770): what the
+  // reference's commented code states (its live code returns 0.0); partition independent
+  double inner_product(const Tpetra::Vector<double, int, int> &phi, const Tpetra::Vector<double, int, int> &psi) const {
+    double r = 0.0;
+    check(mesh_->ctx(), nosh_inner_product(mesh_->ctx(), phi.getData(), psi.getData(), &r));
+    return r;
+  }
+  double norm(const Tpetra::Vector<double, int, int> &psi) const { return std::sqrt(inner_product(psi, psi)); }
+  double gibbs_energy(const Tpetra::Vector<double, int, int> &psi) const {
+    double r = 0.0;
+    check(mesh_->ctx(), nosh_gibbs_energy(mesh_->ctx(), psi.getData(), &r));
+    return r;
+  }
+
   // evalModelImpl (:392-525)
   void evalModel(const InArgs &in, const OutArgs &out) const {
     double alpha = in.alpha, beta = in.beta;
@@ -939,4 +955,108 @@ private:
   std::vector<double> p_init_;
 };
 }  // namespace model_evaluator
+
+// ---------------------------------------------------------------------------------------------
+// src/observer.hpp / src/continuation_data_saver.hpp: what Piro/LOCA call after every continuation step -- a CSV row
+// "(0) step,(1) <param>,(2) Gibbs energy,(2) ||x||_2 scaled" and an outNNNN dump of the state -- and the entry
+// point that drives them: nosh-cont's LOCA run (executables/nosh-cont/nosh-cont.cpp:206-344, examples/conf.xml:35-75:
+// "Arc Length" stepper, "Tangent" predictor, adaptive step size) on the device drivers.
+// ---------------------------------------------------------------------------------------------
+class continuation_data_saver {
+public:
+  explicit continuation_data_saver(const std::shared_ptr<nosh::mesh> &mesh, std::string prefix = "out")
+      : mesh_(mesh), prefix_(std::move(prefix)), index_(0) {}
+  void saveSolution(const Tpetra::Vector<double, int, int> &x, double /*p*/) {
+    char name[32];
+    std::snprintf(name, sizeof(name), "%04zu.vtk", index_);
+    mesh_->write(prefix_ + name, &x);
+    index_++;
+  }
+  size_t count() const { return index_; }
+
+private:
+  const std::shared_ptr<nosh::mesh> mesh_;
+  const std::string prefix_;
+  size_t index_;
+};
+
+class observer {
+public:
+  observer(const std::shared_ptr<const nosh::model_evaluator::nls> &model_eval, const std::string &csv_filename = "",
+           const std::string &cont_param_name = "")
+      : model_eval_(model_eval), csv_(csv_filename.empty() ? nullptr : std::fopen(csv_filename.c_str(), "w")),
+        cont_param_name_(cont_param_name), index_(0) {}
+  ~observer() {
+    if (csv_) std::fclose(csv_);
+  }
+  observer(const observer &) = delete;
+  // src/observer.cpp:134-159 (save_continuation_statistics_)
+  void observeSolution(const Tpetra::Vector<double, int, int> &soln, double param_val) {
+    if (!csv_) return;
+    if (index_ == 0) std::fprintf(csv_, "(0) step,(1) %s,(2) Gibbs energy,(2) ||x||_2 scaled\n", cont_param_name_.c_str());
+    std::fprintf(csv_, "%d,%.15e,%.15e,%.15e\n", index_, param_val, model_eval_->gibbs_energy(soln), model_eval_->norm(soln));
+    std::fflush(csv_);
+    index_++;
+  }
+
+private:
+  const std::shared_ptr<const nosh::model_evaluator::nls> model_eval_;
+  std::FILE *csv_;
+  const std::string cont_param_name_;
+  int index_;
+};
+
+struct continuation_options {  // examples/conf.xml:35-75
+  double initial_value = 0.0, min_value = -100.0, max_value = 100.0;
+  double initial_step_size = 1.0e-3, min_step_size = 1.0e-7, max_step_size = 1.0e-2, aggressiveness = 2.0;
+  int max_steps = 10, max_nonlinear_iterations = 20, max_linear_iterations = 1000;
+  double nonlinear_tolerance = 1.0e-8, linear_tolerance = 1.0e-10;
+};
+// Arc-length continuation in `param_name` from the state x (updated in place); the other parameters keep the values
+// in `params`.  observer / saver (either may be null) see every accepted step.  Returns the step records.
+inline std::vector<nosh_arclength_step> continuation(const std::shared_ptr<const nosh::model_evaluator::nls> &model,
+                                                     std::map<std::string, double> params, const std::string &param_name,
+                                                     Tpetra::Vector<double, int, int> &x, const continuation_options &o,
+                                                     nosh::observer *obs = nullptr, nosh::continuation_data_saver *saver = nullptr) {
+  params[param_name] = o.initial_value;
+  param_list pl(params);
+  nosh_arclength_options opt;
+  opt.initial_step_size = o.initial_step_size;
+  opt.min_step_size = o.min_step_size;
+  opt.max_step_size = o.max_step_size;
+  opt.aggressiveness = o.aggressiveness;
+  opt.max_steps = o.max_steps;
+  opt.nl_maxit = o.max_nonlinear_iterations;
+  opt.nl_tol = o.nonlinear_tolerance;
+  opt.lin_tol = o.linear_tolerance;
+  opt.lin_maxit = o.max_linear_iterations;
+  opt.reserved = 0;
+  opt.min_value = o.min_value;
+  opt.max_value = o.max_value;
+  struct hook {
+    nosh::observer *obs;
+    nosh::continuation_data_saver *saver;
+    std::shared_ptr<const Tpetra::Map<int, int>> map;
+  } h{obs, saver, model->mesh()->complex_map()};
+  nosh_ctx *c = model->mesh()->ctx();
+  check(c, nosh_ctx_set_step_observer(
+               c,
+               [](void *user, int, double param, double, double, const double *psi, int64_t n) -> int {
+                 auto *hk = static_cast<hook *>(user);
+                 Tpetra::Vector<double, int, int> v(hk->map);
+                 std::copy(psi, psi + n, v.getDataNonConst());
+                 if (hk->saver) hk->saver->saveSolution(v, param);
+                 if (hk->obs) hk->obs->observeSolution(v, param);
+                 return 0;
+               },
+               &h));
+  std::vector<nosh_arclength_step> steps((size_t)o.max_steps + 1);
+  int n = 0;
+  const nosh_status st = nosh_continuation_arclength(c, pl.size(), pl.names.data(), pl.values.data(), param_name.c_str(), &opt,
+                                                     x.getDataNonConst(), steps.data(), &n);
+  nosh_ctx_set_step_observer(c, nullptr, nullptr);
+  check(c, st);
+  steps.resize((size_t)n);
+  return steps;
+}
 }  // namespace nosh

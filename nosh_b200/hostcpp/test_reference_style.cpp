@@ -556,6 +556,66 @@ static void run_poisson() {
   std::printf("poisson: %d CG iterations, max |u| = %.3f, done\n", st.iterations, scale);
 }
 
+// ---- nosh-cont (executables/nosh-cont/nosh-cont.cpp:206-344): arc-length continuation in mu with the observer's CSV
+// and the outNNNN dumps, on a mesh read from a file ----
+static void run_continuation() {
+  // a small tetrahedral box written as a VTK file with the plain-gl tags, then read back like nosh-cont does
+  auto gen = std::make_shared<nosh::mesh>(7, 7, 7, 0.1);
+  const auto &xc = gen->local_coords();
+  const size_t N = gen->info().n_owned;
+  std::vector<int32_t> cells((size_t)gen->info().n_cells * 4);
+  nosh::check(gen->ctx(), nosh_mesh_get_cells(gen->ctx(), cells.data()));
+  std::vector<double> psi(2 * N, 0.0), A(3 * N, 0.0), V(N, -1.0);
+  for (size_t k = 0; k < N; k++) {
+    psi[2 * k] = 1.0;
+    A[3 * k] = -0.5 * xc[3 * k + 1];
+    A[3 * k + 1] = 0.5 * xc[3 * k];
+  }
+  const char *names[3] = {"psi", "A", "V"};
+  const int32_t ncomps[3] = {2, 3, 1};
+  const double *vals[3] = {psi.data(), A.data(), V.data()};
+  const std::string path = "/tmp/nosh_b200_cont_box.vtk";
+  g_checks++;
+  if (nosh_meshfile_write(path.c_str(), 3, (int64_t)N, xc.data(), (int64_t)cells.size() / 4, cells.data(), 3, names, ncomps,
+                          vals, 1) != NOSH_OK) {
+    std::printf("FAIL write %s\n", path.c_str());
+    g_fail++;
+    return;
+  }
+  auto mesh = nosh::read(path);
+  auto mvp = std::make_shared<nosh::vector_field::explicit_values>(*mesh, "A", 0.0);
+  auto thickness = std::make_shared<nosh::scalar_field::constant>(*mesh, 1.0);
+  auto sp = std::make_shared<nosh::scalar_field::explicit_values>(*mesh, "V");
+  auto x = mesh->get_complex_vector("psi");
+  auto model = std::make_shared<const nosh::model_evaluator::nls>(mesh, mvp, sp, 1.0, thickness, x, "mu");
+  nosh::observer obs(model, "/tmp/nosh_b200_continuationData.dat", "mu");
+  nosh::continuation_data_saver saver(mesh, "/tmp/nosh_b200_out");
+  nosh::continuation_options opt;
+  opt.initial_step_size = 0.05;
+  opt.max_step_size = 0.1;
+  opt.max_steps = 3;
+  auto steps = nosh::continuation(model, {{"g", 1.0}, {"mu", 0.0}, {"beta", 1.0}}, "mu", *x, opt, &obs, &saver);
+  REQUIRE_APPROX((double)steps.size(), 4.0, 0.0);
+  REQUIRE_APPROX((double)saver.count(), 4.0, 0.0);
+  for (const auto &st : steps) REQUIRE_APPROX((double)st.converged, 1.0, 0.0);
+  g_checks++;
+  if (!(steps.back().param > steps.front().param)) { std::printf("FAIL continuation did not advance mu\n"); g_fail++; }
+  // the CSV has a header and one row per step; the last dump holds the returned state
+  int lines = 0;
+  if (std::FILE *f = std::fopen("/tmp/nosh_b200_continuationData.dat", "r")) {
+    for (int ch; (ch = std::fgetc(f)) != EOF;) lines += ch == '\n';
+    std::fclose(f);
+  }
+  REQUIRE_APPROX((double)lines, 5.0, 0.0);
+  auto back = nosh::read("/tmp/nosh_b200_out0003.vtk")->get_complex_vector("psi");
+  double worst = 0.0;
+  for (size_t k = 0; k < 2 * N; k++) worst = std::fmax(worst, std::fabs((*back)[k] - (*x)[k]));
+  REQUIRE_APPROX(1.0 + worst, 1.0, 1e-15);
+  REQUIRE_APPROX(model->gibbs_energy(*x), steps.back().gibbs_energy, 1e-14);
+  std::printf("continuation: mu = %.4f after %zu steps, Gibbs energy %.6f, done\n", steps.back().param, steps.size() - 1,
+              steps.back().gibbs_energy);
+}
+
 int main() {
   std::fflush(stdout);
   for (int P : {2, 3}) {
@@ -572,6 +632,7 @@ int main() {
     run_io(rectanglesmall(), 0.25, 2.5);
     run_io(cubesmall(), 0.25, 0.25);
     run_poisson();
+    run_continuation();
   } catch (const std::exception &e) {
     std::printf("FAIL uncaught exception: %s\n", e.what());
     return 2;
