@@ -97,3 +97,15 @@ def test_b200_arm_fails_loudly_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and r.stdout.strip() == ""
+
+
+def test_count_rule_of_the_parity_gate():
+    """bench.count_close: the GPU count must lie in the oracle's interval widened by max(2, 3 x its own spread)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.count_close(530, [533, 533, 532, 532])            # measured at 1.0M vertices: slack 3
+    assert bench.count_close(191, [191, 191]) and bench.count_close(193, [191, 191])
+    assert not bench.count_close(194, [191, 191])
+    assert bench.count_close(1369, [1431, 1415, 1414]) and not bench.count_close(1300, [1431, 1415, 1414])
