@@ -47,13 +47,71 @@ inline dim3 grid_for(int64_t n, int tpb = 256) { return dim3((unsigned)cdiv(n > 
     CUDA_CHECK(cudaGetLastError());                              \
   } while (0)
 
-// Set-up temporaries come from the device's stream-ordered memory pool: the expand-sort-compress products
-// allocate and free tens of GB in many pieces, and cudaMalloc / cudaFree map and unmap every one of them
-// (measured: the same set-up took 0.4 ... 7.6 s depending on the allocator's mood).  With the pool's
-// release threshold raised for the duration of the set-up, freed blocks are reused without unmapping;
-// the pool is trimmed again when the hierarchy is complete.  Persistent level data stays in cudaMalloc'ed
-// DBufs.
-thread_local cudaStream_t g_tstream = nullptr;
+// Set-up temporaries come from ONE cudaMalloc'ed arena with a first-fit sub-allocator.  The expand-sort-compress
+// products allocate and free hundreds of buffers; cudaMalloc / cudaFree per buffer cost milliseconds each (cudaFree
+// synchronises), and the stream-ordered pool (cudaMallocAsync) -- used in round 1 -- grows through the virtual-
+// memory API, which on this pool's VMs takes 0.05 ... 1.7 s for 8 GB (profiles/r2_alloc_probe.jsonl: cudaMalloc of
+// the same 8.6 GB: 1 - 7 ms, every time).  All work is on one stream, so a block handed back by one temporary may
+// be given to the next at once: the kernels that used it were enqueued earlier (the ordering cudaFreeAsync gives).
+// A request the arena cannot serve falls back to cudaMalloc / cudaFree.
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0;
+  struct Blk {
+    size_t off, size;
+    bool free;
+  };
+  std::vector<Blk> blocks;  // by offset
+  size_t high = 0, used = 0;
+  void init(size_t bytes) {
+    if (cudaMalloc(&base, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      base = nullptr;
+      bytes = 0;
+    }
+    cap = bytes;
+    blocks.assign(1, Blk{0, bytes, true});
+  }
+  void *alloc(size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    for (size_t i = 0; i < blocks.size(); i++)
+      if (blocks[i].free && blocks[i].size >= bytes) {
+        if (blocks[i].size > bytes) blocks.insert(blocks.begin() + i + 1, Blk{blocks[i].off + bytes, blocks[i].size - bytes, true});
+        blocks[i].size = bytes;
+        blocks[i].free = false;
+        used += bytes;
+        high = std::max(high, used);
+        return base + blocks[i].off;
+      }
+    return nullptr;
+  }
+  bool owns(const void *p) const { return base && (const char *)p >= base && (const char *)p < base + cap; }
+  void release(void *p) {
+    const size_t off = (size_t)((char *)p - base);
+    for (size_t i = 0; i < blocks.size(); i++)
+      if (blocks[i].off == off && !blocks[i].free) {
+        blocks[i].free = true;
+        used -= blocks[i].size;
+        if (i + 1 < blocks.size() && blocks[i + 1].free) {
+          blocks[i].size += blocks[i + 1].size;
+          blocks.erase(blocks.begin() + i + 1);
+        }
+        if (i > 0 && blocks[i - 1].free) {
+          blocks[i - 1].size += blocks[i].size;
+          blocks.erase(blocks.begin() + i);
+        }
+        return;
+      }
+  }
+  void destroy() {
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = 0;
+    blocks.clear();
+  }
+};
+thread_local Arena *g_arena = nullptr;
+thread_local size_t g_fallback_bytes = 0;
 template <typename T>
 struct TBuf {
   T *p = nullptr;
@@ -63,14 +121,21 @@ struct TBuf {
   TBuf &operator=(const TBuf &) = delete;
   ~TBuf() { release(); }
   void release() {
-    if (p) cudaFreeAsync(p, g_tstream);
+    if (p) {
+      if (g_arena && g_arena->owns(p)) g_arena->release(p);
+      else cudaFree(p);
+    }
     p = nullptr;
     n = 0;
   }
   void alloc(size_t count) {
     release();
     if (count == 0) count = 1;
-    CUDA_CHECK(cudaMallocAsync(&p, count * sizeof(T), g_tstream));
+    p = g_arena ? (T *)g_arena->alloc(count * sizeof(T)) : nullptr;
+    if (!p) {
+      CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+      g_fallback_bytes += count * sizeof(T);
+    }
     n = count;
   }
   void ensure(size_t count) {
@@ -470,8 +535,7 @@ void sort_compress(Ctx *ctx, Temp &tmp, TBuf<uint64_t> &keys, TBuf<uint32_t> &id
 
 // Expand (already counted) -> sort -> compress, in ROW PANELS of at most ~panel_products products each: the
 // temporaries of one panel (44 B per product + the sort's double buffers) are reused by the next, so a product
-// with 460M terms (A P on 8M vertices) maps ~4 GB of pool memory instead of ~29 GB -- first-touch mapping of the
-// temporaries was what made the set-up take 0.35 ... 2.7 s depending on the box.  rows_disjoint: every output row
+// with 460M terms (A P on 8M vertices) needs ~4 GB of the temporaries' arena instead of ~29 GB.  rows_disjoint: every output row
 // is produced by one panel only (C = A B): the panels' results are simply concatenated, bit-identical to one
 // panel.  Otherwise (C = A^T B) the compressed panels are merged by one more, small, sort-compress pass.
 template <typename ExpandFn>
@@ -1082,48 +1146,33 @@ void build_hierarchy(Ctx *ctx) {
   amg_free(ctx);
   Amg *H = new Amg();
   ctx->amg = H;
-  // stream-ordered pool for the temporaries (see TBuf): keep freed blocks mapped until the set-up is done
-  g_tstream = ctx->stream;
-  cudaMemPool_t pool = nullptr;
-  CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
-  uint64_t keep_all = UINT64_MAX, keep_none = 0;
-  CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
-  struct PoolGuard {
-    cudaMemPool_t pool;
-    cudaStream_t stream;
-    uint64_t *zero;
-    ~PoolGuard() {
-      cudaStreamSynchronize(stream);
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, zero);
-      cudaMemPoolTrimTo(pool, 0);
-    }
-  } pool_guard{pool, ctx->stream, &keep_none};
-  // Grow the pool ONCE, up front, to what one panel of the expand-sort-compress products plus the compressed
-  // results need (esc_finish).  First-touch mapping of pool memory costs 6 ... 45 ms per GB depending on the box
-  // (measured: 23.8 GB in 0.13 s on one box, 1.06 s on another), which is what made the un-panelled set-up
-  // (~29 GB of temporaries for A P on 8M vertices) take 0.35 ... 2.7 s.  One allocation, freed straight back into
-  // the pool (release threshold = keep everything), maps the memory in one step.
+  // the arena for the temporaries (see TBuf): one panel of the expand-sort-compress products (32M products x ~112 B)
+  // plus the compressed results of the largest product (~20 B per level-0 block measured; 40 reserved)
+  Arena arena;
   {
     size_t free_b = 0, total_b = 0;
     CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    // one panel of the expand-sort-compress products (32M products x ~80 B) + the compressed results
-    size_t want = std::min<size_t>((size_t)ctx->nb * 200, ((size_t)3 << 30) + (size_t)ctx->nb * 40);
-    if (const char *e = getenv("NOSH_B200_AMG_PREGROW_MB")) want = (size_t)atoll(e) << 20;
+    size_t want = ((size_t)4 << 30) + (size_t)ctx->nb * 40;  // measured high-water mark at 8M vertices: 6.1 GB
+    want = std::min(want, (size_t)ctx->nb * 400 + ((size_t)64 << 20));  // small problems: a few hundred bytes per block
+    if (const char *e = getenv("NOSH_B200_AMG_ARENA_MB")) want = (size_t)atoll(e) << 20;
     want = std::min(want, free_b / 2);
-    if (want >= ((size_t)64 << 20)) {
-      const auto tg = std::chrono::steady_clock::now();
-      void *p = nullptr;
-      if (cudaMallocAsync(&p, want, ctx->stream) == cudaSuccess) {
-        cudaFreeAsync(p, ctx->stream);
-        cudaStreamSynchronize(ctx->stream);
-      } else {
-        cudaGetLastError();
-      }
-      ctx->stats["amg.pool_pregrow_s"] = std::chrono::duration<double>(std::chrono::steady_clock::now() - tg).count();
-      ctx->stats["amg.pool_pregrow_bytes"] = (double)want;
-      tick("pool pre-grow", 0);
-    }
+    arena.init(want);
+    ctx->stats["amg.arena_bytes"] = (double)arena.cap;
   }
+  g_arena = &arena;
+  g_fallback_bytes = 0;
+  struct ArenaGuard {  // declared before every temporary: destroyed after all of them
+    Arena *a;
+    Ctx *ctx;
+    ~ArenaGuard() {
+      cudaStreamSynchronize(ctx->stream);
+      ctx->stats["amg.arena_high_bytes"] = (double)a->high;
+      ctx->stats["amg.arena_fallback_bytes"] = (double)g_fallback_bytes;
+      g_arena = nullptr;
+      a->destroy();
+    }
+  } arena_guard{&arena, ctx};
+  tick("arena", 0);
   Temp tmp;
   DBuf<double> scratch;
   const int64_t No = ctx->No;

@@ -1,5 +1,5 @@
 """AMG hierarchy set-up time in a FRESH process (the driver's `hierarchy_setup_seconds`): tetgrid n, psi = 1.
-NOSH_B200_AMG_TIMING=1 prints the phases; NOSH_B200_AMG_PREGROW_MB=0 switches the one-shot pool growth off.
+NOSH_B200_AMG_TIMING=1 prints the phases; NOSH_B200_AMG_ARENA_MB sets the size of the temporaries' arena.
     python profiles/amg_setup_probe.py [n]"""
 import json
 import os
@@ -29,9 +29,9 @@ ctx.amg_setup()
 ctx.synchronize()
 wall = time.perf_counter() - t0
 ai = ctx.amg_info()
-out = {"n": n, "setup_seconds": float(ai.setup_seconds), "wall_seconds_incl_pool_trim": wall,
-       "pregrow_mb_env": os.environ.get("NOSH_B200_AMG_PREGROW_MB"), "levels": int(ai.levels)}
-for k in ("amg.pool_pregrow_s", "amg.pool_pregrow_bytes"):
+out = {"n": n, "setup_seconds": float(ai.setup_seconds), "wall_seconds": wall,
+       "arena_mb_env": os.environ.get("NOSH_B200_AMG_ARENA_MB"), "levels": int(ai.levels)}
+for k in ("amg.arena_bytes", "amg.arena_high_bytes", "amg.arena_fallback_bytes", "amg.setup.arena"):
     try:
         out[k] = ctx.stat(k)
     except KeyError:
