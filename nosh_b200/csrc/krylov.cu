@@ -1018,11 +1018,15 @@ void apply_halo_dev(Ctx *ctx, int epi, int fuse, ApplyArgs &A, double2 *x) {
 }
 
 // y = op(x) with the plain/diag epilogues.  nranks > 1 without peer memory: x must have Nl entries.
-void apply_op_dev(Ctx *ctx, int op, double2 *x, double2 *y) {
+void apply_op_dev(Ctx *ctx, int op, double2 *x, double2 *y) { apply_op_gated_dev(ctx, op, x, y, nullptr); }
+// ... as a no-op once gate->done is set (solvers whose control flow lives on the device; every rank sees the same
+// flag, so a skipped launch skips its halo push on all of them)
+void apply_op_gated_dev(Ctx *ctx, int op, double2 *x, double2 *y, const KrylovState *gate) {
   ensure_work(ctx);
   ApplyArgs A = base_args(ctx, nullptr, x, y);
   int epi;
   op_args(ctx, op, A, &epi);
+  A.gate = gate;
   apply_halo_dev(ctx, epi, FUSE_NONE, A, x);
 }
 

@@ -12,6 +12,7 @@ void jac_diags_dev(Ctx *ctx, double g, const double2 *psi);
 void keoreg_diags_dev(Ctx *ctx, double g, const double2 *psi);
 void axpy_dev(Ctx *ctx, double a, const double2 *x, double2 *y);
 void apply_op_dev(Ctx *ctx, int op, double2 *x, double2 *y);
+void apply_op_gated_dev(Ctx *ctx, int op, double2 *x, double2 *y, const KrylovState *gate);
 void compute_f_dev(Ctx *ctx, double g, double2 *psi, double2 *f);
 void minres_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, double2 *x_out, double tol, int maxit,
                 nosh_krylov_result *res, double *hist_host);
