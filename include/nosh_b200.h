@@ -410,7 +410,7 @@ NOSH_API nosh_status nosh_continuation(nosh_ctx *ctx, int np, const char *const 
  * constraint <xdot, x - x0>/len + pdot (p - p0) = ds with LOCA's scaled dot product (Euclidean / vector
  * length, parameter scaling 1), Newton on the bordered system by two MINRES solves with the same
  * Jacobian (J a = -F, J b = -dF/dp), tangent J t = -dF/dp after every accepted step.
- * steps: max_steps+1 records (step 0 = the solution at the initial parameter value);
+ * steps: max_steps+1 records (step 0 = the solution at the initial parameter value; +1 with NOSH_ARC_HIT_BOUND);
  * *n_records = number written.  Follows the branch through turning points, where the natural
  * continuation of nosh_continuation fails. */
 typedef struct {
@@ -422,9 +422,20 @@ typedef struct {
   double nl_tol;   /* on sqrt(||F||^2 + g^2) */
   double lin_tol;
   int32_t lin_maxit;
-  int32_t reserved;
+  int32_t flags;               /* NOSH_ARC_SCALING | NOSH_ARC_HIT_BOUND; 0: neither */
   double min_value, max_value; /* stop once the parameter leaves [min_value, max_value] */
+  /* NOSH_ARC_SCALING (LOCA "Enable Arc Length Scaling", its default): 0 selects LOCA's defaults 0.5, 0.8, 1e-3, 1 */
+  double goal_contribution, max_contribution, min_scale, initial_scale;
 } nosh_arclength_options;
+/* flags: the two LOCA stepper defaults nosh-cont inherits (examples/conf.xml sets neither).
+ * NOSH_ARC_SCALING: the parameter enters the arc length as s*p; s is reset whenever the parameter's share of the
+ * tangent s*|dp/ds| exceeds max_contribution so that it becomes goal_contribution; the step sizes of the options
+ * are then parameter increments (converted with the first tangent).
+ * NOSH_ARC_HIT_BOUND (LOCA "Hit Continuation Bound"): the step that would cross min_value / max_value is shortened
+ * to land on the bound, and a final natural-continuation step ends the run ON the bound (one more record:
+ * steps[] needs max_steps + 2 entries). */
+#define NOSH_ARC_SCALING 1
+#define NOSH_ARC_HIT_BOUND 2
 typedef struct {
   int32_t step;
   int32_t converged;
@@ -436,8 +447,9 @@ typedef struct {
   double gibbs_energy;
   double norm;
   double fnorm;
-  double step_size;  /* arc length of this step */
+  double step_size;  /* arc length of this step (the final step onto a bound: the parameter increment) */
   double dparam_ds;  /* parameter component of the unit tangent at the new point */
+  double scale;      /* parameter scale factor s in force after this step (1 without NOSH_ARC_SCALING) */
 } nosh_arclength_step;
 NOSH_API nosh_status nosh_continuation_arclength(nosh_ctx *ctx, int np, const char *const *names,
                                                  const double *values, const char *pname,

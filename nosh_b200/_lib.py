@@ -20,6 +20,7 @@ OP_JACOBIAN, OP_KEO, OP_KEOREG = 0, 1, 2
 PREC_NONE, PREC_KEOREG_AMG = 0, 1
 SOLVER_MINRES, SOLVER_CG, SOLVER_GMRES = 0, 1, 2
 AMG_REUSE_NONE, AMG_REUSE_FULL = 0, 1
+ARC_SCALING, ARC_HIT_BOUND = 1, 2
 FVM_VERTEX_NONE, FVM_VERTEX_EXP, FVM_VERTEX_EXP_LINEARIZED = 0, 1, 2
 FVM_DIRICHLET_NONE, FVM_DIRICHLET_IDENTITY, FVM_DIRICHLET_ZERO, FVM_DIRICHLET_VALUE = 0, 1, 2, 3
 AMG_MAX_LEVELS = 16
@@ -54,7 +55,9 @@ class ArclengthOptions(C.Structure):
     _fields_ = [("initial_step_size", C.c_double), ("min_step_size", C.c_double), ("max_step_size", C.c_double),
                 ("aggressiveness", C.c_double), ("max_steps", C.c_int32), ("nl_maxit", C.c_int32),
                 ("nl_tol", C.c_double), ("lin_tol", C.c_double), ("lin_maxit", C.c_int32),
-                ("reserved", C.c_int32), ("min_value", C.c_double), ("max_value", C.c_double)]
+                ("flags", C.c_int32), ("min_value", C.c_double), ("max_value", C.c_double),
+                ("goal_contribution", C.c_double), ("max_contribution", C.c_double), ("min_scale", C.c_double),
+                ("initial_scale", C.c_double)]
 
 
 class ArclengthStep(C.Structure):
@@ -62,7 +65,7 @@ class ArclengthStep(C.Structure):
                 ("linear_iterations", C.c_int32), ("predictor_linear_iterations", C.c_int32),
                 ("reserved", C.c_int32), ("param", C.c_double), ("gibbs_energy", C.c_double),
                 ("norm", C.c_double), ("fnorm", C.c_double), ("step_size", C.c_double),
-                ("dparam_ds", C.c_double)]
+                ("dparam_ds", C.c_double), ("scale", C.c_double)]
 
 
 class NewtonResult(C.Structure):

@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (AMG_REUSE_FULL, AMG_REUSE_NONE, LAYOUT_CSR, LAYOUT_SELL32, MAT_DKEO, MAT_KEO,  # noqa: F401
+from ._lib import (AMG_REUSE_FULL, AMG_REUSE_NONE, ARC_HIT_BOUND, ARC_SCALING, LAYOUT_CSR, LAYOUT_SELL32, MAT_DKEO, MAT_KEO,  # noqa: F401
                    NO_TRANS, OP_JACOBIAN, OP_KEO, OP_KEOREG, PREC_KEOREG_AMG, PREC_NONE, AmgInfo,
                    ArclengthOptions, ArclengthStep, ContinuationStep, KrylovResult, MeshInfo, NewtonResult)
 
@@ -556,14 +556,20 @@ class Context:
 
     def continuation_arclength(self, params, pname, psi, initial_step_size=1e-3, min_step_size=1e-7,
                                max_step_size=1e-2, aggressiveness=2.0, max_steps=10, nl_tol=1e-8, nl_maxit=20,
-                               lin_tol=1e-10, lin_maxit=1000, min_value=-100.0, max_value=100.0):
+                               lin_tol=1e-10, lin_maxit=1000, min_value=-100.0, max_value=100.0, scaling=False,
+                               hit_bound=False, goal_contribution=0.0, max_contribution=0.0, min_scale=0.0,
+                               initial_scale=0.0):
         """Pseudo-arclength continuation (defaults: the LOCA settings of examples/conf.xml:35-75); psi is
-        updated in place.  Returns the step records."""
+        updated in place.  Returns the step records.  scaling / hit_bound: LOCA's "Enable Arc Length Scaling" and
+        "Hit Continuation Bound" (both on in LOCA by default; see include/nosh_b200.h)."""
         n, names, vals = _params(params)
+        flags = (ARC_SCALING if scaling else 0) | (ARC_HIT_BOUND if hit_bound else 0)
         opt = ArclengthOptions(float(initial_step_size), float(min_step_size), float(max_step_size),
                                float(aggressiveness), int(max_steps), int(nl_maxit), float(nl_tol),
-                               float(lin_tol), int(lin_maxit), 0, float(min_value), float(max_value))
-        steps = (ArclengthStep * (max_steps + 1))()
+                               float(lin_tol), int(lin_maxit), flags, float(min_value), float(max_value),
+                               float(goal_contribution), float(max_contribution), float(min_scale),
+                               float(initial_scale))
+        steps = (ArclengthStep * (max_steps + 2))()
         nrec = C.c_int32(0)
         self._ck(self.L.nosh_continuation_arclength(self.h, n, names, _ptr(vals), pname.encode(), C.byref(opt),
                                                     _ptr(psi), steps, C.byref(nrec)))

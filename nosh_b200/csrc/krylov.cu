@@ -1530,6 +1530,15 @@ void continuation_dev(Ctx *ctx, int np, const char *const *names, const double *
 //   tangent after every accepted step:  J t = -dF/dp,  (xdot, pdot) = +-(t, 1)/sqrt(<t,t>/len + 1), sign
 //   such that the direction is kept
 //   step size: ds *= 1 + aggr ((nl_maxit - its)/(nl_maxit - 1))^2 after success, ds /= 2 after failure.
+// Optional, opt->flags (LOCA's defaults "Enable Arc Length Scaling" / "Hit Continuation Bound", which nosh-cont
+// inherits; derivations in oracle/continuation.py):
+//   NOSH_ARC_SCALING    the scaled dot product is <x,y>/len + s^2 p q; when a new tangent has s |pdot| > c_max,
+//                       s is reset such that s |pdot| = c_goal, the tangent renormalised and ds, ds_min, ds_max
+//                       multiplied by |pdot_old / pdot_new|; the step sizes of the options are parameter
+//                       increments, divided by |pdot| of the first tangent
+//   NOSH_ARC_HIT_BOUND  a step whose predictor would leave [min_value, max_value] is shortened to land on the
+//                       bound and is the last arc-length step; one natural-continuation step (constant predictor)
+//                       to the bound itself ends the run
 // ---------------------------------------------------------------------------------------------------------
 void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *values, const char *pname,
                    const nosh_arclength_options *opt, double2 *psi, nosh_arclength_step *out, int *nsteps_out) {
@@ -1541,6 +1550,12 @@ void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *val
   if (!(opt->initial_step_size != 0.0) || !(opt->min_step_size > 0.0) || !(opt->max_step_size >= opt->min_step_size) ||
       opt->max_steps < 0 || opt->nl_maxit < 2)
     NOSH_THROW(NOSH_EINVAL, "bad arc-length options");
+  const bool scaling = (opt->flags & NOSH_ARC_SCALING) != 0, hit_bound = (opt->flags & NOSH_ARC_HIT_BOUND) != 0;
+  const double c_goal = opt->goal_contribution > 0.0 ? opt->goal_contribution : 0.5;
+  const double c_max = opt->max_contribution > 0.0 ? opt->max_contribution : 0.8;
+  const double sc_min = opt->min_scale > 0.0 ? opt->min_scale : 1e-3;
+  if (scaling && !(c_goal < 1.0 && c_max < 1.0)) NOSH_THROW(NOSH_EINVAL, "arc-length contributions must be < 1");
+  double sc = scaling && opt->initial_scale > 0.0 ? opt->initial_scale : 1.0;  // parameter scale factor s
   std::vector<double> vals(values, values + np);
   const int64_t No = ctx->No, Nl = ctx->Nl > 0 ? ctx->Nl : 1;
   const double len = 2.0 * (double)ctx->n_global;  // Tpetra vector length of the complex_map
@@ -1575,26 +1590,42 @@ void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *val
     st.fnorm = fn;
     st.step_size = ds;
     st.dparam_ds = pdot;
+    st.scale = sc;
     st.gibbs_energy = weighted_sum_dev(ctx, 2, psi, psi) / volume;
     st.norm = sqrt(weighted_sum_dev(ctx, 1, psi, psi) / volume);
     if (out) out[k] = st;
     return conv ? observe_step(ctx, k, st.param, st.gibbs_energy, st.norm, psi) : false;
   };
   // tangent at (psi, p): J t = -dF/dp; returns MINRES iterations, writes (XD, pdot) with the sign that
-  // keeps <(XD,pdot)_new, (XD,pdot)_old> > 0 (first call: pdot has the sign of ds)
-  auto tangent = [&](double &pdot, bool first, double sign0) {
+  // keeps <(XD,pdot)_new, (XD,pdot)_old> > 0 (first call: pdot has the sign of ds); ratio = |pdot before /
+  // after a change of the scale factor| (1 without)
+  auto tangent = [&](double &pdot, bool first, double sign0, double &ratio) {
     prepare(psi);
     compute_dfdp_dev(ctx, np, names, vals.data(), pname, psi, Fp.p);
     nosh_krylov_result kr;
     jacobian_solve(ctx, Fp.p, -1.0, Bv.p, opt->lin_tol, opt->lin_maxit, &kr);
     const double tt = dot_dev(ctx, Bv.p, Bv.p) / len;
-    double pd = 1.0 / sqrt(tt + 1.0);
+    double pd = 1.0 / sqrt(tt + sc * sc);
+    bool flip;
     if (first) {
-      if (sign0 < 0.0) pd = -pd;
-    } else {
-      const double along = dot_dev(ctx, Bv.p, XD.p) / len * pd + pd * pdot;
-      if (along < 0.0) pd = -pd;
+      flip = sign0 < 0.0;
+    } else {  // against the old tangent, in the old scale
+      const double along = dot_dev(ctx, Bv.p, XD.p) / len * pd + sc * sc * pd * pdot;
+      flip = along < 0.0;
     }
+    ratio = 1.0;
+    if (scaling) {
+      const double c = sc * pd;
+      if (c > c_max) {
+        double sn = c_goal / pd * sqrt((1.0 - c * c) / (1.0 - c_goal * c_goal));
+        if (sn < sc_min) sn = sc_min;
+        const double pn = 1.0 / sqrt(tt + sn * sn);
+        ratio = pd / pn;
+        pd = pn;
+        sc = sn;
+      }
+    }
+    if (flip) pd = -pd;
     lincomb(pd, Bv.p, 0.0, Bv.p, XD.p);
     pdot = pd;
     return kr.iterations;
@@ -1608,13 +1639,31 @@ void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *val
   bool stop = record(0, nr.converged, nr.steps, nr.total_linear_iterations, 0, nr.fnorm, 0.0, 0.0);
   done = 1;
   if (nr.converged && opt->max_steps > 0 && !stop) {
-    double ds = opt->initial_step_size, pdot = 0.0;
-    int pred_its = tangent(pdot, true, ds);
+    double ds = opt->initial_step_size, pdot = 0.0, ratio = 1.0;
+    double ds_min = opt->min_step_size, ds_max = opt->max_step_size;
+    int pred_its = tangent(pdot, true, ds, ratio);
     ds = fabs(ds);
+    if (scaling) {  // parameter increments -> arc lengths
+      const double u = 1.0 / fabs(pdot);
+      ds *= u;
+      ds_min *= u;
+      ds_max *= u;
+    }
     double p0 = vals[ip];
+    int reached = 0;
+    double bound = 0.0;
     if (No) CUDA_CHECK(cudaMemcpyAsync(X0.p, psi, sizeof(double2) * No, cudaMemcpyDeviceToDevice, ctx->stream));
     for (int k = 1; k <= opt->max_steps;) {
       // predictor
+      bool capped = false;
+      if (hit_bound) {
+        const double pred = p0 + ds * pdot;
+        if (pred > opt->max_value || pred < opt->min_value) {
+          bound = pred > opt->max_value ? opt->max_value : opt->min_value;
+          ds = (bound - p0) / pdot;
+          capped = true;
+        }
+      }
       lincomb(1.0, X0.p, ds, XD.p, psi);
       vals[ip] = p0 + ds * pdot;
       // corrector: Newton on the bordered system
@@ -1625,7 +1674,7 @@ void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *val
         const double g = prepare(psi);
         compute_f_dev(ctx, g, psi, F);
         lincomb(1.0, psi, -1.0, X0.p, Dx.p);
-        const double gc = dot_dev(ctx, XD.p, Dx.p) / len + pdot * (vals[ip] - p0) - ds;
+        const double gc = dot_dev(ctx, XD.p, Dx.p) / len + sc * sc * pdot * (vals[ip] - p0) - ds;
         nrm = sqrt(dot_dev(ctx, F, F) + gc * gc);
         if (nrm < opt->nl_tol) {
           ok = true;
@@ -1641,7 +1690,7 @@ void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *val
         lin += ka.iterations + kb.iterations;
         if (ka.breakdown || kb.breakdown) break;  // failed step: halved below
         const double xa = dot_dev(ctx, XD.p, Av.p) / len, xb = dot_dev(ctx, XD.p, Bv.p) / len;
-        const double dp = -(gc + xa) / (pdot + xb);
+        const double dp = -(gc + xa) / (sc * sc * pdot + xb);
         axpy_dev(ctx, 1.0, Av.p, psi);
         axpy_dev(ctx, dp, Bv.p, psi);
         vals[ip] += dp;
@@ -1650,7 +1699,7 @@ void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *val
       if (!ok) {
         // failed step: halve and retry from the last solution (LOCA: "Failed Step Reduction Factor" 0.5)
         ds *= 0.5;
-        if (ds < opt->min_step_size) {
+        if (ds < ds_min) {
           if (No) CUDA_CHECK(cudaMemcpyAsync(psi, X0.p, sizeof(double2) * No, cudaMemcpyDeviceToDevice, ctx->stream));
           vals[ip] = p0;
           break;
@@ -1662,15 +1711,38 @@ void arclength_dev(Ctx *ctx, int np, const char *const *names, const double *val
       p0 = vals[ip];
       if (No) CUDA_CHECK(cudaMemcpyAsync(X0.p, psi, sizeof(double2) * No, cudaMemcpyDeviceToDevice, ctx->stream));
       const int pred_prev = pred_its;
-      pred_its = tangent(pdot, false, 0.0);
+      pred_its = tangent(pdot, false, 0.0, ratio);
       stop = record(k, 1, its, lin, pred_prev, nrm, ds_used, pdot);
       done = k + 1;
       if (stop) break;
       const double fac = (double)(opt->nl_maxit - its) / (double)(opt->nl_maxit - 1);
       ds *= 1.0 + opt->aggressiveness * fac * fac;
-      if (ds > opt->max_step_size) ds = opt->max_step_size;
-      if (vals[ip] > opt->max_value || vals[ip] < opt->min_value) break;
+      if (ds > ds_max) ds = ds_max;
+      ds *= ratio;
+      ds_min *= ratio;
+      ds_max *= ratio;
+      const bool outside = vals[ip] > opt->max_value || vals[ip] < opt->min_value;
+      if (hit_bound && (capped || outside)) {
+        if (!capped) bound = vals[ip] > opt->max_value ? opt->max_value : opt->min_value;
+        reached = 1;
+        break;
+      }
+      if (outside) break;
       k++;
+    }
+    if (reached && vals[ip] != bound) {
+      // the last step: natural continuation to the bound itself, constant predictor
+      const double before = vals[ip];
+      vals[ip] = bound;
+      newton_dev(ctx, np, names, vals.data(), psi, opt->nl_tol, opt->nl_maxit, opt->lin_tol, opt->lin_maxit, &nr,
+                 nullptr, nullptr);
+      if (nr.converged) {
+        record(done, 1, nr.steps, nr.total_linear_iterations, 0, nr.fnorm, bound - before, pdot);
+        done++;
+      } else {
+        vals[ip] = before;
+        if (No) CUDA_CHECK(cudaMemcpyAsync(psi, X0.p, sizeof(double2) * No, cudaMemcpyDeviceToDevice, ctx->stream));
+      }
     }
   }
   if (nsteps_out) *nsteps_out = done;

@@ -1011,6 +1011,8 @@ struct continuation_options {  // examples/conf.xml:35-75
   double initial_step_size = 1.0e-3, min_step_size = 1.0e-7, max_step_size = 1.0e-2, aggressiveness = 2.0;
   int max_steps = 10, max_nonlinear_iterations = 20, max_linear_iterations = 1000;
   double nonlinear_tolerance = 1.0e-8, linear_tolerance = 1.0e-10;
+  // LOCA's stepper defaults, which nosh-cont inherits (examples/conf.xml sets neither)
+  bool enable_arc_length_scaling = true, hit_continuation_bound = true;
 };
 // Arc-length continuation in `param_name` from the state x (updated in place); the other parameters keep the values
 // in `params`.  observer / saver (either may be null) see every accepted step.  Returns the step records.
@@ -1030,9 +1032,10 @@ inline std::vector<nosh_arclength_step> continuation(const std::shared_ptr<const
   opt.nl_tol = o.nonlinear_tolerance;
   opt.lin_tol = o.linear_tolerance;
   opt.lin_maxit = o.max_linear_iterations;
-  opt.reserved = 0;
+  opt.flags = (o.enable_arc_length_scaling ? NOSH_ARC_SCALING : 0) | (o.hit_continuation_bound ? NOSH_ARC_HIT_BOUND : 0);
   opt.min_value = o.min_value;
   opt.max_value = o.max_value;
+  opt.goal_contribution = opt.max_contribution = opt.min_scale = opt.initial_scale = 0.0;  // LOCA's defaults
   struct hook {
     nosh::observer *obs;
     nosh::continuation_data_saver *saver;
@@ -1050,7 +1053,7 @@ inline std::vector<nosh_arclength_step> continuation(const std::shared_ptr<const
                  return 0;
                },
                &h));
-  std::vector<nosh_arclength_step> steps((size_t)o.max_steps + 1);
+  std::vector<nosh_arclength_step> steps((size_t)o.max_steps + 2);
   int n = 0;
   const nosh_status st = nosh_continuation_arclength(c, pl.size(), pl.names.data(), pl.values.data(), param_name.c_str(), &opt,
                                                      x.getDataNonConst(), steps.data(), &n);

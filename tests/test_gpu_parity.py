@@ -478,6 +478,42 @@ def test_arclength_continuation(nb, orc):
     ctx.close()
 
 
+@pytest.mark.parametrize("case", ["scaling+max", "max", "scaling+min"])
+def test_arclength_scaling_and_bounds(nb, orc, case):
+    """LOCA's two stepper defaults nosh-cont inherits: arc-length scaling (the parameter's share of the tangent is
+    brought back to 0.5 when it exceeds 0.8; step sizes are parameter increments) and "Hit Continuation Bound" (the
+    step that would cross a bound lands on it, a final natural step ends the run ON the bound)."""
+    coords, cells = orc.meshgen.tetgrid(9)
+    ctx, P, psi = make_pair(nb, orc, coords, cells, 1, group=512)
+    scaling = case.startswith("scaling")
+    ds0 = -0.05 if case.endswith("min") else 0.05
+    lo, hi = (-0.1, 100.0) if case.endswith("min") else (-100.0, 0.25 if scaling else 0.2)
+    xo, recs = orc.continuation.arclength(P, 1.0, 0.0, psi, ds0, 1e-7, 0.05, 2.0, 8, p_min=lo, p_max=hi,
+                                          scaling=scaling, hit_bound=True)
+    xg = psi.copy()
+    steps = ctx.continuation_arclength({"g": 1.0, "mu": 0.0}, "mu", xg, initial_step_size=ds0, min_step_size=1e-7,
+                                       max_step_size=0.05, aggressiveness=2.0, max_steps=8, min_value=lo,
+                                       max_value=hi, scaling=scaling, hit_bound=True)
+    assert len(steps) == len(recs) and len(recs) < 10          # the bound ended the run, not max_steps
+    for s, r in zip(steps, recs):
+        assert s.step == r["step"] and s.converged == 1
+        assert s.param == pytest.approx(r["param"], rel=1e-7, abs=1e-12)
+        assert s.newton_steps == r["newton_steps"]
+        assert s.step_size == pytest.approx(r["step_size"], rel=1e-6, abs=1e-10)
+        assert s.dparam_ds == pytest.approx(r["dparam_ds"], rel=1e-6, abs=1e-9)
+        assert s.scale == pytest.approx(r["scale"], rel=1e-7)
+        assert s.gibbs_energy == pytest.approx(r["gibbs_energy"], rel=1e-7)
+    assert steps[-1].param == (lo if case.endswith("min") else hi)         # exactly on the bound
+    if scaling:
+        assert steps[1].scale < 1.0                                           # the first tangent was rescaled ...
+        assert abs(steps[1].scale * steps[1].dparam_ds) < 0.8                 # ... into the allowed band
+        assert steps[1].param == pytest.approx(ds0, rel=0.01)                 # step sizes are parameter increments
+    else:
+        assert all(s.scale == 1.0 for s in steps)
+    assert relerr(xg, xo) <= 1e-5
+    ctx.close()
+
+
 @pytest.mark.parametrize("n", [7, 16])
 def test_persistent_minres_is_bit_identical(nb, orc, n):
     """The one-launch cooperative MINRES (tuning key "persistent_minres") against the multi-launch loop:
