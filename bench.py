@@ -675,8 +675,12 @@ def run_b200(args):
             newton = {"params": {"g": 1.0, "mu": 0.1, "theta": 0.0}, "psi0": "1", "nl_tol": 1e-8, "lin_tol": 1e-10}
             psi0 = torch.zeros(2 * No, device="cuda", dtype=torch.float64)
             psi0[0::2] = 1.0
-            for label, prec, runs in (("amg", nosh_b200.PREC_KEOREG_AMG, 2), ("none", nosh_b200.PREC_NONE, 1)):
+            for label, prec, runs in (("amg", nosh_b200.PREC_KEOREG_AMG, 2), ("amg_mixed", nosh_b200.PREC_KEOREG_AMG, 2),
+                                      ("none", nosh_b200.PREC_NONE, 1)):
                 ctx.set_preconditioner(prec)
+                # "amg_mixed": the same cycle with fp32 copies of the finest-level K and P inside the smoother and
+                # the transfers (tuning key "amg_mixed"; vectors, coarse levels and the Krylov operator stay fp64)
+                ctx.set_tuning("amg_mixed", 1 if label == "amg_mixed" else 0)
                 for k in range(runs):          # amg: the first run builds the hierarchy (reuse = full afterwards)
                     psi = psi0.clone()
                     barrier()
@@ -703,6 +707,7 @@ def run_b200(args):
         except Exception as e:      # the extra keys must never cost the contract line
             newton = {"error": "%s: %s" % (type(e).__name__, e)}
         ctx.set_preconditioner(nosh_b200.PREC_NONE)
+        ctx.set_tuning("amg_mixed", 0)
 
     nb = int(mi.n_blocks)
     bytes_apply = nb * 20 + (No + 1) * 8 + No * (16 + 16 + 24)   # SURVEY.md 8(d), per launch per GPU

@@ -536,7 +536,13 @@ NOSH_API nosh_status nosh_fvm_cg(nosh_ctx *ctx, const double *b, double *x, doub
  * 2*(n_owned+n_ghost) doubles owned by the ctx. */
 NOSH_API nosh_status nosh_scratch_vector(nosh_ctx *ctx, int slot, double **dev_ptr);
 /* tuning knobs for measurements (profiles/apply_variants.py): key "apply_variant" = which compiled variant
- * of the SELL-32 apply kernel the MINRES loop uses (0 = default).  Results do not depend on it. */
+ * of the SELL-32 apply kernel the MINRES loop uses (0 = default).  Results do not depend on it.
+ * Other keys (all leave results unchanged unless stated): "persistent_minres", "persistent_mgpu", "mgpu_lean",
+ * "mgpu_fence" (loop schedules), "sell_sigma" (row-length sorting window; before the mesh is set), "amg_graph"
+ * (V-cycle replayed as a CUDA graph), "amg_panel_products" (set-up panel size), and
+ * "amg_mixed" = 1: the V-cycle's finest-level smoother and transfer operators read fp32 copies of K and P -- a
+ * DIFFERENT (fp32-close, still symmetric positive definite) preconditioner, ~15 % faster per iteration; the
+ * solvers' own operator, all vectors and the convergence test stay fp64.  Off by default. */
 NOSH_API nosh_status nosh_ctx_set_tuning(nosh_ctx *ctx, const char *key, int value);
 /* number of kernels this library has launched on ctx so far */
 NOSH_API int64_t nosh_launch_count(const nosh_ctx *ctx);

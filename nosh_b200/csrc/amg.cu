@@ -820,10 +820,33 @@ __global__ void k_cheb_first(int64_t n, const double2 *b, const double2 *dinv, d
   x[i] = v;
 }
 
+__device__ __forceinline__ B22 load_b22(const B22 *p) { return *p; }
+__device__ __forceinline__ B22 load_b22(const float4 *p) {
+  const float4 f = *p;
+  B22 r;
+  r.a = f.x;
+  r.b = f.y;
+  r.c = f.z;
+  r.d = f.w;
+  return r;
+}
+__global__ void k_b22_to_f32(int64_t n, const B22 *in, float4 *out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const B22 v = in[i];
+  out[i] = make_float4((float)v.a, (float)v.b, (float)v.c, (float)v.d);
+}
+__global__ void k_c64_to_c32(int64_t n, const double2 *in, float2 *out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2 v = in[i];
+  out[i] = make_float2((float)v.x, (float)v.y);
+}
+
 // b_c[I] = sum_i P_iI^T r_i : LPR lanes per coarse node, fixed lane-strided order + xor tree
-template <int LPR>
+template <int LPR, typename PV>
 __global__ void __launch_bounds__(256) k_restrict(int64_t nc, const int32_t *r_rowptr, const int32_t *r_fine,
-                                                  const int32_t *r_pos, const B22 *p_val, const double2 *r,
+                                                  const int32_t *r_pos, const PV *p_val, const double2 *r,
                                                   double2 *bc, const KrylovState *gate) {
   if (gate && gate->done) return;
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -833,7 +856,7 @@ __global__ void __launch_bounds__(256) k_restrict(int64_t nc, const int32_t *r_r
   if (I < nc) {
     const int e1 = r_rowptr[I + 1];
     for (int e = r_rowptr[I] + sl; e < e1; e += LPR) {
-      const B22 P = p_val[r_pos[e]];
+      const B22 P = load_b22(p_val + r_pos[e]);
       const double2 v = __ldg(r + r_fine[e]);
       s.x += P.a * v.x + P.c * v.y;
       s.y += P.b * v.x + P.d * v.y;
@@ -847,15 +870,16 @@ __global__ void __launch_bounds__(256) k_restrict(int64_t nc, const int32_t *r_r
   if (I < nc && sl == 0) bc[I] = s;
 }
 // x_i += sum_J P_iJ xc_J
+template <typename PV>
 __global__ void __launch_bounds__(256) k_prolong(int64_t n, const int32_t *p_rowptr, const int32_t *p_col,
-                                                 const B22 *p_val, const double2 *xc, double2 *x,
+                                                 const PV *p_val, const double2 *xc, double2 *x,
                                                  const KrylovState *gate) {
   if (gate && gate->done) return;
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   double2 s = x[i];
   for (int q = p_rowptr[i]; q < p_rowptr[i + 1]; q++) {
-    const B22 P = p_val[q];
+    const B22 P = load_b22(p_val + q);
     const double2 v = __ldg(xc + p_col[q]);
     s.x += P.a * v.x + P.b * v.y;
     s.y += P.c * v.x + P.d * v.y;
@@ -937,6 +961,7 @@ void level_apply(Ctx *ctx, AmgLevel &L, int lev, int mode, const double2 *x, dou
     A.sell_row = ctx->sell_permuted ? ctx->sell_row.p : nullptr;
     A.col = ctx->col.p;
     A.val = ctx->Kval.p;
+    if (ctx->amg_mixed && mode != M_APPLY) A.val32 = ctx->Kval32.p;
     A.x = x;
     A.y = y;
     A.a = 1.0;
@@ -1340,16 +1365,23 @@ double2 *vcycle_level(Ctx *ctx, Amg &H, int lev, const double2 *b, double2 *out,
   // coarse-grid correction
   level_apply(ctx, L, lev, M_RESID, xa, L.r.p, b, nullptr, 0.0, 0.0, gate, nullptr);
   AmgLevel &C = *H.levels[lev + 1];
+  const bool p32 = lev == 0 && ctx->amg_mixed && L.p_val32.p;
   if (C.n <= SMALL_LEVEL)  // long rows of P^T, few of them: a full warp per coarse node
-    k_restrict<32><<<(unsigned)cdiv(C.n * 32, 256), 256, 0, ctx->stream>>>(C.n, L.r_rowptr.p, L.r_fine.p, L.r_pos.p,
-                                                                          L.p_val.p, L.r.p, C.b.p, gate);
+    k_restrict<32, B22><<<(unsigned)cdiv(C.n * 32, 256), 256, 0, ctx->stream>>>(C.n, L.r_rowptr.p, L.r_fine.p, L.r_pos.p,
+                                                                               L.p_val.p, L.r.p, C.b.p, gate);
+  else if (p32)
+    k_restrict<8, float4><<<(unsigned)cdiv(C.n * 8, 256), 256, 0, ctx->stream>>>(C.n, L.r_rowptr.p, L.r_fine.p, L.r_pos.p,
+                                                                                L.p_val32.p, L.r.p, C.b.p, gate);
   else
-    k_restrict<8><<<(unsigned)cdiv(C.n * 8, 256), 256, 0, ctx->stream>>>(C.n, L.r_rowptr.p, L.r_fine.p, L.r_pos.p,
-                                                                        L.p_val.p, L.r.p, C.b.p, gate);
+    k_restrict<8, B22><<<(unsigned)cdiv(C.n * 8, 256), 256, 0, ctx->stream>>>(C.n, L.r_rowptr.p, L.r_fine.p, L.r_pos.p,
+                                                                             L.p_val.p, L.r.p, C.b.p, gate);
   ctx->launches++;
   CUDA_CHECK(cudaGetLastError());
   const double2 *xc = vcycle_level(ctx, H, lev + 1, C.b.p, nullptr, gate);
-  ALAUNCH(ctx, k_prolong, n, n, L.p_rowptr.p, L.p_col.p, L.p_val.p, xc, xa, gate);
+  if (p32 && C.n > SMALL_LEVEL)
+    ALAUNCH(ctx, k_prolong<float4>, n, n, L.p_rowptr.p, L.p_col.p, L.p_val32.p, xc, xa, gate);
+  else
+    ALAUNCH(ctx, k_prolong<B22>, n, n, L.p_rowptr.p, L.p_col.p, L.p_val.p, xc, xa, gate);
   // post-smoothing
   rho = 1.0 / ch.sigma;
   level_apply(ctx, L, lev, M_CHEB, xa, xb, b, dvec, 0.0, 1.0 / ch.theta, gate, L.sinv.p);
@@ -1371,6 +1403,21 @@ void amg_free(Ctx *ctx) {
   ctx->amg_valid = false;
 }
 
+// the fp32 copies the mixed-precision cycle reads: K whenever it was refilled, the finest P once per hierarchy
+static void mixed_refresh(Ctx *ctx) {
+  if (!ctx->amg_mixed || ctx->amg->levels.size() < 2) return;
+  if (ctx->kval32_version != ctx->kval_version || ctx->Kval32.n < (size_t)ctx->nstored) {
+    ctx->Kval32.ensure(ctx->nstored > 0 ? ctx->nstored : 1);
+    if (ctx->nstored) ALAUNCH(ctx, k_c64_to_c32, ctx->nstored, ctx->nstored, ctx->Kval.p, ctx->Kval32.p);
+    ctx->kval32_version = ctx->kval_version;
+  }
+  AmgLevel &L = *ctx->amg->levels[0];
+  if (!L.p_val32.p && L.p_nnz > 0) {
+    L.p_val32.alloc(L.p_nnz);
+    ALAUNCH(ctx, k_b22_to_f32, L.p_nnz, L.p_nnz, L.p_val.p, L.p_val32.p);
+  }
+}
+
 void amg_ensure(Ctx *ctx) {
   if (!ctx->has_mesh) NOSH_THROW(NOSH_ESTATE, "no mesh set");
   if (!ctx->keoreg_ok || !ctx->keo_filled)
@@ -1383,9 +1430,11 @@ void amg_ensure(Ctx *ctx) {
       l0_refresh_diag(ctx, *ctx->amg->levels[0]);
       ctx->amg_dinv_version = ctx->keoreg_version;
     }
+    mixed_refresh(ctx);
     return;
   }
   build_hierarchy(ctx);
+  mixed_refresh(ctx);
 }
 
 static void vcycle_launches(Ctx *ctx, const double2 *b, double2 *x, const KrylovState *gate) {
@@ -1413,7 +1462,8 @@ void amg_vcycle(Ctx *ctx, const double2 *b, double2 *x, const KrylovState *gate)
     return;
   }
   for (auto &g : H.graphs)
-    if (g.b == b && g.x == x && g.gate == gate && g.degree == ctx->amg_degree && g.coarse_degree == ctx->amg_coarse_degree) {
+    if (g.b == b && g.x == x && g.gate == gate && g.degree == ctx->amg_degree && g.coarse_degree == ctx->amg_coarse_degree &&
+        g.mixed == ctx->amg_mixed) {
       CUDA_CHECK(cudaGraphLaunch(g.exec, ctx->stream));
       ctx->launches += g.launches;
       return;
@@ -1433,7 +1483,7 @@ void amg_vcycle(Ctx *ctx, const double2 *b, double2 *x, const KrylovState *gate)
     throw;
   }
   CUDA_CHECK(cudaStreamEndCapture(ctx->stream, &graph));
-  VcycleGraph g{b, x, gate, ctx->amg_degree, ctx->amg_coarse_degree, nullptr, ctx->launches - l0};
+  VcycleGraph g{b, x, gate, ctx->amg_degree, ctx->amg_coarse_degree, ctx->amg_mixed, nullptr, ctx->launches - l0};
   const cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) NOSH_THROW(NOSH_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));

@@ -31,6 +31,7 @@ struct AmgLevel {
   DBuf<double> p0;         // n: tentative-prolongator weight
   DBuf<int32_t> p_rowptr, p_col;  // P by fine row
   DBuf<B22> p_val;
+  DBuf<float4> p_val32;  // level 0 with the mixed-precision cycle: fp32 copy of p_val (a, b, c, d)
   DBuf<int32_t> r_rowptr, r_fine, r_pos;  // P^T by coarse row: fine node, position in p_val
   int64_t p_nnz = 0;
   // V-cycle vectors (n entries; level 0: Nl entries, ghost part stays zero)
@@ -42,7 +43,7 @@ struct VcycleGraph {
   const double2 *b;
   double2 *x;
   const KrylovState *gate;
-  int degree, coarse_degree;
+  int degree, coarse_degree, mixed;
   cudaGraphExec_t exec;
   int64_t launches;
 };

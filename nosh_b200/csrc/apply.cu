@@ -73,7 +73,13 @@ __device__ __forceinline__ double2 gather_x(const ApplyArgs &A, int c) {
   return __ldg(A.x + c);
 }
 
-template <int EPI, int FUSE, int U, bool PF, bool GH>
+template <bool F32>
+__device__ __forceinline__ double2 load_val(const ApplyArgs &A, int p) {
+  if (F32) return ld_stream_f2(A.val32 + p);
+  return ld_stream2(A.val + p);
+}
+
+template <int EPI, int FUSE, int U, bool PF, bool GH, bool F32 = false>
 __device__ __forceinline__ void apply_sell_cta(const ApplyArgs &A, double *red) {
   const int chunk = A.chunk_list ? __ldg(A.chunk_list + blockIdx.x) : (int)blockIdx.x;
   const int64_t pos = (int64_t)chunk * CHUNK + threadIdx.x;  // SELL position; the row stored there:
@@ -95,7 +101,7 @@ __device__ __forceinline__ void apply_sell_cta(const ApplyArgs &A, double *red) 
       while (have) {
         double2 v[U], xv[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) v[u] = ld_stream2(A.val + p + 32 * u);
+        for (int u = 0; u < U; u++) v[u] = load_val<F32>(A, p + 32 * u);
 #pragma unroll
         for (int u = 0; u < U; u++) xv[u] = gather_x<GH>(A, c[u]);
         p += 32 * U;
@@ -120,7 +126,7 @@ __device__ __forceinline__ void apply_sell_cta(const ApplyArgs &A, double *red) 
 #pragma unroll
         for (int u = 0; u < U; u++) c[u] = ld_stream_i32(A.col + p + 32 * u);
 #pragma unroll
-        for (int u = 0; u < U; u++) v[u] = ld_stream2(A.val + p + 32 * u);
+        for (int u = 0; u < U; u++) v[u] = load_val<F32>(A, p + 32 * u);
 #pragma unroll
         for (int u = 0; u < U; u++) xv[u] = gather_x<GH>(A, c[u]);
 #pragma unroll
@@ -134,7 +140,7 @@ __device__ __forceinline__ void apply_sell_cta(const ApplyArgs &A, double *red) 
     }
     for (; p < pend; p += 32) {
       const int c = ld_stream_i32(A.col + p);
-      const double2 v = ld_stream2(A.val + p);
+      const double2 v = load_val<F32>(A, p);
       double2 xv = gather_x<GH>(A, c);
       if (FUSE == FUSE_MINRES) {
         xv = scaled(xv, scale);
@@ -180,7 +186,7 @@ __device__ __forceinline__ void apply_sell_cta(const ApplyArgs &A, double *red) 
 // GHK: the launch carries a separate ghost vector (A.xg).  Only the CTAs at or behind halo_first_block -- the
 // chunks that reference ghosts, listed last -- wait for the neighbours' flags and use the ghost-aware gather;
 // all other CTAs run the plain body (the pointer select per gather costs ~15 % on the interior rows: measured).
-template <int EPI, int FUSE, int U, int MINB, bool PF, bool GHK = false>
+template <int EPI, int FUSE, int U, int MINB, bool PF, bool GHK = false, bool F32 = false>
 __global__ void __launch_bounds__(CHUNK, MINB) k_apply_sell(const ApplyArgs A) {
   if (krylov_skip<FUSE>(A)) return;
   if (A.gate && A.gate->done) return;
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(CHUNK, MINB) k_apply_sell(const ApplyArgs A) {
       return;
     }
   }
-  apply_sell_cta<EPI, FUSE, U, PF, false>(A, red);
+  apply_sell_cta<EPI, FUSE, U, PF, false, F32>(A, red);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -272,7 +278,11 @@ void launch2(Ctx *ctx, const ApplyArgs &A) {
   if (grid == 0) return;
   constexpr bool ghost_ok = FUSE == FUSE_NONE || FUSE == FUSE_AXPBY;
   if (A.xg && !ghost_ok) NOSH_THROW(NOSH_EINVAL, "internal: separate ghost vector with a fused Krylov/smoother apply");
-  if (ctx->layout == NOSH_LAYOUT_SELL32 && A.xg) {
+  constexpr bool f32_ok = EPI == EPI_DIAG && (FUSE == FUSE_RESID || FUSE == FUSE_CHEB);
+  if (A.val32 && !(f32_ok && ctx->layout == NOSH_LAYOUT_SELL32)) NOSH_THROW(NOSH_EINVAL, "internal: fp32 values with this apply variant");
+  if (A.val32) {
+    if constexpr (f32_ok) k_apply_sell<EPI, FUSE, 4, 2, false, false, true><<<grid, CHUNK, 0, ctx->stream>>>(A);
+  } else if (ctx->layout == NOSH_LAYOUT_SELL32 && A.xg) {
     if constexpr (ghost_ok) k_apply_sell<EPI, FUSE, 4, 2, false, true><<<grid, CHUNK, 0, ctx->stream>>>(A);
   } else if (ctx->layout == NOSH_LAYOUT_SELL32) {
     // measurement variants exist for the two kernels of the MINRES loop only (compile time)

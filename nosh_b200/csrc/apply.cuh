@@ -38,6 +38,7 @@ struct ApplyArgs {
   const int32_t *sell_row;   // SELL-32-sigma: row stored at a SELL position (NULL: identity); mesh.cu
   const int32_t *col;
   const double2 *val;
+  const float2 *val32;  // optional fp32 copy of val (FUSE_RESID / FUSE_CHEB on SELL-32: the mixed-precision V-cycle)
   const double2 *x;  // Nl entries (owned + ghosts); owned entries only when xg is set
   const double2 *xg; // optional: ghost entries (column c >= No reads xg[c - No]) -- the landing slot of the
                      // peer-memory halo exchange, so the caller's vector needs no ghost room (FUSE_NONE/AXPBY)

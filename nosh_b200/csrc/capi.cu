@@ -1146,6 +1146,8 @@ nosh_status nosh_ctx_set_tuning(nosh_ctx *ctx, const char *key, int value) {
     ctx->amg_valid = false;
   } else if (strcmp(key, "amg_graph") == 0) {
     ctx->amg_graph = value != 0;
+  } else if (strcmp(key, "amg_mixed") == 0) {
+    ctx->amg_mixed = value != 0;
   } else if (strcmp(key, "mgpu_lean") == 0) {
     ctx->mgpu_lean = value != 0;
   } else if (strcmp(key, "mgpu_fence") == 0) {

@@ -250,6 +250,12 @@ struct Ctx {
   int amg_reuse = 1;          // nosh_amg_reuse: 0 none, 1 full ("reuse: type" = "full", keo_regularized.cpp:300)
   int64_t amg_panel_products = (int64_t)32 << 20;  // products per row panel of the set-up's sparse products (amg.cu)
   int amg_graph = 1;          // replay the V-cycle as a CUDA graph (amg.cu:amg_vcycle)
+  // mixed-precision V-cycle (tuning key "amg_mixed", off by default): the two finest-level smoother passes read an
+  // fp32 copy of K (12 B per block instead of 20), restriction / prolongation an fp32 copy of the finest P.  Vectors,
+  // diagonals, accumulation and every coarser level stay fp64; the Krylov solver's own operator is never touched.
+  int amg_mixed = 0;
+  DBuf<float2> Kval32;
+  int64_t kval_version = 0, kval32_version = -1;
   bool amg_keep_l0 = false;   // keep the level-0 block CSR copy (parity accessors)
   int64_t keoreg_version = 0, amg_dinv_version = -1;
   int lin_solver = 0;         // nosh_linear_solver of the Newton / continuation drivers (default MINRES)
@@ -321,6 +327,11 @@ __device__ __forceinline__ double2 ld_stream2(const double2 *p) {
                : "=d"(r.x), "=d"(r.y)
                : "l"(p));
   return r;
+}
+__device__ __forceinline__ double2 ld_stream_f2(const float2 *p) {
+  float a, b;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "l"(p));
+  return make_double2((double)a, (double)b);
 }
 __device__ __forceinline__ int ld_stream_i32(const int *p) {
   int r;

@@ -273,6 +273,7 @@ void keo_fill(Ctx *ctx, int np, const char *const *names, const double *values, 
   ctx->keo_filled = true;
   ctx->keo_mu = mu;
   ctx->keo_theta = theta;
+  ctx->kval_version++;
   ctx->keoreg_version++;  // the regularised KEO shares these values: a kept AMG hierarchy refreshes its finest level
 }
 

@@ -118,6 +118,40 @@ def test_vcycle_matches_oracle(nb, orc, degree, coarse_degree):
     assert b @ y > 0
 
 
+def test_mixed_precision_cycle(nb, orc):
+    """Tuning key "amg_mixed": the finest level's smoother passes read an fp32 copy of K, restriction and prolongation
+    an fp32 copy of P.  The cycle stays a fixed symmetric positive definite operator (K_ij and K_ji round to
+    conjugates), differs from the fp64 cycle by fp32 rounding only, and MINRES -- whose own operator stays fp64 --
+    reaches the same solution in the same number of iterations (+-1)."""
+    ctx, P, Pm, H, x, params = setup_pair(nb, orc, n=16, coarse_max=64)
+    rng = np.random.default_rng(8)
+    b, c = rng.standard_normal(2 * P.N), rng.standard_normal(2 * P.N)
+    y64 = ctx.keoreg_apply(b)
+    J = oracle_jacobian(P)
+    rhs = -P.compute_f(params["g"], x)
+    x64, r64 = ctx.minres(rhs, tol=1e-10, maxit=500, prec=nb.PREC_KEOREG_AMG)
+    ctx.set_tuning("amg_mixed", 1)
+    y32 = ctx.keoreg_apply(b)
+    assert 0 < relerr(y32, y64) <= 1e-6                       # really another operator, fp32-close
+    assert relerr(y32, H.vcycle(b)) <= 1e-6
+    assert abs(c @ y32 - b @ ctx.keoreg_apply(c)) <= 1e-11 * abs(c @ y32)      # symmetric to fp64 rounding
+    assert b @ y32 > 0
+    x32, r32 = ctx.minres(rhs, tol=1e-10, maxit=500, prec=nb.PREC_KEOREG_AMG)
+    assert r32.converged == 1 and abs(r32.iterations - r64.iterations) <= 1
+    assert np.linalg.norm(J @ x32 - rhs) <= 1e-8 * np.linalg.norm(rhs)
+    assert relerr(x32, x64) <= 1e-7
+    # K changes (new mu): the fp32 copy follows; switching back gives the fp64 cycle's bits again
+    p2 = dict(params, mu=params["mu"] + 0.1)
+    ctx.keoreg_rebuild(p2, x)
+    y32b = ctx.keoreg_apply(b)
+    ctx.set_tuning("amg_mixed", 0)
+    y64b = ctx.keoreg_apply(b)
+    assert 0 < relerr(y32b, y64b) <= 1e-6 and relerr(y64b, y64) > 1e-4
+    ctx.keoreg_rebuild(params, x)
+    assert np.array_equal(ctx.keoreg_apply(b), y64)
+    ctx.close()
+
+
 def test_single_level_is_the_exact_inverse(nb, orc):
     ctx, P, Pm, H, x, params = setup_pair(nb, orc, n=6, coarse_max=512)
     b = np.cos(np.arange(2 * P.N) * 0.7)
