@@ -79,6 +79,10 @@ def parse():
                          "on the regularised KEO, keo_regularized::apply)")
     ap.add_argument("--amg-degree", type=int, default=1)
     ap.add_argument("--amg-coarse-degree", type=int, default=2)
+    ap.add_argument("--no-strong-probe", action="store_true",
+                    help="skip the short strong-scaling measurement (configs[4]: the SAME 64M-vertex mesh on any "
+                         "number of GPUs) the default run appends as `strong_scaling_64M`")
+    ap.add_argument("--strong-probe-n", type=int, default=400)
     ap.add_argument("--no-newton", action="store_true",
                     help="default workload: skip the extra keys that report one full Newton-MINRES solve of the "
                          "same mesh (BASELINE.json configs[2]) with and without the AMG preconditioner")
@@ -709,6 +713,61 @@ def run_b200(args):
         ctx.set_preconditioner(nosh_b200.PREC_NONE)
         ctx.set_tuning("amg_mixed", 0)
 
+    # ---- configs[4], driver-visible: the SAME mesh (400^3 = 64M vertices) whatever the number of GPUs, a few steps
+    # of the same workload on a second context -- the per-N lines of a scaling run then carry a strong-scaling
+    # curve next to the weak one.  CUDA events, max over ranks; outside the contract's timed region. ----
+    strong = None
+    if not args.no_strong_probe and not args.strong:
+        c2 = None
+        try:
+            sn = args.strong_probe_n
+            c2 = make_ctx(stream=stream)
+            t0 = time.perf_counter()
+            mi2 = c2.mesh_tetgrid(sn, sn, sn, lo=(-5.0, -5.0, -5.0), hi=(5.0, 5.0, 5.0))
+            c2.set_thickness(None, 1.0)
+            c2.set_potential_constant(-1.0)
+            c2.set_mvp_constcurl((0.0, 0.0, 1.0))
+            c2.synchronize()
+            t_setup2 = time.perf_counter() - t0
+            No2 = int(mi2.n_owned)
+            ang2 = torch.rand(No2, generator=gen, device="cuda", dtype=torch.float64) * (2 * np.pi)
+            psi2 = torch.stack([torch.cos(ang2), torch.sin(ang2)], 1).reshape(-1).contiguous()
+            b2 = torch.randn(2 * No2, generator=gen, device="cuda", dtype=torch.float64)
+            x2 = torch.empty_like(b2)
+            del ang2
+            ssteps, ms2 = 2, None
+            for phase in ("warm", "timed"):
+                barrier()
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for k in range(1 if phase == "warm" else ssteps):
+                    par = dict(PARAMS)
+                    par["mu"] = PARAMS["mu"] * (1.0 + 1e-9 * (k + 3))
+                    c2.keo_fill(par)
+                    c2.jac_rebuild(par, psi2)
+                    _, r2 = c2.minres(b2, x2, tol=0.0, maxit=ITERS)
+                    assert r2.iterations == ITERS, r2.iterations
+                e1.record()
+                barrier()
+                ms2 = e0.elapsed_time(e1) / ssteps
+            if world > 1:
+                t = torch.tensor([ms2], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms2 = float(t.item())
+            Ng2 = int(mi2.n_global)
+            strong = {"workload": workload_text(sn, sn, Ng2, No2), "n_vertices": Ng2, "steps": ssteps, "warmup": 1,
+                      "ms_per_step": ms2, "value": 2.0 * Ng2 * ITERS / (ms2 * 1e-3) / 1e9, "unit": "GDOF/s",
+                      "scaling": "strong", "setup_s": t_setup2}
+            del psi2, b2, x2
+        except Exception as e:      # the extra keys must never cost the contract line
+            strong = {"error": "%s: %s" % (type(e).__name__, e)}
+        if c2 is not None:
+            try:
+                c2.close()
+            except Exception:
+                pass
+
     nb = int(mi.n_blocks)
     bytes_apply = nb * 20 + (No + 1) * 8 + No * (16 + 16 + 24)   # SURVEY.md 8(d), per launch per GPU
     peak, peak_src = measured_peak()
@@ -760,6 +819,8 @@ def run_b200(args):
         }
         if newton:
             out["newton_solve"] = newton
+        if strong:
+            out["strong_scaling_64M"] = strong
         if parity is not None:
             out["parity"] = parity
         if not args.no_cpu_baseline and world == 1:

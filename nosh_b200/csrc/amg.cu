@@ -47,69 +47,15 @@ inline dim3 grid_for(int64_t n, int tpb = 256) { return dim3((unsigned)cdiv(n > 
     CUDA_CHECK(cudaGetLastError());                              \
   } while (0)
 
-// Set-up temporaries come from ONE cudaMalloc'ed arena with a first-fit sub-allocator.  The expand-sort-compress
-// products allocate and free hundreds of buffers; cudaMalloc / cudaFree per buffer cost milliseconds each (cudaFree
-// synchronises), and the stream-ordered pool (cudaMallocAsync) -- used in round 1 -- grows through the virtual-
-// memory API, which on this pool's VMs takes 0.05 ... 1.7 s for 8 GB (profiles/r2_alloc_probe.jsonl: cudaMalloc of
-// the same 8.6 GB: 1 - 7 ms, every time).  All work is on one stream, so a block handed back by one temporary may
-// be given to the next at once: the kernels that used it were enqueued earlier (the ordering cudaFreeAsync gives).
-// A request the arena cannot serve falls back to cudaMalloc / cudaFree.
-struct Arena {
-  char *base = nullptr;
-  size_t cap = 0;
-  struct Blk {
-    size_t off, size;
-    bool free;
-  };
-  std::vector<Blk> blocks;  // by offset
-  size_t high = 0, used = 0;
-  void init(size_t bytes) {
-    if (cudaMalloc(&base, bytes) != cudaSuccess) {
-      cudaGetLastError();
-      base = nullptr;
-      bytes = 0;
-    }
-    cap = bytes;
-    blocks.assign(1, Blk{0, bytes, true});
-  }
-  void *alloc(size_t bytes) {
-    bytes = (bytes + 511) & ~(size_t)511;
-    for (size_t i = 0; i < blocks.size(); i++)
-      if (blocks[i].free && blocks[i].size >= bytes) {
-        if (blocks[i].size > bytes) blocks.insert(blocks.begin() + i + 1, Blk{blocks[i].off + bytes, blocks[i].size - bytes, true});
-        blocks[i].size = bytes;
-        blocks[i].free = false;
-        used += bytes;
-        high = std::max(high, used);
-        return base + blocks[i].off;
-      }
-    return nullptr;
-  }
-  bool owns(const void *p) const { return base && (const char *)p >= base && (const char *)p < base + cap; }
-  void release(void *p) {
-    const size_t off = (size_t)((char *)p - base);
-    for (size_t i = 0; i < blocks.size(); i++)
-      if (blocks[i].off == off && !blocks[i].free) {
-        blocks[i].free = true;
-        used -= blocks[i].size;
-        if (i + 1 < blocks.size() && blocks[i + 1].free) {
-          blocks[i].size += blocks[i + 1].size;
-          blocks.erase(blocks.begin() + i + 1);
-        }
-        if (i > 0 && blocks[i - 1].free) {
-          blocks[i - 1].size += blocks[i].size;
-          blocks.erase(blocks.begin() + i);
-        }
-        return;
-      }
-  }
-  void destroy() {
-    if (base) cudaFree(base);
-    base = nullptr;
-    cap = 0;
-    blocks.clear();
-  }
-};
+// All memory of the set-up comes from ONE cudaMalloc'ed arena (common.cuh: Arena, first fit, blocks can be handed
+// back): the temporaries below (TBuf) and, through g_dbuf_arena, every DBuf -- the hierarchy's own buffers included,
+// which build_hierarchy moves into one exact-size allocation at the end.  The expand-sort-compress products
+// allocate and free hundreds of buffers; cudaMalloc / cudaFree per buffer cost 0.3 ... 10 ms each depending on the
+// box (cudaFree synchronises), and the stream-ordered pool (cudaMallocAsync) -- used in round 1 -- grows through the
+// virtual-memory API, which on this pool's VMs takes 0.05 ... 1.7 s for 8 GB (profiles/r2_alloc_probe.jsonl).  All
+// work is on one stream, so a block handed back by one temporary may be given to the next at once: the kernels that
+// used it were enqueued earlier (the ordering cudaFreeAsync gives).  A request the arena cannot serve falls back to
+// cudaMalloc / cudaFree.
 thread_local Arena *g_arena = nullptr;
 thread_local size_t g_fallback_bytes = 0;
 template <typename T>
@@ -1148,18 +1094,24 @@ void build_coarse_inverse(Ctx *ctx, Amg &H) {
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 
-void build_hierarchy(Ctx *ctx) {
-  const auto t0 = std::chrono::steady_clock::now();
+// every device buffer a level keeps
+template <class F>
+void for_each_buffer(AmgLevel &L, F &&f) {
+  f(L.rowptr); f(L.col); f(L.val); f(L.slice_off); f(L.scol); f(L.sval); f(L.dinv); f(L.sinv); f(L.offsum);
+  f(L.agg); f(L.p0); f(L.p_rowptr); f(L.p_col); f(L.p_val); f(L.p_val32); f(L.r_rowptr); f(L.r_fine); f(L.r_pos);
+  f(L.b); f(L.x); f(L.x2); f(L.d); f(L.r);
+}
+
+void build_levels(Ctx *ctx, Amg *H, std::chrono::steady_clock::time_point t0) {
   // NOSH_B200_AMG_TIMING=1: phase times of the set-up on stderr
   static const bool timing = [] {
     const char *e = getenv("NOSH_B200_AMG_TIMING");
     return e && atoi(e) != 0;
   }();
-  auto tlast = t0;
+  (void)t0;
+  auto tlast = std::chrono::steady_clock::now();
   // phase times: always recorded (nosh_ctx_get_stat "amg.setup.<phase>" = seconds summed over the levels; a
   // stream synchronisation per phase is noise against the set-up), printed with NOSH_B200_AMG_TIMING=1
-  for (auto it = ctx->stats.begin(); it != ctx->stats.end();)
-    it = it->first.rfind("amg.setup.", 0) == 0 ? ctx->stats.erase(it) : std::next(it);
   auto tick = [&](const char *what, int lev) {
     cudaStreamSynchronize(ctx->stream);
     const auto now = std::chrono::steady_clock::now();
@@ -1168,36 +1120,6 @@ void build_hierarchy(Ctx *ctx) {
     if (timing) fprintf(stderr, "[amg setup] level %d %-22s %8.1f ms\n", lev, what, 1e3 * sec);
     tlast = now;
   };
-  amg_free(ctx);
-  Amg *H = new Amg();
-  ctx->amg = H;
-  // the arena for the temporaries (see TBuf): one panel of the expand-sort-compress products (32M products x ~112 B)
-  // plus the compressed results of the largest product (~20 B per level-0 block measured; 40 reserved)
-  Arena arena;
-  {
-    size_t free_b = 0, total_b = 0;
-    CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    size_t want = ((size_t)4 << 30) + (size_t)ctx->nb * 40;  // measured high-water mark at 8M vertices: 6.1 GB
-    want = std::min(want, (size_t)ctx->nb * 400 + ((size_t)64 << 20));  // small problems: a few hundred bytes per block
-    if (const char *e = getenv("NOSH_B200_AMG_ARENA_MB")) want = (size_t)atoll(e) << 20;
-    want = std::min(want, free_b / 2);
-    arena.init(want);
-    ctx->stats["amg.arena_bytes"] = (double)arena.cap;
-  }
-  g_arena = &arena;
-  g_fallback_bytes = 0;
-  struct ArenaGuard {  // declared before every temporary: destroyed after all of them
-    Arena *a;
-    Ctx *ctx;
-    ~ArenaGuard() {
-      cudaStreamSynchronize(ctx->stream);
-      ctx->stats["amg.arena_high_bytes"] = (double)a->high;
-      ctx->stats["amg.arena_fallback_bytes"] = (double)g_fallback_bytes;
-      g_arena = nullptr;
-      a->destroy();
-    }
-  } arena_guard{&arena, ctx};
-  tick("arena", 0);
   Temp tmp;
   DBuf<double> scratch;
   const int64_t No = ctx->No;
@@ -1317,6 +1239,85 @@ void build_hierarchy(Ctx *ctx) {
   }
   build_coarse_inverse(ctx, *H);
   tick("dense coarse inverse", (int)H->levels.size() - 1);
+}
+
+void build_hierarchy(Ctx *ctx) {
+  const auto t0 = std::chrono::steady_clock::now();
+  amg_free(ctx);
+  Amg *H = new Amg();
+  ctx->amg = H;
+  for (auto it = ctx->stats.begin(); it != ctx->stats.end();)
+    it = it->first.rfind("amg.setup.", 0) == 0 ? ctx->stats.erase(it) : std::next(it);
+  // the arena: one panel of the expand-sort-compress products (32M products x ~112 B), the compressed results of
+  // the largest product, the level-0 block-CSR copy the products read and the hierarchy itself
+  Arena arena;
+  {
+    size_t free_b = 0, total_b = 0;
+    CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    size_t want = ((size_t)4 << 30) + (size_t)ctx->nb * 90;  // measured high-water mark at 8M vertices: 12.6 GB = 105 B/block
+    want = std::min(want, (size_t)ctx->nb * 800 + ((size_t)64 << 20));  // small problems: a few hundred bytes per block
+    if (const char *e = getenv("NOSH_B200_AMG_ARENA_MB")) want = (size_t)atoll(e) << 20;
+    want = std::min(want, free_b / 2);
+    const double t = wall_now();
+    arena.init(want);
+    ctx->stats["amg.setup.arena"] = wall_now() - t;
+    ctx->stats["amg.arena_bytes"] = (double)arena.cap;
+  }
+  const AllocStats a0 = g_alloc_stats;
+  g_arena = g_dbuf_arena = &arena;
+  g_fallback_bytes = 0;
+  auto leave = [&] {
+    g_arena = g_dbuf_arena = nullptr;
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stats["amg.arena_high_bytes"] = (double)arena.high;
+    ctx->stats["amg.arena_fallback_bytes"] = (double)g_fallback_bytes;
+    ctx->stats["amg.alloc.malloc_calls"] = (double)(g_alloc_stats.malloc_n - a0.malloc_n);
+    ctx->stats["amg.alloc.malloc_s"] = g_alloc_stats.malloc_s - a0.malloc_s;
+    ctx->stats["amg.alloc.free_calls"] = (double)(g_alloc_stats.free_n - a0.free_n);
+    ctx->stats["amg.alloc.free_s"] = g_alloc_stats.free_s - a0.free_s;
+    const double t = wall_now();
+    arena.destroy();
+    ctx->stats["amg.setup.arena release"] = wall_now() - t;
+  };
+  try {
+    build_levels(ctx, H, t0);
+    // the hierarchy leaves the arena: one allocation of the exact size, every buffer copied into it
+    const double t = wall_now();
+    g_arena = g_dbuf_arena = nullptr;
+    size_t total = 0;
+    auto count = [&](auto &buf) {
+      if (buf.p && buf.owner == &arena) total += (buf.bytes() + 511) & ~(size_t)511;
+    };
+    for (auto *L : H->levels) for_each_buffer(*L, count);
+    count(H->coarse_inv);
+    if (total) {
+      const double tm = wall_now();
+      CUDA_CHECK(cudaMalloc(&H->store, total));
+      g_alloc_stats.malloc_s += wall_now() - tm;
+      g_alloc_stats.malloc_n++;
+    }
+    H->store_bytes = total;
+    size_t off = 0;
+    auto move = [&](auto &buf) {
+      if (buf.p && buf.owner == &arena) {
+        const size_t bytes = (buf.bytes() + 511) & ~(size_t)511;
+        buf.rehome((char *)H->store + off, ctx->stream);
+        off += bytes;
+      }
+    };
+    for (auto *L : H->levels) for_each_buffer(*L, move);
+    move(H->coarse_inv);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (arena.used != 0) NOSH_THROW(NOSH_ESTATE, "internal: AMG set-up left %zu bytes of its arena in use", arena.used);
+    ctx->stats["amg.store_bytes"] = (double)total;
+    ctx->stats["amg.setup.move to permanent storage"] = wall_now() - t;
+  } catch (...) {
+    // whatever was built points into the arena: drop it before the arena goes
+    amg_free(ctx);
+    leave();
+    throw;
+  }
+  leave();
   ctx->amg_valid = true;
   ctx->amg_dinv_version = ctx->keoreg_version;
   H->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

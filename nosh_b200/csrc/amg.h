@@ -54,9 +54,13 @@ struct Amg {
   int64_t n_coarse2 = 0;
   double setup_seconds = 0.0;
   std::vector<VcycleGraph> graphs;
+  void *store = nullptr;  // one allocation holding every buffer of the levels (build_hierarchy moves them here)
+  size_t store_bytes = 0;
   ~Amg() {
     for (auto &g : graphs) cudaGraphExecDestroy(g.exec);
     for (auto *l : levels) delete l;
+    coarse_inv.release();
+    if (store) cudaFree(store);
   }
 };
 

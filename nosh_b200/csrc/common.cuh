@@ -2,10 +2,12 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -45,23 +47,115 @@ struct Exception {
                  __LINE__);                                                                  \
   } while (0)
 
+// A cudaMalloc'ed block with a first-fit sub-allocator (blocks can be handed back).  Used by the AMG set-up
+// (amg.cu), whose hundreds of allocations would otherwise each be a driver call: on this pool's VMs a cudaMalloc /
+// cudaFree costs 0.3 ... 10 ms depending on the box, whatever the size.
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0;
+  struct Blk {
+    size_t off, size;
+    bool free;
+  };
+  std::vector<Blk> blocks;  // by offset
+  size_t high = 0, used = 0;
+  void init(size_t bytes) {
+    if (cudaMalloc(&base, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      base = nullptr;
+      bytes = 0;
+    }
+    cap = bytes;
+    blocks.assign(1, Blk{0, bytes, true});
+  }
+  void *alloc(size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    for (size_t i = 0; i < blocks.size(); i++)
+      if (blocks[i].free && blocks[i].size >= bytes) {
+        if (blocks[i].size > bytes) blocks.insert(blocks.begin() + i + 1, Blk{blocks[i].off + bytes, blocks[i].size - bytes, true});
+        blocks[i].size = bytes;
+        blocks[i].free = false;
+        used += bytes;
+        high = std::max(high, used);
+        return base + blocks[i].off;
+      }
+    return nullptr;
+  }
+  bool owns(const void *p) const { return base && (const char *)p >= base && (const char *)p < base + cap; }
+  void release(void *p) {
+    const size_t off = (size_t)((char *)p - base);
+    for (size_t i = 0; i < blocks.size(); i++)
+      if (blocks[i].off == off && !blocks[i].free) {
+        blocks[i].free = true;
+        used -= blocks[i].size;
+        if (i + 1 < blocks.size() && blocks[i + 1].free) {
+          blocks[i].size += blocks[i + 1].size;
+          blocks.erase(blocks.begin() + i + 1);
+        }
+        if (i > 0 && blocks[i - 1].free) {
+          blocks[i - 1].size += blocks[i].size;
+          blocks.erase(blocks.begin() + i);
+        }
+        return;
+      }
+  }
+  void destroy() {
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = 0;
+    blocks.clear();
+  }
+};
+// While set (AMG set-up), DBuf allocations of this thread come from the arena; a DBuf remembers where its memory
+// came from, so it may be released -- or moved to permanent storage with rehome() -- at any later time BEFORE the
+// arena dies.
+inline thread_local Arena *g_dbuf_arena = nullptr;
+struct AllocStats {
+  double malloc_s = 0.0, free_s = 0.0;
+  int64_t malloc_n = 0, free_n = 0;
+};
+inline thread_local AllocStats g_alloc_stats;
+inline double wall_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 template <typename T>
 struct DBuf {
   T *p = nullptr;
   size_t n = 0;
+  Arena *owner = nullptr;  // memory from an arena (returned to it on release)
+  bool borrowed = false;   // memory owned by someone else (rehome): never freed here
   DBuf() = default;
   DBuf(const DBuf &) = delete;
   DBuf &operator=(const DBuf &) = delete;
   ~DBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p && !borrowed) {
+      if (owner) {
+        owner->release(p);
+      } else {
+        const double t = wall_now();
+        cudaFree(p);
+        g_alloc_stats.free_s += wall_now() - t;
+        g_alloc_stats.free_n++;
+      }
+    }
     p = nullptr;
     n = 0;
+    owner = nullptr;
+    borrowed = false;
   }
   void alloc(size_t count) {
     release();
     if (count == 0) count = 1;
-    CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+    if (g_dbuf_arena) {
+      p = (T *)g_dbuf_arena->alloc(count * sizeof(T));
+      if (p) owner = g_dbuf_arena;
+    }
+    if (!p) {
+      const double t = wall_now();
+      CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+      g_alloc_stats.malloc_s += wall_now() - t;
+      g_alloc_stats.malloc_n++;
+    }
     n = count;
   }
   void ensure(size_t count) {
@@ -70,6 +164,20 @@ struct DBuf {
   void swap(DBuf &o) {
     std::swap(p, o.p);
     std::swap(n, o.n);
+    std::swap(owner, o.owner);
+    std::swap(borrowed, o.borrowed);
+  }
+  size_t bytes() const { return n * sizeof(T); }
+  // copy the contents to dst (device memory someone else owns, at least bytes() long), give the old memory back,
+  // point there from now on.  Stream-ordered: the old block may be reused by work enqueued later on `stream`.
+  void rehome(void *dst, cudaStream_t stream) {
+    if (!p) return;
+    CUDA_CHECK(cudaMemcpyAsync(dst, p, bytes(), cudaMemcpyDeviceToDevice, stream));
+    const size_t keep = n;
+    release();
+    p = (T *)dst;
+    n = keep;
+    borrowed = true;
   }
 };
 

@@ -31,7 +31,9 @@ wall = time.perf_counter() - t0
 ai = ctx.amg_info()
 out = {"n": n, "setup_seconds": float(ai.setup_seconds), "wall_seconds": wall,
        "arena_mb_env": os.environ.get("NOSH_B200_AMG_ARENA_MB"), "levels": int(ai.levels)}
-for k in ("amg.arena_bytes", "amg.arena_high_bytes", "amg.arena_fallback_bytes", "amg.setup.arena"):
+for k in ("amg.arena_bytes", "amg.arena_high_bytes", "amg.arena_fallback_bytes", "amg.setup.arena", "amg.store_bytes",
+          "amg.setup.move to permanent storage", "amg.alloc.malloc_calls", "amg.alloc.malloc_s",
+          "amg.alloc.free_calls", "amg.alloc.free_s"):
     try:
         out[k] = ctx.stat(k)
     except KeyError:
