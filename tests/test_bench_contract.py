@@ -50,6 +50,24 @@ def test_multi_gpu_lines_carry_the_parity_object():
         assert d["gpu_launches"] <= 10 * d["steps"]            # one cooperative launch per MINRES solve and rank
 
 
+def test_final_lines_carry_the_strong_scaling_probe_and_the_mixed_cycle():
+    """Every default line holds a short run on the SAME 64M-vertex mesh (configs[4]): the 2- and 8-GPU lines of the
+    round give the strong-scaling curve; the AMG block lists the fp64 and the mixed-precision cycle side by side."""
+    ms = {}
+    for name, n in (("r2_bench_weak_2gpu_final.json", 2), ("r2_bench_weak_8gpu_final.json", 8)):
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        sp = d["strong_scaling_64M"]
+        assert d["n_gpus"] == n and d["parity"]["ok_all_ranks"] is True
+        assert sp["n_vertices"] == 64_000_000 and sp["scaling"] == "strong" and sp["steps"] >= 2
+        assert abs(sp["value"] - 2.0 * sp["n_vertices"] * 200 / (sp["ms_per_step"] * 1e-3) / 1e9) < 1e-9 * sp["value"]
+        ms[n] = sp["ms_per_step"]
+        nw = d["newton_solve"]
+        assert nw["amg"]["minres_iterations_per_step"] == nw["amg_mixed"]["minres_iterations_per_step"]
+        assert nw["amg_mixed"]["solve_seconds"] < nw["amg"]["solve_seconds"]
+        assert nw["amg"]["hierarchy_setup_seconds"] < 0.6
+    assert 3.5 < ms[2] / ms[8] <= 4.0                    # 2 -> 8 GPUs on the same mesh
+
+
 def test_rank_other_than_zero_of_the_reference_arm_does_no_work():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
