@@ -74,10 +74,15 @@ __device__ __forceinline__ double2 gather_x(const ApplyArgs &A, int c) {
 }
 
 template <bool F32>
-__device__ __forceinline__ double2 load_val(const ApplyArgs &A, int p) {
-  if (F32) return ld_stream_f2(A.val32 + p);
-  return ld_stream2(A.val + p);
-}
+struct ValT {
+  using type = double2;
+  static __device__ __forceinline__ type load(const ApplyArgs &A, int p) { return ld_stream2(A.val + p); }
+};
+template <>
+struct ValT<true> {
+  using type = float2;
+  static __device__ __forceinline__ type load(const ApplyArgs &A, int p) { return ld_stream_f2(A.val32 + p); }
+};
 
 template <int EPI, int FUSE, int U, bool PF, bool GH, bool F32 = false>
 __device__ __forceinline__ void apply_sell_cta(const ApplyArgs &A, double *red) {
@@ -99,9 +104,10 @@ __device__ __forceinline__ void apply_sell_cta(const ApplyArgs &A, double *red) 
         for (int u = 0; u < U; u++) c[u] = ld_stream_i32(A.col + p + 32 * u);
       }
       while (have) {
-        double2 v[U], xv[U];
+        typename ValT<F32>::type v[U];
+        double2 xv[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) v[u] = load_val<F32>(A, p + 32 * u);
+        for (int u = 0; u < U; u++) v[u] = ValT<F32>::load(A, p + 32 * u);
 #pragma unroll
         for (int u = 0; u < U; u++) xv[u] = gather_x<GH>(A, c[u]);
         p += 32 * U;
@@ -122,11 +128,12 @@ __device__ __forceinline__ void apply_sell_cta(const ApplyArgs &A, double *red) 
       // U independent (column, value) loads, then U gathers, then the FMAs
       for (; p + 32 * (U - 1) < pend; p += 32 * U) {
         int c[U];
-        double2 v[U], xv[U];
+        typename ValT<F32>::type v[U];
+        double2 xv[U];
 #pragma unroll
         for (int u = 0; u < U; u++) c[u] = ld_stream_i32(A.col + p + 32 * u);
 #pragma unroll
-        for (int u = 0; u < U; u++) v[u] = load_val<F32>(A, p + 32 * u);
+        for (int u = 0; u < U; u++) v[u] = ValT<F32>::load(A, p + 32 * u);
 #pragma unroll
         for (int u = 0; u < U; u++) xv[u] = gather_x<GH>(A, c[u]);
 #pragma unroll
@@ -138,9 +145,35 @@ __device__ __forceinline__ void apply_sell_cta(const ApplyArgs &A, double *red) 
         }
       }
     }
-    for (; p < pend; p += 32) {
+    if (!PF && p < pend) {
+      // remainder: ONE masked batch (same ascending order => same bits) instead of a loop of single, dependent
+      // col -> x loads; masked entries gather x[0], a valid address, and are never used
+      int c[U];
+      typename ValT<F32>::type v[U];
+      double2 xv[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) c[u] = p + 32 * u < pend ? ld_stream_i32(A.col + p + 32 * u) : 0;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (p + 32 * u < pend) v[u] = ValT<F32>::load(A, p + 32 * u);
+        else v[u] = typename ValT<F32>::type();
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) xv[u] = gather_x<GH>(A, c[u]);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (p + 32 * u < pend) {
+          if (FUSE == FUSE_MINRES) {
+            xv[u] = scaled(xv[u], scale);
+          }
+          cfma(acc, v[u], xv[u]);
+        }
+      }
+      p = pend;
+    }
+    for (; p < pend; p += 32) {  // PF variants only
       const int c = ld_stream_i32(A.col + p);
-      const double2 v = load_val<F32>(A, p);
+      const typename ValT<F32>::type v = ValT<F32>::load(A, p);
       double2 xv = gather_x<GH>(A, c);
       if (FUSE == FUSE_MINRES) {
         xv = scaled(xv, scale);
@@ -272,6 +305,13 @@ __global__ void __launch_bounds__(CHUNK, 2) k_apply_csr(const ApplyArgs A) {
   }
 }
 
+// pairs in flight per thread of the fp32-value variant: 12 B per pair instead of 20, so more of them are needed to
+// keep the same bytes in flight (profiles/r2_summary.md section 8)
+constexpr int F32_U = 5;
+// ... and of every fp64 kernel: 5 divides the 15 blocks per row of a Kuhn tet mesh (three full batches, no
+// remainder); other row lengths end in one masked batch (apply_sell_cta).  Round 1 used 4.
+constexpr int DEF_U = 5;
+
 template <int EPI, int FUSE>
 void launch2(Ctx *ctx, const ApplyArgs &A) {
   const unsigned grid = A.chunk_list ? (unsigned)A.n_list : (unsigned)cdiv(A.No, CHUNK);
@@ -281,22 +321,29 @@ void launch2(Ctx *ctx, const ApplyArgs &A) {
   constexpr bool f32_ok = EPI == EPI_DIAG && (FUSE == FUSE_RESID || FUSE == FUSE_CHEB);
   if (A.val32 && !(f32_ok && ctx->layout == NOSH_LAYOUT_SELL32)) NOSH_THROW(NOSH_EINVAL, "internal: fp32 values with this apply variant");
   if (A.val32) {
-    if constexpr (f32_ok) k_apply_sell<EPI, FUSE, 4, 2, false, false, true><<<grid, CHUNK, 0, ctx->stream>>>(A);
+    if constexpr (f32_ok) {
+      switch (ctx->apply_variant) {  // measurement variants, like the fp64 kernels below
+        case 1: k_apply_sell<EPI, FUSE, 4, 2, false, false, true><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+        case 2: k_apply_sell<EPI, FUSE, 5, 2, false, false, true><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+        case 3: k_apply_sell<EPI, FUSE, 8, 2, false, false, true><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+        default: k_apply_sell<EPI, FUSE, F32_U, 2, false, false, true><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      }
+    }
   } else if (ctx->layout == NOSH_LAYOUT_SELL32 && A.xg) {
-    if constexpr (ghost_ok) k_apply_sell<EPI, FUSE, 4, 2, false, true><<<grid, CHUNK, 0, ctx->stream>>>(A);
+    if constexpr (ghost_ok) k_apply_sell<EPI, FUSE, DEF_U, 2, false, true><<<grid, CHUNK, 0, ctx->stream>>>(A);
   } else if (ctx->layout == NOSH_LAYOUT_SELL32) {
     // measurement variants exist for the two kernels of the MINRES loop only (compile time)
     constexpr bool tunable = EPI == EPI_DIAG && (FUSE == FUSE_NONE || FUSE == FUSE_MINRES);
     const int v = tunable ? ctx->apply_variant : 0;
     switch (v) {
-      case 1: k_apply_sell<EPI, FUSE, tunable ? 8 : 4, 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
-      case 2: k_apply_sell<EPI, FUSE, 4, 2, tunable><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
-      case 3: k_apply_sell<EPI, FUSE, tunable ? 8 : 4, tunable ? 1 : 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
-      case 4: k_apply_sell<EPI, FUSE, tunable ? 8 : 4, tunable ? 1 : 2, tunable><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
-      case 5: k_apply_sell<EPI, FUSE, tunable ? 6 : 4, 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
-      case 6: k_apply_sell<EPI, FUSE, tunable ? 2 : 4, 2, tunable><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
-      case 7: k_apply_sell<EPI, FUSE, tunable ? 12 : 4, tunable ? 1 : 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
-      default: k_apply_sell<EPI, FUSE, 4, 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      case 1: k_apply_sell<EPI, FUSE, tunable ? 8 : DEF_U, 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      case 2: k_apply_sell<EPI, FUSE, tunable ? 4 : DEF_U, 2, tunable><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      case 3: k_apply_sell<EPI, FUSE, tunable ? 8 : DEF_U, tunable ? 1 : 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      case 4: k_apply_sell<EPI, FUSE, tunable ? 8 : DEF_U, tunable ? 1 : 2, tunable><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      case 5: k_apply_sell<EPI, FUSE, tunable ? 6 : DEF_U, 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      case 6: k_apply_sell<EPI, FUSE, tunable ? 4 : DEF_U, 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      case 7: k_apply_sell<EPI, FUSE, tunable ? 12 : DEF_U, tunable ? 1 : 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
+      default: k_apply_sell<EPI, FUSE, DEF_U, 2, false><<<grid, CHUNK, 0, ctx->stream>>>(A); break;
     }
   } else
     k_apply_csr<EPI, FUSE, 8><<<grid, CHUNK, 0, ctx->stream>>>(A);

@@ -436,10 +436,10 @@ __device__ __forceinline__ double2 ld_stream2(const double2 *p) {
                : "l"(p));
   return r;
 }
-__device__ __forceinline__ double2 ld_stream_f2(const float2 *p) {
-  float a, b;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "l"(p));
-  return make_double2((double)a, (double)b);
+__device__ __forceinline__ float2 ld_stream_f2(const float2 *p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
 }
 __device__ __forceinline__ int ld_stream_i32(const int *p) {
   int r;

@@ -14,6 +14,9 @@ __device__ __forceinline__ void cfma(double2 &acc, double2 v, double2 x) {
   acc.x = __fma_rn(-v.y, x.y, __fma_rn(v.x, x.x, acc.x));
   acc.y = __fma_rn(v.y, x.x, __fma_rn(v.x, x.y, acc.y));
 }
+// fp32 matrix value (mixed-precision V-cycle): widened at the FMA, so that a thread's values in flight cost half the
+// registers
+__device__ __forceinline__ void cfma(double2 &acc, float2 v, double2 x) { cfma(acc, make_double2((double)v.x, (double)v.y), x); }
 __device__ __forceinline__ double2 scaled(double2 x, double s) {
   return make_double2(__dmul_rn(x.x, s), __dmul_rn(x.y, s));
 }

@@ -273,6 +273,43 @@ __global__ void __launch_bounds__(1024) k_finalize(const FinArgs F) {
   finalize_levels<true>(F, sm);
 }
 
+// One SELL-32 row of the persistent loops: acc += sum_p val[p] * (scale * x[col[p]]) over p = p0, p0 + 32, ... <
+// pend, in ascending p (the order of every other apply kernel => identical bits), PU (column, value) pairs in
+// flight per thread.  The remainder is ONE masked batch, not a loop of single dependent col -> x loads: with the
+// 15 blocks per row of a Kuhn tet mesh and PU = 4 that loop was three serialised round trips per row; PU = 5
+// (15 = 3 x 5) and the masked batch took 4 % off the MINRES iteration and 12 % off the stand-alone apply
+// (profiles/r2_summary.md section 11).  x is read with plain loads: it is written inside the same launch.
+constexpr int PERSIST_U = 5;
+template <int PU>
+__device__ __forceinline__ void sell_row_scaled(double2 &acc, const int32_t *col, const double2 *val, const double2 *x,
+                                                int p, const int pend, const double scale) {
+  for (; p + 32 * (PU - 1) < pend; p += 32 * PU) {
+    int c[PU];
+    double2 v[PU], xv[PU];
+#pragma unroll
+    for (int u = 0; u < PU; u++) c[u] = ld_stream_i32(col + p + 32 * u);
+#pragma unroll
+    for (int u = 0; u < PU; u++) v[u] = ld_stream2(val + p + 32 * u);
+#pragma unroll
+    for (int u = 0; u < PU; u++) xv[u] = x[c[u]];
+#pragma unroll
+    for (int u = 0; u < PU; u++) cfma(acc, v[u], scaled(xv[u], scale));
+  }
+  if (p < pend) {
+    int c[PU];
+    double2 v[PU], xv[PU];
+#pragma unroll
+    for (int u = 0; u < PU; u++) c[u] = p + 32 * u < pend ? ld_stream_i32(col + p + 32 * u) : 0;
+#pragma unroll
+    for (int u = 0; u < PU; u++) v[u] = p + 32 * u < pend ? ld_stream2(val + p + 32 * u) : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int u = 0; u < PU; u++) xv[u] = x[c[u]];  // masked entries read x[0]: a valid address, never used
+#pragma unroll
+    for (int u = 0; u < PU; u++)
+      if (p + 32 * u < pend) cfma(acc, v[u], scaled(xv[u], scale));
+  }
+}
+
 // -------------------------------------------------------------------------------------------------------
 // Persistent MINRES (one GPU, no preconditioner, SELL-32): the whole iteration loop in ONE cooperative
 // launch.  CTA c owns the chunks c, c + grid, ... in every phase, so the element-wise phases (B, C) need no
@@ -324,7 +361,8 @@ __device__ __forceinline__ double persist_level3(const PersistArgs &P, double *s
   return t;
 }
 
-template <int EPI>
+// PU: (column, value) pairs in flight per thread in phase A (same ascending summation order for every PU)
+template <int EPI, int PU>
 __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent(const PersistArgs P) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
@@ -357,23 +395,7 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent(const PersistArg
         if (slice < P.A.nslices) {
           int p = __ldg(P.A.slice_off + slice) + lane;
           const int pend = __ldg(P.A.slice_off + slice + 1);
-          for (; p + 96 < pend; p += 128) {
-            int c[4];
-            double2 v[4], xv[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) c[u] = ld_stream_i32(P.A.col + p + 32 * u);
-#pragma unroll
-            for (int u = 0; u < 4; u++) v[u] = ld_stream2(P.A.val + p + 32 * u);
-#pragma unroll
-            for (int u = 0; u < 4; u++) xv[u] = rcur[c[u]];  // written in this launch: coherent loads
-#pragma unroll
-            for (int u = 0; u < 4; u++) cfma(acc, v[u], scaled(xv[u], scale));
-          }
-          for (; p < pend; p += 32) {
-            const int c = ld_stream_i32(P.A.col + p);
-            const double2 v = ld_stream2(P.A.val + p);
-            cfma(acc, v, scaled(rcur[c], scale));
-          }
+          sell_row_scaled<PU>(acc, P.A.col, P.A.val, rcur, p, pend, scale);
         }
         double contrib = 0.0;
         if (row < P.A.No) {
@@ -656,24 +678,8 @@ __global__ void __launch_bounds__(CHUNK, 2) k_minres_persistent_mgpu(const Persi
         if (slice < P.A.nslices) {
           int p = __ldg(P.A.slice_off + slice) + lane;
           const int pend = __ldg(P.A.slice_off + slice + 1);
-          for (; p + 96 < pend; p += 128) {
-            int c[4];
-            double2 v[4], xv[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) c[u] = ld_stream_i32(P.A.col + p + 32 * u);
-#pragma unroll
-            for (int u = 0; u < 4; u++) v[u] = ld_stream2(P.A.val + p + 32 * u);
-#pragma unroll
-            for (int u = 0; u < 4; u++) xv[u] = rcur[c[u]];  // owned: other SMs wrote them, ghosts: the peers did --
-                                                             // both ordered by the exchange + grid sync (acquire)
-#pragma unroll
-            for (int u = 0; u < 4; u++) cfma(acc, v[u], scaled(xv[u], scale));
-          }
-          for (; p < pend; p += 32) {
-            const int c = ld_stream_i32(P.A.col + p);
-            const double2 v = ld_stream2(P.A.val + p);
-            cfma(acc, v, scaled(rcur[c], scale));
-          }
+          // owned entries: other SMs wrote them; ghosts: the peers did -- both ordered by the exchange + grid sync
+          sell_row_scaled<PERSIST_U>(acc, P.A.col, P.A.val, rcur, p, pend, scale);
         }
         double contrib = 0.0;
         if (row < P.A.No) {
@@ -1099,11 +1105,13 @@ void minres_dev(Ctx *ctx, int op, int prec, const double2 *b, double bscale, dou
     PA.n_groups = ctx->n_groups_global;
     PA.cpg = ctx->chunks_per_group;
     PA.maxit = maxit;
-    const void *fn = epi == EPI_DIAG ? (const void *)k_minres_persistent<EPI_DIAG> : (const void *)k_minres_persistent<EPI_NONE>;
+    const bool u4 = ctx->apply_variant == 6;  // measurement variant (profiles/apply_variants.py): the round-1 batch size
+    const void *fn = epi == EPI_DIAG ? (u4 ? (const void *)k_minres_persistent<EPI_DIAG, 4> : (const void *)k_minres_persistent<EPI_DIAG, PERSIST_U>)
+                                     : (u4 ? (const void *)k_minres_persistent<EPI_NONE, 4> : (const void *)k_minres_persistent<EPI_NONE, PERSIST_U>);
     if (ctx->persist_grid == 0) {
       int per_sm = 0, sms = 0, coop = 0;
       CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minres_persistent<EPI_DIAG>, CHUNK, 0));
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_minres_persistent<EPI_DIAG, PERSIST_U>, CHUNK, 0));
       CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
       ctx->persist_grid = coop ? per_sm * sms : -1;
     }

@@ -15,8 +15,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=200)
 ap.add_argument("--reps", type=int, default=50)
 a = ap.parse_args()
-DESC = {0: "U=4, 64 regs, 2 CTAs/SM (baseline)", 1: "U=8, 64 regs", 2: "U=4 + column prefetch", 3: "U=8, 1 CTA/SM",
-        4: "U=8, 1 CTA/SM + prefetch", 5: "U=6, 64 regs", 6: "U=2 + prefetch", 7: "U=12, 1 CTA/SM"}
+DESC = {0: "U=5, 64 regs, 2 CTAs/SM (default)", 1: "U=8, 64 regs", 2: "U=4 + column prefetch", 3: "U=8, 1 CTA/SM",
+        4: "U=8, 1 CTA/SM + prefetch", 5: "U=6, 64 regs", 6: "U=4, 64 regs (the round-1 default)", 7: "U=12, 1 CTA/SM"}
 ctx = nosh_b200.Context()
 mi = ctx.mesh_tetgrid(a.n)
 ctx.set_thickness(None, 1.0)
@@ -54,14 +54,19 @@ for v in range(8):
                 "minres_ms_per_iteration": ms_minres, "bit_identical_to_variant_0": same})
     print(out[-1], file=sys.stderr)
 # the MINRES loop as one cooperative launch (krylov.cu k_minres_persistent) vs five launches per iteration
-ctx.set_tuning("apply_variant", 0)
 loop = {}
-for mode in (0, 1, 0, 1):
+xs = {}
+for mode, var in ((0, 0), (1, 0), (1, 6), (0, 0), (1, 0), (1, 6)):
+    ctx.set_tuning("apply_variant", var)
     ctx.set_tuning("persistent_minres", mode)
     ctx.minres(b, x, tol=0.0, maxit=50)
     ctx.timer_start()
     ctx.minres(b, x, tol=0.0, maxit=400)
-    loop.setdefault("persistent" if mode else "multi_launch", []).append(ctx.timer_stop() / 400)
+    key = ("persistent" if mode else "multi_launch") + ("_U4" if var == 6 else "")
+    loop.setdefault(key, []).append(ctx.timer_stop() / 400)
+    xs[key] = x.clone()
     print(mode, loop, file=sys.stderr)
+loop["bits_equal"] = bool(all(torch.equal(v, xs["multi_launch"]) for v in xs.values()))
+ctx.set_tuning("apply_variant", 0)
 print(json.dumps({"n": a.n, "vertices": No, "bytes_per_apply": bytes_apply, "variants": out,
                   "minres_ms_per_iteration": loop}))

@@ -23,6 +23,8 @@ ap.add_argument("--precond", default="none", choices=["none", "amg"])
 ap.add_argument("--persistent", type=int, default=0,
                 help="0: the multi-launch MINRES loop (one launch per phase: readable launch lists); 1: the default "
                      "one-launch cooperative kernel")
+ap.add_argument("--amg-mixed", type=int, default=0, help="1: the mixed-precision cycle (tuning key amg_mixed)")
+ap.add_argument("--apply-variant", type=int, default=0)
 ap.add_argument("--amg-degree", type=int, default=1)
 ap.add_argument("--amg-coarse-degree", type=int, default=2)
 a = ap.parse_args()
@@ -42,8 +44,10 @@ par = {"g": 1.0, "mu": 1.0, "theta": 0.0}
 
 
 ctx.set_tuning("persistent_minres", a.persistent)
+ctx.set_tuning("apply_variant", a.apply_variant)
 if a.precond == "amg":
     ctx.amg_set_options(degree=a.amg_degree, coarse_degree=a.amg_coarse_degree)
+    ctx.set_tuning("amg_mixed", a.amg_mixed)
 
 
 def step(k):
