@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BASE_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
              "vs_baseline", "dtype", "data", "config", "e2e"]
@@ -75,8 +77,9 @@ def test_rank_other_than_zero_of_the_reference_arm_does_no_work():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
-def test_committed_b200_line_has_every_contract_key():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_default_1gpu_v3.json")))
+@pytest.mark.parametrize("name", ["r2_bench_default_1gpu_v3.json", "r2_bench_default_1gpu_final.json"])
+def test_committed_b200_line_has_every_contract_key(name):
+    d = json.load(open(os.path.join(ROOT, "profiles", name)))
     for k in BASE_KEYS + ["roofline", "cpu_baseline", "gpu_launches", "clocks", "parity"]:
         assert k in d, k
     # the parity gate ran before anything was timed: entry-wise KEO / F / J x / dF/dmu at 1.0M vertices <= 1e-12
@@ -90,7 +93,8 @@ def test_committed_b200_line_has_every_contract_key():
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "ms_per_launch_batches"):
         assert k in rf, k
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
-    assert 0.7 <= rf["frac"] <= 1.1                      # BASELINE.json's target is >= 70 % of the HBM roofline
+    assert 0.7 <= rf["frac"] <= 1.2                      # BASELINE.json's target is >= 70 % of the HBM roofline; the
+                                                         # measured peak is a COPY's: a read-mostly kernel may pass it
     for k in ("value", "unit", "cores", "kind", "sample"):
         assert k in d["cpu_baseline"], k
     for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
