@@ -115,3 +115,48 @@ def test_arclength_restatement_follows_the_branch_through_a_fold():
     # natural continuation to mu = 0.1 lands on the same branch: same norm as the arc-length curve there
     xn, nrecs = P.continuation(1.0, "mu", 0.0, 0.05, 2, psi)
     assert np.interp(nrecs[-1]["param"], mus[:k + 1], norms[:k + 1]) == pytest.approx(nrecs[-1]["norm"], rel=5e-3)  # linear interpolation of a curved branch
+
+
+def vcycle_matrix(H, n2):
+    return np.column_stack([H.vcycle(e) for e in np.eye(n2)])
+
+
+def test_vcycle_is_a_convergent_mesh_independent_preconditioner():
+    """Multigrid theory instead of another implementation: with a symmetric V(1,1) cycle B on an SPD matrix A the
+    eigenvalues of B A lie in (0, 1] (the stationary iteration x += B (b - A x) converges monotonically in the energy
+    norm), and for smoothed aggregation their spread does not grow with the mesh.  Dense eigenvalues, two meshes."""
+    kappa = {}
+    for n in (7, 11):
+        P, J, Pm, x = regularised_problem(n, state="random")
+        H = amg.Hierarchy(Pm, coarse_max=40)
+        assert len(H.levels) >= 2
+        n2 = Pm.shape[0]
+        B = vcycle_matrix(H, n2)
+        assert np.abs(B - B.T).max() <= 1e-12 * np.abs(B).max()
+        A = Pm.toarray()
+        L = np.linalg.cholesky(A)                        # B A is similar to the symmetric L^T B L
+        ev = np.linalg.eigvalsh(L.T @ (0.5 * (B + B.T)) @ L)
+        assert ev.min() > 0.0 and ev.max() <= 1.0 + 1e-10
+        kappa[n] = ev.max() / ev.min()
+        assert 1.0 - ev.min() < 0.9                      # energy-norm contraction number of the cycle
+    assert kappa[11] <= 1.5 * kappa[7] and kappa[11] < 12.0
+
+
+def test_coarse_grid_correction_is_the_energy_projection():
+    """P (P^T A P)^-1 P^T A is the A-orthogonal projection onto range(P): idempotent, A-self-adjoint, and it leaves
+    range(P) alone -- which holds iff the coarse operator really is the Galerkin product of the stored P."""
+    P_, J, Pm, x = regularised_problem(7, state="random")
+    H = amg.Hierarchy(Pm, coarse_max=40)
+    L0, L1 = H.levels[0], H.levels[1]
+    A, Pr, Ac = L0.A.toarray(), L0.P.toarray(), L1.A.toarray()
+    assert np.abs(Ac - Pr.T @ A @ Pr).max() <= 1e-12 * np.abs(Ac).max()
+    Pi = Pr @ np.linalg.solve(Ac, Pr.T @ A)
+    assert np.abs(Pi @ Pi - Pi).max() <= 1e-9
+    assert np.abs(A @ Pi - (A @ Pi).T).max() <= 1e-9 * np.abs(A).max()
+    assert np.abs(Pi @ Pr - Pr).max() <= 1e-9
+    # the tentative prolongator has orthonormal columns, one aggregate per fine node; smoothing keeps the pattern
+    # of A P0 and damps with 4/3 / lambda_max(D^-1 A)
+    assert L0.agg.min() == 0 and np.unique(L0.agg).size == L1.n
+    lam_true = np.linalg.eigvals(np.diag(L0.dinv) @ A).real.max()
+    assert 0.7 * lam_true <= L0.lam <= lam_true * (1 + 1e-12)       # power iteration: a lower estimate
+    assert L0.omega == pytest.approx(amg.SA_DAMPING / L0.lam)
