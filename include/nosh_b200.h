@@ -460,10 +460,13 @@ NOSH_API nosh_status nosh_continuation_arclength(nosh_ctx *ctx, int np, const ch
  * nosh::read (src/mesh_reader.cpp:19-162) + the vertex tags the drivers take from the file --
  * mesh::get_complex_vector("psi"), get_vector("V"), get_multi_vector("A") (src/mesh.cpp:249-446) -- and
  * mesh::write for the outNNNN state dumps (src/mesh.cpp:249-263, src/continuation_data_saver.hpp:24-50).
- * The reference goes through MOAB (.h5m / Exodus); MOAB, HDF5 and netCDF are not available here, so the
- * supported format is the legacy VTK unstructured grid, ASCII or BINARY (what `meshio-convert in.e out.vtk`
- * writes; MOAB reads it too).  Triangles / tetrahedra only, the highest-dimensional kind present.
- * .h5m / .e / .exo paths return NOSH_EUNSUPPORTED.  Errors: nosh_meshfile_last_error(). */
+ * The reference goes through MOAB (.h5m / Exodus); MOAB, HDF5 and netCDF are not available here.  Read: the legacy
+ * VTK unstructured grid, ASCII or BINARY (what `meshio-convert in.e out.vtk` writes; MOAB reads it too), and
+ * Exodus II (.e .exo .ex2 .g .gen) in the netCDF CLASSIC container (CDF-1 / CDF-2 / CDF-5; own reader of the
+ * container) -- nodal variables of the last time step, X_R / X_Z joined into the complex tag X, X_X / X_Y / X_Z
+ * into the vector tag X.  Written: legacy VTK.  Triangles / tetrahedra only, the highest-dimensional kind present.
+ * .h5m and Exodus files in the netCDF-4 (HDF5) container return NOSH_EUNSUPPORTED.
+ * Errors: nosh_meshfile_last_error(). */
 typedef struct nosh_meshfile nosh_meshfile;
 NOSH_API const char *nosh_meshfile_last_error(void);
 NOSH_API nosh_status nosh_meshfile_read(const char *path, nosh_meshfile **out);

@@ -3,10 +3,15 @@
 // The reference reads .h5m / Exodus files through MOAB (src/mesh_reader.cpp:19-162), takes the vertex
 // tags "psi" (2 doubles), "A" (3 doubles), "V" from them (src/mesh.cpp:249-446: get_vector,
 // get_complex_vector, get_multi_vector) and dumps states as outNNNN.h5m (mesh::write :249-263,
-// src/continuation_data_saver.hpp:24-50).  MOAB, HDF5 and netCDF are not available offline, so the format
-// supported here is the legacy VTK unstructured grid (ASCII or BINARY) -- what `meshio-convert in.e out.vtk`
-// produces from the reference's meshes, and a format MOAB itself reads and writes.  Cells other than
-// triangles (VTK type 5) / tetrahedra (type 10) are ignored, like the reference's tri/tet dispatch
+// src/continuation_data_saver.hpp:24-50).  MOAB, HDF5 and netCDF are not available offline, so the formats
+// supported here are
+//  * the legacy VTK unstructured grid (ASCII or BINARY), read and written -- what `meshio-convert in.e out.vtk`
+//    produces from the reference's meshes, and a format MOAB itself reads and writes;
+//  * Exodus II in the netCDF CLASSIC container (CDF-1, 64-bit-offset CDF-2, CDF-5), read only, with a reader of
+//    that container written here (exodus.inc) -- the format of the reference's own test meshes
+//    (test/data/*.e.md5).  Exodus files in the netCDF-4 container are HDF5 files and stay NOSH_EUNSUPPORTED,
+//    like .h5m.
+// Cells other than triangles / tetrahedra are ignored, like the reference's tri/tet dispatch
 // (src/mesh_reader.cpp:127-160).
 //
 // nosh_morton_order: the contiguous vertex ranges of nosh_partition_range only make a good partition if
@@ -15,6 +20,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -111,6 +117,8 @@ bool ends_with(const std::string &s, const char *suf) {
 
 }  // namespace
 
+#include "exodus.inc"
+
 extern "C" {
 
 const char *nosh_meshfile_last_error(void) { return g_err.c_str(); }
@@ -119,10 +127,13 @@ static nosh_status meshfile_read_impl(const char *path, nosh_meshfile **out) {
   if (!path || !out) return fail(NOSH_EINVAL, "NULL argument");
   *out = nullptr;
   const std::string p(path);
-  if (ends_with(p, ".h5m") || ends_with(p, ".e") || ends_with(p, ".exo") || ends_with(p, ".h5"))
+  if (ends_with(p, ".h5m") || ends_with(p, ".h5"))
     return fail(NOSH_EUNSUPPORTED,
-                "MOAB/HDF5/Exodus files need libraries that are not available here; convert with "
-                "`meshio-convert in out.vtk` (legacy VTK)");
+                "MOAB/HDF5 files need libraries that are not available here; convert with "
+                "`meshio-convert in out.vtk` (legacy VTK) or to Exodus II in the netCDF classic container");
+  if (ends_with(p, ".e") || ends_with(p, ".exo") || ends_with(p, ".ex2") || ends_with(p, ".exii") || ends_with(p, ".g") ||
+      ends_with(p, ".gen"))
+    return exodus_read_impl(p, out);
   Reader R;
   R.f.open(path, std::ios::binary);
   if (!R.f) return fail(NOSH_EINVAL, "cannot open " + p);
