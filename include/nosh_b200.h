@@ -464,7 +464,9 @@ NOSH_API nosh_status nosh_continuation_arclength(nosh_ctx *ctx, int np, const ch
  * VTK unstructured grid, ASCII or BINARY (what `meshio-convert in.e out.vtk` writes; MOAB reads it too), and
  * Exodus II (.e .exo .ex2 .g .gen) in the netCDF CLASSIC container (CDF-1 / CDF-2 / CDF-5; own reader of the
  * container) -- nodal variables of the last time step, X_R / X_Z joined into the complex tag X, X_X / X_Y / X_Z
- * into the vector tag X.  Written: legacy VTK.  Triangles / tetrahedra only, the highest-dimensional kind present.
+ * into the vector tag X -- and gmsh MSH (.msh, ASCII, formats 2.x and 4.1: nodes, 3-node triangles, 4-node
+ * tetrahedra, $NodeData views).  Written: legacy VTK.  Triangles / tetrahedra only, the highest-dimensional kind
+ * present; vertices no kept cell uses are dropped (MSH).
  * .h5m and Exodus files in the netCDF-4 (HDF5) container return NOSH_EUNSUPPORTED.
  * Errors: nosh_meshfile_last_error(). */
 typedef struct nosh_meshfile nosh_meshfile;

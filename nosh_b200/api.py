@@ -65,8 +65,8 @@ def _io_check(rc):
 
 def read_mesh(path):
     """nosh::read + the vertex tags (host only): returns (coords (N,3), cells (C,dim+1) int32, fields dict).
-    Legacy VTK unstructured grids (ASCII or BINARY) and Exodus II files in the netCDF classic container; complex
-    states come back as (N,2) arrays."""
+    Legacy VTK unstructured grids (ASCII or BINARY), Exodus II files in the netCDF classic container and gmsh MSH
+    files (ASCII 2.x / 4.1); complex states come back as (N,2) arrays."""
     L = _lib.lib()
     h = C.c_void_p()
     _io_check(L.nosh_meshfile_read(str(path).encode(), C.byref(h)))

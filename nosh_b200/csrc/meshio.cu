@@ -10,7 +10,9 @@
 //  * Exodus II in the netCDF CLASSIC container (CDF-1, 64-bit-offset CDF-2, CDF-5), read only, with a reader of
 //    that container written here (exodus.inc) -- the format of the reference's own test meshes
 //    (test/data/*.e.md5).  Exodus files in the netCDF-4 container are HDF5 files and stay NOSH_EUNSUPPORTED,
-//    like .h5m.
+//    like .h5m;
+//  * gmsh MSH, ASCII, formats 2.x and 4.1, read only (msh.inc) -- what `gmsh -3 examples/meshes/pacman.geo`
+//    writes, i.e. the reference's meshes before any conversion.
 // Cells other than triangles / tetrahedra are ignored, like the reference's tri/tet dispatch
 // (src/mesh_reader.cpp:127-160).
 //
@@ -118,6 +120,7 @@ bool ends_with(const std::string &s, const char *suf) {
 }  // namespace
 
 #include "exodus.inc"
+#include "msh.inc"
 
 extern "C" {
 
@@ -134,6 +137,7 @@ static nosh_status meshfile_read_impl(const char *path, nosh_meshfile **out) {
   if (ends_with(p, ".e") || ends_with(p, ".exo") || ends_with(p, ".ex2") || ends_with(p, ".exii") || ends_with(p, ".g") ||
       ends_with(p, ".gen"))
     return exodus_read_impl(p, out);
+  if (ends_with(p, ".msh")) return msh_read_impl(p, out);
   Reader R;
   R.f.open(path, std::ios::binary);
   if (!R.f) return fail(NOSH_EINVAL, "cannot open " + p);
