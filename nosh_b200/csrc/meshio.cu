@@ -56,6 +56,7 @@ T byteswap(T v) {
 struct Reader {
   std::ifstream f;
   bool binary = false;
+  uint64_t fsize = 0;  // counts in the file are bounded by it before anything is sized with them
   std::string token() {
     std::string t;
     f >> t;
@@ -76,6 +77,7 @@ struct Reader {
   // n values of VTK type `type` converted to T
   template <typename T>
   bool read_array(const std::string &type, size_t n, std::vector<T> &out) {
+    if (n > fsize) return false;  // a value takes at least one byte
     out.resize(n);
     const std::string ty = upper(type);
     if (!binary) {
@@ -141,6 +143,9 @@ static nosh_status meshfile_read_impl(const char *path, nosh_meshfile **out) {
   Reader R;
   R.f.open(path, std::ios::binary);
   if (!R.f) return fail(NOSH_EINVAL, "cannot open " + p);
+  R.f.seekg(0, std::ios::end);
+  R.fsize = (uint64_t)R.f.tellg();
+  R.f.seekg(0);
   std::string line;
   std::getline(R.f, line);
   if (line.find("# vtk DataFile") != 0) return fail(NOSH_EINVAL, p + ": not a legacy VTK file");
